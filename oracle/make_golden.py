@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference module.
+
+Run in the build container only (needs /root/reference, CPU):
+
+    python oracle/make_golden.py [--only NAME]
+
+For each fixture this script
+  1. draws seeded synthetic inputs and re-draws "fragile" Gaussians - those
+     whose integer rectangle, visibility bit or depth rank could flip under a
+     few-ulp change of the projected floats - so that the integer pins are a
+     property of the input and not of one BLAS build (SURVEY.md section 8c:
+     "fixtures must be tie-free"); fixtures tagged ``ties`` keep exact depth
+     ties on purpose (identity view, so depth = -z is exact everywhere);
+  2. runs the reference renderer forward + backward with ``torch.argsort``
+     forced to ``stable=True`` (the only patch; DR:527 is otherwise
+     implementation-defined on ties);
+  3. derives the integer pins (visible, rect, stable depth order) from the
+     REFERENCE's own intermediates (compute_2d_covariance / _compute_radius);
+  4. cross-checks the oracle restatement against all of it and refuses to write
+     the fixture if the oracle disagrees;
+  5. writes inputs, outputs, gradients and pins to tests/golden/NAME.npz.
+
+Phase-blending gradients cannot come from the reference (it raises inside
+autograd, SURVEY.md note 3); they come from the oracle's ``.clone()``
+restatement and the fixture says so (``grad_source = 'oracle_clone'``).
+"""
+
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/scripts")
+
+from oracle import fresnel_oracle as fo  # noqa: E402
+
+_orig_argsort = torch.argsort
+
+
+def _stable_argsort(x, *a, **k):
+    k["stable"] = True
+    return _orig_argsort(x, *a, **k)
+
+
+torch.argsort = _stable_argsort
+import models.differentiable_renderer as dr  # noqa: E402  (the reference)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_camera(cam: fo.Camera) -> "dr.Camera":
+    c = dr.Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, cam.near, cam.far)
+    c.set_view(cam.view_matrix.clone())
+    return c
+
+
+def cam_vec(cam: fo.Camera) -> np.ndarray:
+    v = cam.view_matrix.to(torch.float32).numpy()[:3, :].reshape(-1)
+    return np.concatenate([v, np.array([cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height,
+                                        cam.near, cam.far])]).astype(np.float64)
+
+
+def fragile_mask(inp, cam, W, H, max_radius, allow_ties) -> np.ndarray:
+    """Gaussians whose integer pins sit within a safety margin of flipping."""
+    pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, max_radius)
+    u, v, r = (pn[k].astype(np.float64) for k in ("u", "v", "radius"))
+    d = pn["depth"].astype(np.float64)
+    eps = 2e-3
+    frag = np.zeros(u.shape[0], bool)
+    for e in (u - r, u + r, v - r, v + r):
+        frag |= np.abs(e - np.round(e)) < eps
+    frag |= (np.abs(d - cam.near) < 1e-4) | (np.abs(d - cam.far) < 1e-2)
+    frag |= ~np.isfinite(u) | ~np.isfinite(v) | ~np.isfinite(r)
+    if not allow_ties:
+        bits = pn["depth_bits"].astype(np.int64)
+        o = np.argsort(bits, kind="stable")
+        gap = np.diff(bits[o])
+        close = np.zeros_like(frag)
+        near = np.nonzero(gap < 16)[0]
+        close[o[near]] = True
+        close[o[near + 1]] = True
+        frag |= close
+    return frag
+
+
+def settle(inp, cam, W, H, max_radius, seed, redraw, allow_ties=False):
+    """Re-draw fragile Gaussians until none is left."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    for it in range(50):
+        frag = fragile_mask(inp, cam, W, H, max_radius, allow_ties)
+        n = int(frag.sum())
+        if n == 0:
+            return inp
+        idx = torch.from_numpy(np.nonzero(frag)[0])
+        redraw(inp, idx, g)
+    raise RuntimeError("could not settle fixture")
+
+
+def upstream(H, W, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(3, H, W, generator=g) * 2 - 1, torch.rand(H, W, generator=g) * 2 - 1)
+
+
+def leafs(inp, names):
+    return {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in inp.items()}
+
+
+GRAD_NAMES = ("positions", "scales", "rotations", "colors", "opacities")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-3))
+
+
+def run_tile(name, inp, cam, W, H, bg=(0.0, 0.0, 0.0), max_radius=64, phase=False, amp=0.25,
+             note=""):
+    t0 = time.time()
+    gi, gd = upstream(H, W)
+    rc = ref_camera(cam)
+    ren = dr.TileBasedRenderer(W, H, background=bg, max_radius=max_radius,
+                               use_phase_blending=phase, phase_amplitude=amp)
+    # reference forward (+ backward when it can)
+    L = leafs(inp, GRAD_NAMES + (("phases",) if phase else ()))
+    ph = L["phases"] if phase else None
+    if phase:
+        with torch.no_grad():
+            img_r, dep_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"],
+                               L["opacities"], rc, return_depth=True, phases=ph)
+        grads_r = None
+    else:
+        img_r, dep_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"],
+                           L["opacities"], rc, return_depth=True, phases=None)
+        ((img_r * gi).sum() + (dep_r * gd).sum()).backward()
+        grads_r = {k: (L[k].grad if L[k].grad is not None else torch.zeros_like(L[k])).numpy()
+                   for k in GRAD_NAMES}
+    # reference-derived pins
+    with torch.no_grad():
+        cov, m2, dep = dr.compute_2d_covariance(inp["positions"], inp["scales"], inp["rotations"], rc)
+        rad = ren._compute_radius(cov)
+        vis = fo.visibility(m2[:, 0], m2[:, 1], dep, rad, cam, W, H).numpy()
+        rect = fo.rects(m2[:, 0], m2[:, 1], rad, W, H).astype(np.int32)
+        order = torch.argsort(dep).numpy().astype(np.int32)
+    # oracle
+    Lo = leafs(inp, GRAD_NAMES + (("phases",) if phase else ()))
+    img_o, dep_o, alpha_o = fo.render_tile_based(
+        Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"], Lo["opacities"], cam, W, H,
+        background=bg, max_radius=max_radius, use_phase_blending=phase, phase_amplitude=amp,
+        phases=Lo["phases"] if phase else None)
+    ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
+    grads_o = {k: (Lo[k].grad if Lo[k].grad is not None else torch.zeros_like(Lo[k])).numpy()
+               for k in GRAD_NAMES + (("phases",) if phase else ())}
+    pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, max_radius)
+
+    # cross-checks: oracle vs reference
+    e_img, e_dep = rel(img_o.detach(), img_r.detach()), rel(dep_o.detach(), dep_r.detach())
+    assert e_img < 1e-5 and e_dep < 1e-5, (name, e_img, e_dep)
+    assert np.array_equal(pn["visible"], vis), name
+    vi = np.nonzero(vis)[0]
+    assert np.array_equal(pn["rect"][vi], rect[vi]), name
+    assert np.array_equal(pn["order"], order), name
+    worst = 0.0
+    if grads_r is not None:
+        for k in GRAD_NAMES:
+            e = rel(grads_o[k], grads_r[k])
+            assert e < 1e-4, (name, k, e)
+            worst = max(worst, e)
+        grads, src = grads_r, "reference"
+    else:
+        grads, src = grads_o, "oracle_clone"
+
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=max_radius,
+               phase_blending=int(phase), phase_amplitude=amp,
+               image=img_r.detach().numpy(), depth=dep_r.detach().numpy(),
+               alpha=alpha_o.detach().numpy(),
+               gimage=gi.numpy(), gdepth=gd.numpy(),
+               visible=vis, rect=rect, order=order, grad_source=src, note=note)
+    for k in GRAD_NAMES + ("phases",):
+        out["in_" + k] = inp[k].numpy()
+    for k, g in grads.items():
+        out["grad_" + k] = g
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: N={inp['positions'].shape[0]} vis={int(vis.sum())} M={pn['keys'].shape[0]} "
+          f"oracle-vs-ref img {e_img:.2e} depth {e_dep:.2e} grads {worst:.2e} [{src}] "
+          f"{time.time() - t0:.1f}s")
+
+
+def run_wave(name, inp, cam, W, H, bg, per_channel, note=""):
+    gi, gd = upstream(H, W)
+    rc = ref_camera(cam)
+    names = GRAD_NAMES + ("phases",)
+    ren = dr.WaveFieldRenderer(W, H, background=bg)
+    L = leafs(inp, names)
+    img_r, dep_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"],
+                       rc, return_depth=True, phases=L["phases"])
+    ((img_r * gi).sum() + (dep_r * gd).sum()).backward()
+    Lo = leafs(inp, names)
+    img_o, dep_o = fo.render_wave(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                                  Lo["opacities"], cam, W, H, Lo["phases"], background=bg)
+    ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
+    assert rel(img_o.detach(), img_r.detach()) < 2e-6 and rel(dep_o.detach(), dep_r.detach()) < 2e-5
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=64,
+               image=img_r.detach().numpy(), depth=dep_r.detach().numpy(),
+               gimage=gi.numpy(), gdepth=gd.numpy(), grad_source="reference", note=note)
+    for k in names:
+        out["in_" + k] = inp[k].numpy()
+        gr, go = L[k].grad.numpy(), Lo[k].grad.numpy()
+        assert rel(go, gr) < 5e-5, (name, k, rel(go, gr))
+        out["grad_" + k] = gr
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: wave ok, img max {float(img_r.max()):.3f}")
+
+
+def run_asm(name, inp, cam, W, H, bg, wl, depth_range, note=""):
+    gi, _ = upstream(H, W)
+    rc = ref_camera(cam)
+    names = GRAD_NAMES + ("phases",)
+    ren = dr.ASMWaveFieldRenderer(W, H, background=bg, depth_range=depth_range)
+    L = leafs(inp, names)
+    img_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], rc,
+                phases=L["phases"], wavelengths_rgb=wl)
+    (img_r * gi).sum().backward()
+    Lo = leafs(inp, names)
+    img_o, _ = fo.render_asm(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                             Lo["opacities"], cam, W, H, Lo["phases"], wl, background=bg,
+                             depth_range=depth_range)
+    (img_o * gi).sum().backward()
+    assert rel(img_o.detach(), img_r.detach()) < 5e-6
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=64,
+               wavelengths=wl.numpy(), depth_range=np.array(depth_range),
+               image=img_r.detach().numpy(), gimage=gi.numpy(), grad_source="reference", note=note)
+    for k in names:
+        out["in_" + k] = inp[k].numpy()
+        gr, go = L[k].grad.numpy(), Lo[k].grad.numpy()
+        assert rel(go, gr) < 1e-4, (name, k, rel(go, gr))
+        out["grad_" + k] = gr
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: asm ok, img max {float(img_r.max()):.3f}")
+
+
+# ---------------------------------------------------------------- fixtures
+def redraw_std(inp, idx, g):
+    n = idx.numel()
+    p = torch.randn(n, 3, generator=g) * 0.5
+    p[:, 2] -= 2.0
+    inp["positions"][idx] = p
+
+
+def fx_c1():
+    """Config 1 (BASELINE.json configs[0]): 16,384 Gaussians, 256x256, one view."""
+    W = H = 256
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(16384, seed=0)
+    inp = settle(inp, cam, W, H, 64, 0, redraw_std)
+    run_tile("c1_tile_16k_256", inp, cam, W, H, note="config 1, identity view, black background")
+
+
+def fx_rot():
+    """Rotated look-at camera, non-black background, non-square non-multiple-of-16 image."""
+    W, H = 144, 120
+    cam = fo.camera_from_pose(math.radians(20.0), math.radians(35.0), 128)
+    cam.width, cam.height, cam.cx, cam.cy = W, H, W / 2, H / 2
+    inp = fo.synthetic_cloud(2048, seed=3, s_lo=0.01, s_hi=0.06)
+    inp["positions"][:, 2] += 2.0            # cloud around the origin; camera orbits at distance 2
+
+    def redraw(inp, idx, g):
+        inp["positions"][idx] = torch.randn(idx.numel(), 3, generator=g) * 0.5
+
+    inp = settle(inp, cam, W, H, 64, 3, redraw)
+    run_tile("tile_rotcam_2k_144x120", inp, cam, W, H, bg=(0.2, 0.3, 0.4),
+             note="create_camera_from_pose(el=20deg, az=35deg), W=144 H=120, coloured background")
+
+
+def fx_edge():
+    """Near-plane / behind-camera / border / radius-cap / depth-tie / saturation edge cases."""
+    W, H = 96, 80
+    cam = fo.default_camera(W, H)
+    n = 1024
+    g = torch.Generator().manual_seed(7)
+    inp = fo.synthetic_cloud(n, seed=7, s_lo=0.01, s_hi=0.08)
+    pos = inp["positions"]
+    pos[:, :2] *= 2.0                                   # many centres outside the image
+    pos[:128, 2] = torch.rand(128, generator=g) * 0.3 - 0.15     # around and behind the camera plane
+    pos[128:256, 2] = -(torch.rand(128, generator=g) * 0.2 + 0.05)   # very close: radius cap
+    inp["scales"][256:320] *= 8.0                       # big splats: 64-px cap, whole-image rects
+    zq = torch.round(pos[320:704, 2] * 8) / 8           # exact depth ties (Fresnel-zone style)
+    pos[320:704, 2] = zq
+    inp["opacities"][704:832] = 1.5                     # alpha clamp at 0.99 active
+    inp["opacities"][832:840] = -0.2                    # alpha clamp at 0 active
+    inp["rotations"][840:848] = 0.0                     # zero quaternion: normalise eps path
+    inp["colors"][848:912] *= 3.0                       # image clamp at 1 active
+
+    def redraw(inp, idx, g):
+        m = idx[(idx >= 320) & (idx < 704)]
+        o = idx[(idx < 320) | (idx >= 704)]
+        # keep the special structure: nudge x,y only (depth ties and near-plane z stay)
+        inp["positions"][idx, 0] += (torch.rand(idx.numel(), generator=g) - 0.5) * 0.05
+        inp["positions"][idx, 1] += (torch.rand(idx.numel(), generator=g) - 0.5) * 0.05
+        inp["scales"][idx] *= 1.0 + 0.01 * torch.rand(idx.numel(), 3, generator=g)
+        del m, o
+
+    inp = settle(inp, cam, W, H, 64, 7, redraw, allow_ties=True)
+    run_tile("tile_edge_1k_96x80", inp, cam, W, H, bg=(0.1, 0.0, 0.3),
+             note="ties; near plane, behind camera, border, radius cap, alpha and image clamps, zero quat")
+
+
+def fx_culled():
+    W = H = 64
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(64, seed=9)
+    inp["positions"][:, 2] = inp["positions"][:, 2].abs() + 1.0     # all behind the camera
+    run_tile("tile_allculled_64", inp, cam, W, H, bg=(0.25, 0.5, 0.75), note="nothing visible (DR:545-552)")
+
+
+def fx_phase():
+    W = H = 128
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(2048, seed=11, s_lo=0.01, s_hi=0.05)
+    inp = settle(inp, cam, W, H, 64, 11, redraw_std)
+    run_tile("tile_phase_2k_128", inp, cam, W, H, bg=(0.0, 0.0, 0.0), phase=True, amp=0.25,
+             note="use_phase_blending=True; forward from the reference, gradients from the oracle clone restatement")
+
+
+def fx_wave():
+    W = H = 128
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(2048, seed=13, s_lo=0.01, s_hi=0.05, phase_hi=2 * math.pi)
+    inp = settle(inp, cam, W, H, 64, 13, redraw_std, allow_ties=True)
+    run_wave("wave_scalar_2k_128", inp, cam, W, H, (0.1, 0.2, 0.3), False, note="(N,) phases")
+    g = torch.Generator().manual_seed(14)
+    inp3 = dict(inp)
+    inp3["phases"] = torch.rand(2048, 3, generator=g) * 2 * math.pi
+    run_wave("wave_rgb_2k_128", inp3, cam, W, H, (0.1, 0.2, 0.3), True, note="(N,3) phases")
+
+
+def fx_asm():
+    W = H = 64
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(1024, seed=15, s_lo=0.01, s_hi=0.05, phase_hi=2 * math.pi)
+    inp = settle(inp, cam, W, H, 64, 15, redraw_std, allow_ties=True)
+    wl = torch.tensor([0.0635, 0.05, 0.041])
+    run_asm("asm_1k_64", inp, cam, W, H, (0.05, 0.1, 0.15), wl, (0.1, 4.0),
+            note="wavelengths_rgb=(0.0635,0.05,0.041), depth_range=(0.1,4.0), 16 planes")
+
+
+FIXTURES = dict(culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
+                asm=fx_asm, c1=fx_c1)
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for k, f in FIXTURES.items():
+        if a.only in (None, k):
+            f()
