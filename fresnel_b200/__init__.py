@@ -1,0 +1,14 @@
+"""fresnel_b200: B200-native (sm_100a) drop-in for the differentiable Gaussian-splatting
+renderer of CalebisGross/fresnel (scripts/models/differentiable_renderer.py).
+
+    from fresnel_b200 import TileBasedRenderer, Camera      # instead of models.differentiable_renderer
+
+The compute path is the CUDA library ``csrc/libfresnel_b200.so`` behind ``include/fresnel_b200.h``;
+importing this package does not need a GPU, rendering does.
+"""
+
+from .camera import Camera, camera_vector, create_camera_from_pose
+from .renderer import DEFAULT_T_EPS, TileBasedRenderer, build_bins, render_views
+
+__all__ = ["Camera", "camera_vector", "create_camera_from_pose", "TileBasedRenderer", "render_views",
+           "build_bins", "DEFAULT_T_EPS"]

@@ -1,0 +1,78 @@
+"""ctypes binding of the C-ABI library (include/fresnel_b200.h).
+
+There is no CPU fallback: if ``libfresnel_b200.so`` is missing or a call fails, this module
+raises.  ``lib()`` loads the library built in-tree by ``fresnel_b200.build``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+
+from . import build as _build
+
+_LIB = None
+
+P = c_void_p
+_SIGNATURES = {
+    "frb_version": (c_int, []),
+    "frb_error_string": (c_char_p, [c_int]),
+    "frb_project_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, c_float, P, P, P, P, P, P]),
+    "frb_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
+    "frb_sort_workspace_bytes": (c_size_t, [c_int]),
+    "frb_radix_sort_pairs": (c_int, [c_int, P, P, P, P, c_int, c_int, P, P]),
+    "frb_depth_order_workspace_bytes": (c_size_t, [c_int]),
+    "frb_depth_order": (c_int, [c_int, P, P, P, P]),
+    "frb_scan_workspace_bytes": (c_size_t, [c_int]),
+    "frb_tile_offsets": (c_int, [c_int, P, P, P, P, P]),
+    "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_tile_ranges": (c_int, [c_int, P, c_int, P, P]),
+    "frb_gather_records": (c_int, [c_int, P, P, P, P, P, P]),
+    "frb_phase_ckpt_floats": (c_size_t, [c_int, c_int]),
+    "frb_composite_fwd": (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
+    "frb_composite_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),
+}
+
+# Entry points of later build stages; bound when the library exports them.
+_OPTIONAL = {}
+
+
+class FresnelB200Error(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise FresnelB200Error(
+                f"{path} is missing: build it with `python -m fresnel_b200.build` "
+                "(fresnel_b200 has no CPU or PyTorch fallback path)")
+        handle = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        for name, (res, args) in _OPTIONAL.items():
+            if hasattr(handle, name):
+                fn = getattr(handle, name)
+                fn.restype, fn.argtypes = res, args
+        _LIB = handle
+    return _LIB
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().frb_error_string(code)
+        raise FresnelB200Error(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def exported_symbols():
+    """Names declared in include/fresnel_b200.h (used by the CPU test tier)."""
+    return sorted(_SIGNATURES)

@@ -1,0 +1,343 @@
+// Front-to-back alpha compositing over per-tile Gaussian lists, and its backward.
+// Reference: the per-Gaussian loop of TileBasedRenderer.forward DR:582-667, the epilogue
+// DR:669-686 and the autograd tape through both.
+//
+// One CTA per 16x16 tile, one thread per pixel.  The tile's records (48 B each, contiguous in
+// the sorted instance list) are staged into shared memory in batches by 1D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) through a ring of FRB_STAGES buffers,
+// so the copy of batch b+STAGES-1 overlaps the arithmetic of batch b.  Every thread reads the
+// same record at the same time (shared-memory broadcast, no bank conflicts).
+//
+// Per pixel and record (appendix A.3), with the conic pre-scaled by -0.5*log2(e):
+//     inside = pixel in [x0,x1) x [y0,y1)                       (the reference's rectangle)
+//     g = exp2(A' dx^2 + B' dx dy + C' dy^2);  alpha = clamp(g * opacity, 0, 0.99)
+//     c = alpha * T;  colour += c * rgb;  depth += c * d;  T *= (1 - alpha)
+// T is the reference's (1 - accumulated_alpha) in product form.
+#include "frb_common.cuh"
+
+namespace {
+
+constexpr int TILE = FRB_TILE;
+constexpr int CTA_THREADS = TILE * TILE;
+constexpr int BATCH = 64;                       // records per stage
+constexpr int STAGES = 4;
+constexpr int RECORD_BYTES = FRB_RECORD_FLOATS * 4;
+constexpr float T_FLOOR = 1e-20f;
+constexpr int STATE_GATE_SHIFT = 28;            // state_n = entries consumed | clamp gates << 28
+constexpr int STATE_N_MASK = (1 << STATE_GATE_SHIFT) - 1;
+
+struct __align__(16) StageBuf {
+    float4 rec[BATCH * 3];
+};
+
+__device__ __forceinline__ bool rect_contains(uint32_t pxy_guard, uint32_t pxy_plus1, uint32_t lo, uint32_t hi) {
+    // SWAR test of x0 <= px < x1 and y0 <= py < y1 on 15-bit halves with guard bits:
+    // (px | G) - x0 keeps G iff px >= x0 ; (x1 | G) - (px + 1) keeps G iff px < x1.
+    uint32_t a = pxy_guard - lo;
+    uint32_t b = hi - pxy_plus1;
+    return ((a & b) & 0x80008000u) == 0x80008000u;
+}
+
+template <bool PHASE>
+__global__ void __launch_bounds__(CTA_THREADS)
+composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
+                     const float4* __restrict__ sorted_records, const float* __restrict__ sorted_phases,
+                     float phase_amplitude, float3 bg, float t_eps, float* __restrict__ image,
+                     float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
+                     int* __restrict__ state_n) {
+    __shared__ StageBuf stage[STAGES];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+
+    const int tile = blockIdx.x;
+    const int view = tile / tiles_per_view;
+    const int t_in_view = tile - view * tiles_per_view;
+    const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
+    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
+    const int py = ty * TILE + (threadIdx.x / TILE);
+    const bool in_image = (px < width) && (py < height);
+    const float fpx = (float)px, fpy = (float)py;
+    const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
+    const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
+
+    const int2 range = ranges[tile];
+    const int count = range.y - range.x;
+    const int n_batches = (count + BATCH - 1) / BATCH;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) frb_mbar_init(&full_bar[s], 1);
+        frb_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < STAGES && b < n_batches; ++b) {
+            int cnt = min(BATCH, count - b * BATCH);
+            frb_mbar_expect_tx(&full_bar[b], cnt * RECORD_BYTES);
+            frb_tma_load_1d(stage[b].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
+                            &full_bar[b]);
+        }
+    }
+
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;
+    int consumed = 0;
+    bool done = !in_image;
+    const float stop = fmaxf(t_eps, T_FLOOR);
+
+    for (int b = 0; b < n_batches; ++b) {
+        const int s = b % STAGES;
+        const int cnt = min(BATCH, count - b * BATCH);
+        frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
+        if (!done) {
+            const float4* rec = stage[s].rec;
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                float4 r0 = rec[3 * j + 0], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                bool inside = rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                if (inside && !done) {
+                    float dx = fpx - r0.x, dy = fpy - r0.y;
+                    float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                    float a = frb_ex2(power) * r1.y;
+                    a = fminf(fmaxf(a, 0.0f), FRB_ALPHA_MAX);
+                    float c = a * T;
+                    cr = fmaf(c, r2.x, cr);
+                    cg = fmaf(c, r2.y, cg);
+                    cb = fmaf(c, r2.z, cb);
+                    cd = fmaf(c, r1.z, cd);
+                    T = T * (1.0f - a);
+                    consumed = b * BATCH + j + 1;
+                    done = T < stop;
+                }
+            }
+        }
+        // everyone is finished with stage s: refill it, or stop early when no pixel needs more
+        int all_done = __syncthreads_and(done ? 1 : 0);
+        if (all_done) {
+            // bulk copies already in flight must land before this CTA's shared memory is released
+            for (int bb = b + 1; bb < n_batches && bb < b + STAGES; ++bb)
+                frb_mbar_wait(&full_bar[bb % STAGES], (bb / STAGES) & 1);
+            break;
+        }
+        if (threadIdx.x == 0 && b + STAGES < n_batches) {
+            int nb = b + STAGES;
+            int ncnt = min(BATCH, count - nb * BATCH);
+            frb_mbar_expect_tx(&full_bar[s], ncnt * RECORD_BYTES);
+            frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + nb * BATCH), ncnt * RECORD_BYTES,
+                            &full_bar[s]);
+        }
+    }
+
+    if (in_image) {
+        const size_t hw = (size_t)width * height;
+        const size_t pix = (size_t)view * hw + (size_t)py * width + px;
+        float* img = image + (size_t)view * 3 * hw + (size_t)py * width + px;
+        // DR:670-675
+        float o0 = fmaf(T, bg.x, cr), o1 = fmaf(T, bg.y, cg), o2 = fmaf(T, bg.z, cb);
+        img[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
+        img[hw] = fminf(fmaxf(o1, 0.0f), 1.0f);
+        img[2 * hw] = fminf(fmaxf(o2, 0.0f), 1.0f);
+        depth_out[pix] = cd;
+        alpha_out[pix] = 1.0f - T;
+        state_T[pix] = T;
+        // torch.clamp backward passes the gradient where 0 <= x <= 1 (inclusive): keep the three gates
+        int gates = ((o0 >= 0.0f && o0 <= 1.0f) ? 1 : 0) | ((o1 >= 0.0f && o1 <= 1.0f) ? 2 : 0) |
+                    ((o2 >= 0.0f && o2 <= 1.0f) ? 4 : 0);
+        state_n[pix] = consumed | (gates << STATE_GATE_SHIFT);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward (appendix A.4).  Walks each tile list back to front.  Per pixel:
+//   w_i = gC . rgb_i + gD * depth_i ; T_i = T_{i+1} / (1 - alpha_i) ;
+//   dL/dalpha_i = T_i w_i - (S + T_final X) / (1 - alpha_i),  S = sum_{j>i} c_j w_j,
+//   X = gC . bg - gA  (alpha_out = 1 - T_final)
+// gated by 0 <= g*o <= 0.99 (torch.clamp backward is inclusive).  The ten per-Gaussian
+// partials are summed over the warp with shuffles and added with one atomic per warp.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS)
+composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
+                     const float4* __restrict__ sorted_records, const uint32_t* __restrict__ sorted_gids,
+                     float3 bg, const float* __restrict__ state_T,
+                     const int* __restrict__ state_n, const float* __restrict__ g_image,
+                     const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
+                     float* __restrict__ grad2d) {
+    __shared__ StageBuf stage[STAGES];
+    __shared__ uint32_t gid_s[STAGES][BATCH];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ int max_n_s;
+
+    const int tile = blockIdx.x;
+    const int view = tile / tiles_per_view;
+    const int t_in_view = tile - view * tiles_per_view;
+    const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
+    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
+    const int py = ty * TILE + (threadIdx.x / TILE);
+    const bool in_image = (px < width) && (py < height);
+    const float fpx = (float)px, fpy = (float)py;
+    const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
+    const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
+    const int lane = threadIdx.x & 31;
+
+    const int2 range = ranges[tile];
+
+    float T_final = 1.0f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
+    int my_n = 0;
+    if (in_image) {
+        const size_t hw = (size_t)width * height;
+        const size_t pix = (size_t)view * hw + (size_t)py * width + px;
+        const size_t ip = (size_t)view * 3 * hw + (size_t)py * width + px;
+        T_final = state_T[pix];
+        const int st = state_n[pix];
+        my_n = st & STATE_N_MASK;
+        const int gates = st >> STATE_GATE_SHIFT;   // clamp(image, 0, 1) backward, DR:674-675
+        gr = (gates & 1) ? g_image[ip] : 0.0f;
+        gg = (gates & 2) ? g_image[ip + hw] : 0.0f;
+        gb = (gates & 4) ? g_image[ip + 2 * hw] : 0.0f;
+        gd = g_depth ? g_depth[pix] : 0.0f;
+        ga = g_alpha ? g_alpha[pix] : 0.0f;
+    }
+    if (threadIdx.x == 0) max_n_s = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) frb_mbar_init(&full_bar[s], 1);
+        frb_mbar_fence_init();
+    }
+    __syncthreads();
+    {
+        int wmax = my_n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        if (lane == 0) atomicMax(&max_n_s, wmax);
+    }
+    __syncthreads();
+    const int count = min(max_n_s, range.y - range.x);
+    const int n_batches = (count + BATCH - 1) / BATCH;
+    if (n_batches == 0) return;
+
+    // batches are visited last to first; ring slot k holds visit k
+    auto issue = [&](int visit) {
+        int b = n_batches - 1 - visit;
+        int s = visit % STAGES;
+        int cnt = min(BATCH, count - b * BATCH);
+        frb_mbar_expect_tx(&full_bar[s], cnt * RECORD_BYTES);
+        frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
+                        &full_bar[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int v = 0; v < STAGES && v < n_batches; ++v) issue(v);
+
+    const float X = gr * bg.x + gg * bg.y + gb * bg.z - ga;
+    const float TX = T_final * X;
+    float T = T_final;
+    float S = 0.0f;
+
+    for (int visit = 0; visit < n_batches; ++visit) {
+        const int b = n_batches - 1 - visit;
+        const int s = visit % STAGES;
+        const int cnt = min(BATCH, count - b * BATCH);
+        if (threadIdx.x < cnt) gid_s[s][threadIdx.x] = sorted_gids[range.x + b * BATCH + threadIdx.x];
+        frb_mbar_wait(&full_bar[s], (visit / STAGES) & 1);
+        __syncthreads();  // gid_s visible
+        const float4* rec = stage[s].rec;
+        for (int j = cnt - 1; j >= 0; --j) {
+            float4 r0 = rec[3 * j + 0], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+            const int idx = b * BATCH + j;
+            bool active = (idx < my_n) &&
+                          rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+            float d_u = 0.f, d_v = 0.f, d_A = 0.f, d_B = 0.f, d_C = 0.f, d_o = 0.f, d_dep = 0.f, d_r = 0.f,
+                  d_g = 0.f, d_b = 0.f;
+            if (active) {
+                float dx = fpx - r0.x, dy = fpy - r0.y;
+                float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                float g = frb_ex2(power);
+                float araw = g * r1.y;
+                float a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
+                float om = 1.0f - a;
+                float inv_om = __fdividef(1.0f, om);
+                float Ti = T * inv_om;
+                float c = a * Ti;
+                float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                float dalpha = Ti * w - (S + TX) * inv_om;
+                S = fmaf(c, w, S);
+                T = Ti;
+                d_r = c * gr; d_g = c * gg; d_b = c * gb; d_dep = c * gd;
+                if (araw >= 0.0f && araw <= FRB_ALPHA_MAX) {
+                    d_o = g * dalpha;
+                    float dpow = r1.y * dalpha * g * FRB_LN2;   // dL/d(power): g = 2^power
+                    d_A = dx * dx * dpow;
+                    d_B = dx * dy * dpow;
+                    d_C = dy * dy * dpow;
+                    d_u = -(2.0f * r0.z * dx + r0.w * dy) * dpow;
+                    d_v = -(r0.w * dx + 2.0f * r1.x * dy) * dpow;
+                }
+            }
+            if (__any_sync(0xffffffffu, active)) {
+                d_u = frb_warp_sum(d_u); d_v = frb_warp_sum(d_v);
+                d_A = frb_warp_sum(d_A); d_B = frb_warp_sum(d_B); d_C = frb_warp_sum(d_C);
+                d_o = frb_warp_sum(d_o); d_dep = frb_warp_sum(d_dep);
+                d_r = frb_warp_sum(d_r); d_g = frb_warp_sum(d_g); d_b = frb_warp_sum(d_b);
+                if (lane == 0) {
+                    float* g2 = grad2d + (size_t)gid_s[s][j] * FRB_GRAD_FLOATS;
+                    atomicAdd(g2 + 0, d_u); atomicAdd(g2 + 1, d_v); atomicAdd(g2 + 2, d_A);
+                    atomicAdd(g2 + 3, d_B); atomicAdd(g2 + 4, d_C); atomicAdd(g2 + 5, d_o);
+                    atomicAdd(g2 + 6, d_dep); atomicAdd(g2 + 8, d_r); atomicAdd(g2 + 9, d_g);
+                    atomicAdd(g2 + 10, d_b);
+                }
+            }
+        }
+        __syncthreads();  // stage s and gid_s[s] are free
+        if (threadIdx.x == 0 && visit + STAGES < n_batches) issue(visit + STAGES);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t frb_phase_ckpt_floats(int m, int n_tiles) {
+    (void)m; (void)n_tiles;
+    return 0;
+}
+
+static int check_image_args(int n_views, int width, int height) {
+    if (n_views < 1 || n_views > FRB_MAX_VIEWS || width < 1 || height < 1) return FRB_E_INVALID;
+    if (width > FRB_MAX_IMAGE_SIDE || height > FRB_MAX_IMAGE_SIDE) return FRB_E_TOO_LARGE;
+    return 0;
+}
+
+extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32_t* ranges,
+                                 const float* sorted_records, const float* sorted_phases,
+                                 float phase_amplitude, const float* background_host, float t_eps,
+                                 float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
+                                 float* ckpt, void* stream) {
+    int rc = check_image_args(n_views, width, height);
+    if (rc) return rc;
+    if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n) return FRB_E_INVALID;
+    if (sorted_phases) return FRB_E_INVALID;  // phase blending: see composite_phase.cu
+    (void)ckpt;
+    int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
+    int tpv = tiles_x * tiles_y;
+    float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
+    composite_fwd_kernel<false><<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, nullptr, phase_amplitude,
+        bg, t_eps, image, depth, alpha, state_T, state_n);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
+                                 const float* sorted_records, const uint32_t* sorted_gids,
+                                 const float* sorted_phases, float phase_amplitude,
+                                 const float* background_host, const float* state_T,
+                                 const int32_t* state_n, const float* ckpt, const float* g_image,
+                                 const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
+                                 void* stream) {
+    int rc = check_image_args(n_views, width, height);
+    if (rc) return rc;
+    if (!ranges || !background_host || !state_T || !state_n || !g_image || !grad2d) return FRB_E_INVALID;
+    if (sorted_phases) return FRB_E_INVALID;
+    (void)ckpt; (void)g_phases; (void)phase_amplitude;
+    int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
+    int tpv = tiles_x * tiles_y;
+    float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
+    composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, bg,
+        state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}

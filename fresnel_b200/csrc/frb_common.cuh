@@ -1,0 +1,88 @@
+// Shared device helpers: error plumbing, mbarrier + 1D TMA bulk copy (sm_100a PTX), warp utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fresnel_b200.h"
+#include "frb_math.h"
+
+#define FRB_MAX_VIEWS 32
+
+struct FrbViewSet {
+    int n_views;
+    int n_per_view;
+    FrbCamera cam[FRB_MAX_VIEWS];
+};
+
+// Fills `vs` from n_views * FRB_CAMERA_FLOATS host floats.  Returns 0 or FRB_E_INVALID.
+int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs);
+
+#define FRB_CUDA_OK(expr)                          \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+#define FRB_LAUNCH_CHECK()                         \
+    do {                                           \
+        cudaError_t _e = cudaGetLastError();       \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+static inline int frb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t frb_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier (shared::cta) ------------------------------------------------
+__device__ __forceinline__ void frb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(frb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void frb_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void frb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(frb_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void frb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(frb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- TMA: 1D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP) ----
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void frb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            frb_smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(frb_smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float frb_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float frb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__

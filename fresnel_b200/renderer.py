@@ -1,0 +1,282 @@
+"""Drop-in renderer modules over the C-ABI library.
+
+``TileBasedRenderer`` has the constructor and ``forward`` signature of the reference module
+(scripts/models/differentiable_renderer.py:434-450, 489-511) and is what
+scripts/training/train_gaussian_decoder.py:1212-1221 calls once per view.  The work is done by
+the CUDA kernels in ``csrc/`` through ``include/fresnel_b200.h``; this file only allocates
+device buffers, sequences the launches on the current stream and registers the backward pass
+as a ``torch.autograd.Function``.  There is no CPU path: non-CUDA inputs raise.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .camera import camera_vector
+
+TILE = 16
+RECORD_FLOATS = 12
+DEFAULT_T_EPS = 2.0 ** -20   # pixel stops once transmittance < t_eps; 0 = never (exact mode)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_inputs(**tensors):
+    out = {}
+    dev = None
+    for name, t in tensors.items():
+        if t is None:
+            out[name] = None
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if not t.is_cuda:
+            raise TypeError(
+                f"{name} is on {t.device}: fresnel_b200 renders on CUDA only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise TypeError(f"{name} is on {t.device}, expected {dev}")
+        if t.dtype != torch.float32:
+            t = t.float()
+        out[name] = t.contiguous()
+    return out
+
+
+class TileBins:
+    """Sorted tile instance lists of one batch of views (result of the binning stage)."""
+
+    __slots__ = ("m", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
+                 "records", "rects", "depth_bits", "touched")
+
+
+def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
+               width: int, height: int, max_radius: float, phases=None, keep_debug: bool = False,
+               sort: bool = True) -> TileBins:
+    """Projection + binning: everything up to the per-tile sorted record lists.
+
+    Sequences frb_project_fwd -> frb_depth_order -> frb_tile_offsets -> frb_bin_emit ->
+    frb_radix_sort_pairs (tile bits only) -> frb_tile_ranges -> frb_gather_records.
+    One device->host read (the instance count M) sizes the instance buffers.
+    """
+    L = _lib.lib()
+    dev = positions.device
+    n = positions.shape[0]
+    st = _stream()
+    i32 = dict(dtype=torch.int32, device=dev)
+    tiles_x, tiles_y = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    n_tiles = n_views * tiles_x * tiles_y
+    cam = np.ascontiguousarray(cam_vecs, np.float32)
+
+    b = TileBins()
+    b.records = torch.empty(n, RECORD_FLOATS, dtype=torch.float32, device=dev)
+    b.depth_bits = torch.empty(n, **i32)
+    b.touched = torch.empty(n, **i32)
+    b.rects = torch.empty(n, 4, **i32) if keep_debug else None
+    _lib.check(L.frb_project_fwd(n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), _ptr(colors),
+                                 _ptr(opacities), cam.ctypes.data, float(max_radius), _ptr(b.records),
+                                 _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st),
+               "frb_project_fwd")
+
+    b.order = None
+    if sort and n > 0:
+        b.order = torch.empty(n, **i32)
+        ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        _lib.check(L.frb_depth_order(n, _ptr(b.depth_bits), _ptr(b.order), _ptr(ws), st), "frb_depth_order")
+
+    offsets = torch.empty(n + 1, **i32)
+    ws = torch.empty(max(L.frb_scan_workspace_bytes(n), 4), dtype=torch.uint8, device=dev)
+    _lib.check(L.frb_tile_offsets(n, _ptr(b.touched), _ptr(b.order), _ptr(offsets), _ptr(ws), st),
+               "frb_tile_offsets")
+    m = int(offsets[n].item())          # the one host sync of the forward pass
+    b.m = m
+
+    b.ranges = torch.empty(n_tiles, 2, **i32)
+    b.keys = torch.empty(m, dtype=torch.int64, device=dev)
+    b.sorted_gids = torch.empty(m, **i32)
+    b.sorted_records = torch.empty(max(m, 1), RECORD_FLOATS, dtype=torch.float32, device=dev)
+    b.sorted_phases = None
+    if m > 0:
+        _lib.check(L.frb_bin_emit(n, n_views, width, height, _ptr(b.records), _ptr(b.depth_bits),
+                                  _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st),
+                   "frb_bin_emit")
+        keys_tmp = torch.empty(m, dtype=torch.int64, device=dev)
+        vals_tmp = torch.empty(m, **i32)
+        ws = torch.empty(L.frb_sort_workspace_bytes(m), dtype=torch.uint8, device=dev)
+        tile_bits = max(1, int(math.ceil(math.log2(max(n_tiles, 2)))))
+        begin = 32 if sort else 0
+        _lib.check(L.frb_radix_sort_pairs(m, _ptr(b.keys), _ptr(b.sorted_gids), _ptr(keys_tmp),
+                                          _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st),
+                   "frb_radix_sort_pairs")
+    _lib.check(L.frb_tile_ranges(m, _ptr(b.keys), n_tiles, _ptr(b.ranges), st), "frb_tile_ranges")
+    if m > 0:
+        if phases is not None:
+            b.sorted_phases = torch.empty(m, dtype=torch.float32, device=dev)
+        _lib.check(L.frb_gather_records(m, _ptr(b.sorted_gids), _ptr(b.records), _ptr(b.sorted_records),
+                                        _ptr(phases), _ptr(b.sorted_phases), st), "frb_gather_records")
+    elif phases is not None:
+        b.sorted_phases = torch.empty(1, dtype=torch.float32, device=dev)
+    return b
+
+
+class _TileRenderFn(torch.autograd.Function):
+    """Forward / backward of TileBasedRenderer for n_views views in one call."""
+
+    @staticmethod
+    def forward(ctx, positions, scales, rotations, colors, opacities, phases, cfg):
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
+        L = _lib.lib()
+        dev = positions.device
+        st = _stream()
+        n = positions.shape[0]
+        bins = build_bins(positions, scales, rotations, colors, opacities, cam_vecs, n_views, width, height,
+                          max_radius, phases=phases)
+        f32 = dict(dtype=torch.float32, device=dev)
+        image = torch.empty(n_views, 3, height, width, **f32)
+        depth = torch.empty(n_views, height, width, **f32)
+        alpha = torch.empty(n_views, height, width, **f32)
+        state_T = torch.empty(n_views, height, width, **f32)
+        state_n = torch.empty(n_views, height, width, dtype=torch.int32, device=dev)
+        bg_host = np.asarray(bg, np.float32)
+        ckpt = None
+        if phases is not None:
+            n_tiles = bins.ranges.shape[0]
+            ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m, n_tiles), 1), **f32)
+        _lib.check(L.frb_composite_fwd(n_views, width, height, _ptr(bins.ranges), _ptr(bins.sorted_records),
+                                       _ptr(bins.sorted_phases), float(phase_amp), bg_host.ctypes.data,
+                                       float(t_eps), _ptr(image), _ptr(depth), _ptr(alpha), _ptr(state_T),
+                                       _ptr(state_n), _ptr(ckpt), st), "frb_composite_fwd")
+        ctx.cfg = cfg
+        ctx.n = n
+        ctx.has_phase = phases is not None
+        ctx.save_for_backward(positions, scales, rotations, bins.ranges, bins.sorted_records, bins.sorted_gids,
+                              state_T, state_n,
+                              bins.sorted_phases if phases is not None else positions.new_empty(0),
+                              ckpt if ckpt is not None else positions.new_empty(0))
+        return image, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_alpha):
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
+        (positions, scales, rotations, ranges, sorted_records, sorted_gids, state_T, state_n, sorted_phases,
+         ckpt) = ctx.saved_tensors
+        L = _lib.lib()
+        dev = positions.device
+        st = _stream()
+        n = ctx.n
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_image = (torch.zeros(n_views, 3, height, width, **f32) if g_image is None
+                   else g_image.contiguous().float())
+        g_depth = None if g_depth is None else g_depth.contiguous().float()
+        g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
+        grad2d = torch.zeros(n, RECORD_FLOATS, **f32)
+        g_phases = torch.zeros(n, **f32) if ctx.has_phase else None
+        bg_host = np.asarray(bg, np.float32)
+        _lib.check(L.frb_composite_bwd(n_views, width, height, _ptr(ranges), _ptr(sorted_records),
+                                       _ptr(sorted_gids), _ptr(sorted_phases) if ctx.has_phase else None,
+                                       float(phase_amp), bg_host.ctypes.data, _ptr(state_T), _ptr(state_n),
+                                       _ptr(ckpt) if ctx.has_phase else None, _ptr(g_image), _ptr(g_depth),
+                                       _ptr(g_alpha), _ptr(grad2d), _ptr(g_phases), st), "frb_composite_bwd")
+        g_pos = torch.empty(n, 3, **f32)
+        g_scl = torch.empty(n, 3, **f32)
+        g_rot = torch.empty(n, 4, **f32)
+        g_col = torch.empty(n, 3, **f32)
+        g_opa = torch.empty(n, **f32)
+        cam = np.ascontiguousarray(cam_vecs, np.float32)
+        _lib.check(L.frb_project_bwd(n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), cam.ctypes.data,
+                                     _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col),
+                                     _ptr(g_opa), st), "frb_project_bwd")
+        return g_pos, g_scl, g_rot, g_col, g_opa, g_phases, None
+
+
+def render_views(positions, scales, rotations, colors, opacities, cameras: Sequence, width: int, height: int,
+                 background=(0.0, 0.0, 0.0), max_radius: float = 64, t_eps: float = DEFAULT_T_EPS,
+                 phases=None, phase_amplitude: float = 0.25
+                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Render B views in one pass of the kernels (the loop at train_gaussian_decoder.py:1209-1223).
+
+    positions (B, N, 3), scales (B, N, 3), rotations (B, N, 4), colors (B, N, 3), opacities (B, N),
+    phases (B, N) or None, cameras: B camera objects.  Returns image (B, 3, H, W), depth (B, H, W),
+    alpha (B, H, W); differentiable with respect to the five (six) inputs.
+    """
+    B, N = positions.shape[0], positions.shape[1]
+    if len(cameras) != B:
+        raise ValueError(f"{len(cameras)} cameras for {B} views")
+    if B > 32:
+        outs = [render_views(positions[i:i + 32], scales[i:i + 32], rotations[i:i + 32], colors[i:i + 32],
+                             opacities[i:i + 32], cameras[i:i + 32], width, height, background, max_radius,
+                             t_eps, None if phases is None else phases[i:i + 32], phase_amplitude)
+                for i in range(0, B, 32)]
+        return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
+    t = _check_inputs(positions=positions.reshape(B * N, 3), scales=scales.reshape(B * N, 3),
+                      rotations=rotations.reshape(B * N, 4), colors=colors.reshape(B * N, 3),
+                      opacities=opacities.reshape(B * N),
+                      phases=None if phases is None else phases.reshape(B * N))
+    cam_vecs = np.stack([camera_vector(c, width, height) for c in cameras])
+    cfg = (cam_vecs, B, int(width), int(height), tuple(float(x) for x in background), float(max_radius),
+           float(t_eps), float(phase_amplitude))
+    with torch.cuda.device(t["positions"].device):
+        return _TileRenderFn.apply(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"],
+                                   t["phases"], cfg)
+
+
+class TileBasedRenderer(nn.Module):
+    """Memory-efficient tile-based Gaussian renderer - CUDA drop-in for the reference module.
+
+    Same constructor and call signature as the reference ``TileBasedRenderer``
+    (scripts/models/differentiable_renderer.py:412-686).  Extra keyword-only knobs:
+    ``t_eps`` (early termination threshold on the transmittance; 0 reproduces the reference's
+    exhaustive loop) and ``return_alpha`` on ``forward``.
+    """
+
+    def __init__(self, image_width: int, image_height: int,
+                 background: Tuple[float, float, float] = (0.0, 0.0, 0.0), max_radius: int = 64,
+                 use_phase_blending: bool = False, phase_amplitude: float = 0.25, *,
+                 t_eps: float = DEFAULT_T_EPS):
+        super().__init__()
+        self.width = image_width
+        self.height = image_height
+        self.background = torch.tensor(background)
+        self.max_radius = max_radius
+        self.use_phase_blending = use_phase_blending
+        self.phase_amplitude = phase_amplitude
+        self.t_eps = t_eps
+
+    def forward(self, positions: torch.Tensor, scales: torch.Tensor, rotations: torch.Tensor,
+                colors: torch.Tensor, opacities: torch.Tensor, camera, return_depth: bool = False,
+                phases: Optional[torch.Tensor] = None, return_alpha: bool = False):
+        use_phase = self.use_phase_blending and phases is not None          # DR:571-572
+        bg = tuple(float(x) for x in self.background.tolist())
+        image, depth, alpha = render_views(
+            positions.unsqueeze(0), scales.unsqueeze(0), rotations.unsqueeze(0), colors.unsqueeze(0),
+            opacities.reshape(1, -1), [camera], self.width, self.height, bg, self.max_radius, self.t_eps,
+            phases.reshape(1, -1) if use_phase else None, self.phase_amplitude)
+        out: List[torch.Tensor] = [image[0]]
+        if return_depth:
+            out.append(depth[0])
+        if return_alpha:
+            out.append(alpha[0])
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def render_batch(self, positions, scales, rotations, colors, opacities, cameras, phases=None):
+        """All views of a training batch in one call: (B, N, .) inputs, B cameras (or one camera
+        shared by all views) -> image (B, 3, H, W), depth (B, H, W), alpha (B, H, W)."""
+        B = positions.shape[0]
+        cams = list(cameras) if isinstance(cameras, (list, tuple)) else [cameras] * B
+        bg = tuple(float(x) for x in self.background.tolist())
+        use_phase = self.use_phase_blending and phases is not None
+        return render_views(positions, scales, rotations, colors, opacities, cams, self.width, self.height,
+                            bg, self.max_radius, self.t_eps, phases if use_phase else None,
+                            self.phase_amplitude)

@@ -1,0 +1,136 @@
+/*
+ * fresnel_b200 C-ABI: the drop-in boundary of the B200-native Gaussian-splatting
+ * renderer.  Plain pointers and sizes only; every pointer is a DEVICE pointer
+ * unless the name ends in _host.  All functions are asynchronous on `stream`
+ * (a cudaStream_t passed as void*), return 0 on success and a positive
+ * cudaError_t / negative FRB_E_* code otherwise, and never fall back to the CPU.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository,
+ * DR = scripts/models/differentiable_renderer.py):
+ *   frb_project_fwd / frb_project_bwd     compute_2d_covariance DR:123-195,
+ *                                         quaternion_to_rotation_matrix DR:98-120,
+ *                                         TileBasedRenderer._compute_radius DR:452-487,
+ *                                         visibility + rectangles DR:541-543, 594-600,
+ *                                         pinv(cov + 1e-4 I) DR:578-579, and their autograd
+ *   frb_depth_order / frb_tile_offsets /  torch.argsort(depths) DR:527-538 and the mask
+ *   frb_bin_emit / frb_radix_sort_pairs / compaction DR:554-562, restated as a stable
+ *   frb_tile_ranges / frb_gather_records  (tile|depth) 64-bit key sort (no reference
+ *                                         counterpart for tiles; nearest native code is
+ *                                         src/core/compute/radix_sort.cpp)
+ *   frb_composite_fwd / frb_composite_bwd the per-Gaussian loop DR:582-667, the epilogue
+ *                                         DR:669-686 and the autograd tape through them
+ *                                         (phases != NULL: the Fresnel phase blending
+ *                                         DR:571-575, 629-645, 660-667)
+ *   frb_wave_*                            WaveFieldRenderer.forward DR:747-926
+ *   frb_asm_*                             AngularSpectrumPropagator DR:929-1065 and
+ *                                         ASMWaveFieldRenderer.forward DR:1150-1344
+ *
+ * Views.  Every entry point renders `n_views` independent views in one call (the per-view
+ * loop of scripts/training/train_gaussian_decoder.py:1209-1223).  The n Gaussians are
+ * n_views consecutive groups of n / n_views, group k seen by camera k; tile ids are global:
+ * view * tiles_per_view + tile_y * tiles_x + tile_x.  n_views <= FRB_MAX_VIEWS.
+ *
+ * Layouts
+ *   camera_host : n_views x 20 floats = view-matrix rows 0..2 (12), fx, fy, cx, cy, width,
+ *                 height, near, far  (Camera DR:24-52); width/height equal for all views
+ *   records     : FRB_RECORD_FLOATS floats per Gaussian
+ *                 [u, v, A', B' | C', opacity, depth, rect_lo | r, g, b, rect_hi]
+ *                 A',B',C' = conic * (-0.5*log2 e), B = inv01 + inv10 (DR:618);
+ *                 rect_lo = x0 | y0 << 16, rect_hi = x1 | y1 << 16 | 0x80008000 (bit-cast);
+ *                 the rectangle is [x0,x1) x [y0,y1) of DR:594-597, all zero when culled
+ *   rects       : int32 [x0, x1, y0, y1] per Gaussian (same numbers, unpacked)
+ *   grad2d      : FRB_GRAD_FLOATS floats per Gaussian, accumulated by composite_bwd
+ *                 [du, dv, dA', dB' | dC', dopacity, ddepth, 0 | dr, dg, db, 0]
+ *   keys        : (global_tile_id << 32) | IEEE-754 bits of the fp32 depth
+ *   ranges      : [start, end) into the sorted instance list, per 16x16 tile
+ *   image       : [n_views][3][H][W]; depth, alpha, state_T, state_n : [n_views][H][W]
+ */
+#ifndef FRESNEL_B200_H
+#define FRESNEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRB_TILE 16
+#define FRB_RECORD_FLOATS 12
+#define FRB_GRAD_FLOATS 12
+#define FRB_CAMERA_FLOATS 20
+#define FRB_DEBUG_FLOATS 8
+#define FRB_MAX_VIEWS 32
+#define FRB_MAX_IMAGE_SIDE 32767
+
+#define FRB_E_INVALID (-1)   /* bad argument (size, alignment, null pointer) */
+#define FRB_E_TOO_LARGE (-2) /* image side > FRB_MAX_IMAGE_SIDE, too many views or instances */
+
+int frb_version(void);
+const char* frb_error_string(int code);
+
+/* ---- projection ------------------------------------------------------- */
+/* rects, debug nullable.  debug: [cov a, b, c, d, radius, visible, 0, 0] per Gaussian. */
+int frb_project_fwd(int n, int n_views, const float* positions, const float* scales,
+                    const float* rotations, const float* colors, const float* opacities,
+                    const float* camera_host, float max_radius, float* records, int32_t* rects,
+                    uint32_t* depth_bits, uint32_t* tiles_touched, float* debug, void* stream);
+
+/* g_colors / g_opacities nullable (they are plain copies of grad2d columns). */
+int frb_project_bwd(int n, int n_views, const float* positions, const float* scales,
+                    const float* rotations, const float* camera_host, const float* grad2d,
+                    float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
+                    float* g_opacities, void* stream);
+
+/* ---- binning: depth order, offsets, keys, stable radix sort, ranges, gather -------- */
+/* Stable LSD radix sort of (key, value) pairs on key bits [begin_bit, end_bit).
+ * The sorted result is always left in keys / vals; *_tmp are scratch of the same size. */
+size_t frb_sort_workspace_bytes(int m);
+int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
+                         uint32_t* vals_tmp, int begin_bit, int end_bit, void* workspace,
+                         void* stream);
+/* order[k] = index of the k-th Gaussian in stable ascending depth_bits order (all n of them). */
+size_t frb_depth_order_workspace_bytes(int n);
+int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* workspace,
+                    void* stream);
+/* offsets[k] = sum_{j<k} tiles_touched[order[j]] for k = 0..n (order NULL = identity);
+ * offsets[n] = number of tile instances M. */
+size_t frb_scan_workspace_bytes(int n);
+int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint32_t* order, uint32_t* offsets,
+                     void* workspace, void* stream);
+/* Slot k emits the keys of Gaussian order[k] at offsets[k] (tiles in row-major order). */
+int frb_bin_emit(int n, int n_views, int width, int height, const float* records,
+                 const uint32_t* depth_bits, const uint32_t* order, const uint32_t* offsets,
+                 uint64_t* keys, uint32_t* gids, void* stream);
+int frb_tile_ranges(int m, const uint64_t* keys, int n_tiles, int32_t* ranges, void* stream);
+/* phases / sorted_phases nullable (both or neither). */
+int frb_gather_records(int m, const uint32_t* gids, const float* records, float* sorted_records,
+                       const float* phases, float* sorted_phases, void* stream);
+
+/* ---- compositing ------------------------------------------------------ */
+/* t_eps: a pixel stops once its transmittance has fallen below max(t_eps, 1e-20).
+ * sorted_phases == NULL selects plain alpha compositing; otherwise Fresnel phase blending
+ * with phase_amplitude.  state_T / state_n are per-pixel state for the backward pass
+ * (final transmittance; number of list entries consumed | image-clamp gates << 28).  ckpt (nullable unless phases are
+ * given and a backward pass will follow) receives per-batch (alpha, phase) checkpoints. */
+size_t frb_phase_ckpt_floats(int m, int n_tiles);
+int frb_composite_fwd(int n_views, int width, int height, const int32_t* ranges,
+                      const float* sorted_records, const float* sorted_phases,
+                      float phase_amplitude, const float* background_host, float t_eps,
+                      float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
+                      float* ckpt, void* stream);
+
+/* g_depth, g_alpha nullable (treated as zero).  grad2d (and g_phases) must be zeroed by the
+ * caller; contributions are accumulated with atomics. */
+int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
+                      const float* sorted_records, const uint32_t* sorted_gids,
+                      const float* sorted_phases, float phase_amplitude,
+                      const float* background_host, const float* state_T,
+                      const int32_t* state_n, const float* ckpt, const float* g_image,
+                      const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRESNEL_B200_H */

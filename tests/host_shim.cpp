@@ -1,0 +1,47 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles fresnel_b200/csrc/frb_math.h (the arithmetic the CUDA
+// kernels inline) with g++ so that the CPU-only test tier can check it against the oracle:
+// bit-exact projection / rectangles / visibility and the hand-derived projection backward.
+// Nothing in the product imports or links this file.
+//   g++ -O2 -ffp-contract=off -shared -fPIC tests/host_shim.cpp -o tests/_host_shim.so
+#include <cstring>
+
+#include "../fresnel_b200/csrc/frb_math.h"
+
+static FrbCamera cam_from(const float* c) {
+    FrbCamera cam;
+    std::memcpy(cam.V, c, 12 * sizeof(float));
+    cam.fx = c[12]; cam.fy = c[13]; cam.cx = c[14]; cam.cy = c[15];
+    cam.width = c[16]; cam.height = c[17]; cam.near_ = c[18]; cam.far_ = c[19];
+    return cam;
+}
+
+extern "C" {
+
+// out_f: [u, v, depth, a, b, c, d, radius, A, B, C] per Gaussian; out_i: [visible, x0, x1, y0, y1]
+void shim_project_fwd(int n, const float* p, const float* s, const float* q, const float* cam20,
+                      float max_radius, float* out_f, int* out_i) {
+    FrbCamera cam = cam_from(cam20);
+    for (int i = 0; i < n; ++i) {
+        FrbProjTmp t;
+        FrbProjected o;
+        frb_project_core(p + 3 * i, s + 3 * i, q + 4 * i, cam, t, o);
+        frb_project_finish(cam, max_radius, o);
+        float* f = out_f + 11 * i;
+        f[0] = o.u; f[1] = o.v; f[2] = o.depth; f[3] = o.a; f[4] = o.b; f[5] = o.c; f[6] = o.d;
+        f[7] = o.radius; f[8] = o.A; f[9] = o.B; f[10] = o.C;
+        int* k = out_i + 5 * i;
+        k[0] = o.visible; k[1] = o.x0; k[2] = o.x1; k[3] = o.y0; k[4] = o.y1;
+    }
+}
+
+// g2d: [g_u, g_v, g_A, g_B, g_C, g_depth] per Gaussian (A, B, C are the PRE-SCALED conic)
+void shim_project_bwd(int n, const float* p, const float* s, const float* q, const float* cam20,
+                      const float* g2d, float* gp, float* gs, float* gq) {
+    FrbCamera cam = cam_from(cam20);
+    for (int i = 0; i < n; ++i) {
+        const float* g = g2d + 6 * i;
+        frb_project_bwd_one(p + 3 * i, s + 3 * i, q + 4 * i, cam, g[0], g[1], g[2], g[3], g[4], g[5],
+                            gp + 3 * i, gs + 3 * i, gq + 4 * i);
+    }
+}
+}

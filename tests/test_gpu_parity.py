@@ -1,0 +1,275 @@
+"""GPU tier (-m gpu): the CUDA path through the C-ABI against the oracle and the golden vectors.
+
+Bars: bit-exact for the integer / order work (visibility, rectangles, depth order, 64-bit keys,
+ranges) and for the projected floats; images and depth within 1e-5, gradients within 1e-4
+(max-abs error over max-abs reference per tensor)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fresnel_oracle as fo
+import fresnel_b200
+from fresnel_b200 import _lib
+from fresnel_b200.camera import camera_vector
+from fresnel_b200.renderer import build_bins, _ptr, _stream
+from helpers import GRAD_NAMES, golden_inputs, oracle_camera, rel
+
+pytestmark = pytest.mark.gpu
+IMG_TOL, GRAD_TOL = 1e-5, 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    return torch.device("cuda:0")
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def scene_cases(golden):
+    out = []
+    for name in ("tile_edge_1k_96x80", "tile_rotcam_2k_144x120", "c1_tile_16k_256", "tile_allculled_64"):
+        z = golden(name)
+        W, H = int(z["W"]), int(z["H"])
+        out.append((name, golden_inputs(z), oracle_camera(z["cam"], W, H), W, H))
+    inp = fo.synthetic_cloud(20000, seed=21, s_lo=0.005, s_hi=0.05)
+    out.append(("synthetic_20k_200x136", inp, fo.default_camera(200, 136), 200, 136))
+    return out
+
+
+def gpu_project(inp, cam, W, H, max_radius=64.0):
+    L = _lib.lib()
+    d = dev()
+    n = inp["positions"].shape[0]
+    t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+    rec = torch.empty(n, 12, device=d)
+    rects = torch.empty(n, 4, dtype=torch.int32, device=d)
+    db = torch.empty(n, dtype=torch.int32, device=d)
+    tt = torch.empty(n, dtype=torch.int32, device=d)
+    dbg = torch.empty(n, 8, device=d)
+    camv = camera_vector(cam, W, H)
+    _lib.check(L.frb_project_fwd(n, 1, _ptr(t["positions"]), _ptr(t["scales"]), _ptr(t["rotations"]),
+                                 _ptr(t["colors"]), _ptr(t["opacities"]), camv.ctypes.data, max_radius,
+                                 _ptr(rec), _ptr(rects), _ptr(db), _ptr(tt), _ptr(dbg), _stream()), "project")
+    torch.cuda.synchronize()
+    return rec.cpu().numpy(), rects.cpu().numpy(), db.cpu().numpy().view(np.uint32), tt.cpu().numpy(), \
+        dbg.cpu().numpy()
+
+
+def test_projection_bit_exact(golden):
+    for name, inp, cam, W, H in scene_cases(golden):
+        rec, rects, db, tt, dbg = gpu_project(inp, cam, W, H)
+        pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, 64)
+        assert bits_equal(rec[:, 0], pn["u"]) and bits_equal(rec[:, 1], pn["v"]), name
+        assert bits_equal(rec[:, 6], pn["depth"]), name
+        assert np.array_equal(db, pn["depth_bits"]), name
+        assert bits_equal(dbg[:, 0:4], pn["cov"]), name
+        assert bits_equal(dbg[:, 4], pn["radius"]), name
+        assert np.array_equal(dbg[:, 5] > 0.5, pn["visible"]), name
+        vi = pn["visible"]
+        r = pn["rect"][vi].copy()
+        empty = (r[:, 0] >= r[:, 1]) | (r[:, 2] >= r[:, 3])
+        r[empty] = 0
+        assert np.array_equal(rects[vi], r), name
+        assert np.all(rects[~vi] == 0), name
+        # tiles touched and the packed rectangle in the record
+        tx = (np.maximum(r[:, 1] - 1, 0) // 16 - r[:, 0] // 16 + 1) * (np.maximum(r[:, 3] - 1, 0) // 16 - r[:, 2] // 16 + 1)
+        tx[empty] = 0
+        assert np.array_equal(tt[vi], tx), name
+        lo = rec[:, 7].view(np.uint32)
+        hi = rec[:, 11].view(np.uint32)
+        assert np.array_equal(lo[vi] & 0xFFFF, r[:, 0]) and np.array_equal(lo[vi] >> 16, r[:, 2]), name
+        assert np.array_equal(hi[vi] & 0x7FFF, r[:, 1]) and np.array_equal((hi[vi] >> 16) & 0x7FFF, r[:, 3]), name
+
+
+@pytest.mark.parametrize("m", [0, 1, 31, 2047, 2048, 2049, 100_003, 1_500_000])
+def test_radix_sort_pairs_is_a_stable_sort(m):
+    L = _lib.lib()
+    d = dev()
+    rng = np.random.default_rng(m)
+    # few distinct high words -> many ties on partial-bit sorts, exercising stability
+    keys = (rng.integers(0, 1 << 11, m, dtype=np.uint64) << np.uint64(32)) | rng.integers(0, 1 << 32, m, dtype=np.uint64)
+    vals = np.arange(m, dtype=np.uint32)
+    for begin, end in ((0, 64), (32, 43), (0, 32), (5, 21)):
+        k = torch.from_numpy(keys.view(np.int64).copy()).to(d)
+        v = torch.from_numpy(vals.view(np.int32).copy()).to(d)
+        kt, vt = torch.empty_like(k), torch.empty_like(v)
+        ws = torch.empty(max(L.frb_sort_workspace_bytes(m), 4), dtype=torch.uint8, device=d)
+        _lib.check(L.frb_radix_sort_pairs(m, _ptr(k), _ptr(v), _ptr(kt), _ptr(vt), begin, end, _ptr(ws),
+                                          _stream()), "sort")
+        torch.cuda.synchronize()
+        field = (keys >> np.uint64(begin)) & np.uint64((1 << (end - begin)) - 1)
+        order = np.argsort(field, kind="stable")
+        assert np.array_equal(k.cpu().numpy().view(np.uint64), keys[order]), (m, begin, end)
+        assert np.array_equal(v.cpu().numpy().view(np.uint32), vals[order]), (m, begin, end)
+
+
+@pytest.mark.parametrize("n", [1, 777, 4096, 250_000])
+def test_depth_order_matches_stable_argsort(n):
+    L = _lib.lib()
+    d = dev()
+    rng = np.random.default_rng(n)
+    depth = rng.random(n, dtype=np.float32) * 5
+    depth[rng.integers(0, n, n // 3)] = np.float32(1.25)          # exact ties
+    bits = depth.view(np.uint32)
+    db = torch.from_numpy(bits.view(np.int32).copy()).to(d)
+    order = torch.empty(n, dtype=torch.int32, device=d)
+    ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=d)
+    _lib.check(L.frb_depth_order(n, _ptr(db), _ptr(order), _ptr(ws), _stream()), "depth_order")
+    torch.cuda.synchronize()
+    assert np.array_equal(order.cpu().numpy(), np.argsort(bits, kind="stable").astype(np.int32))
+
+
+@pytest.mark.parametrize("presort", [True, False])
+def test_tile_keys_bit_exact(golden, presort):
+    """Sorted 64-bit (tile | depth) keys, Gaussian ids and tile ranges equal the oracle's, both via
+    depth-presort + tile-bit sort and via a full 64-bit sort of index-ordered instances."""
+    d = dev()
+    for name, inp, cam, W, H in scene_cases(golden):
+        t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+        camv = camera_vector(cam, W, H)[None]
+        b = build_bins(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"], camv, 1, W, H,
+                       64.0, keep_debug=True, sort=presort)
+        torch.cuda.synchronize()
+        pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, 64)
+        assert b.m == pn["keys"].shape[0], name
+        assert np.array_equal(b.keys.cpu().numpy().view(np.uint64), pn["keys"]), name
+        assert np.array_equal(b.sorted_gids.cpu().numpy(), pn["gids"]), name
+        assert np.array_equal(b.ranges.cpu().numpy(), pn["ranges"]), name
+        if presort:
+            # the depth order of the visible Gaussians is the reference's (DR:527-562); culled ones with
+            # negative depth sort differently by bit pattern and never reach a tile
+            o = b.order.cpu().numpy()
+            assert np.array_equal(o[pn["visible"][o]], pn["order"][pn["visible"][pn["order"]]]), name
+        if b.m:
+            rec = b.records.cpu().numpy()
+            assert np.array_equal(b.sorted_records.cpu().numpy()[:b.m].view(np.uint32),
+                                  rec[pn["gids"]].view(np.uint32)), name
+
+
+def render_gpu(z_or_inp, cam, W, H, bg, t_eps, max_radius=64, gimg=None, gdep=None, phases=False, amp=0.25):
+    d = dev()
+    names = GRAD_NAMES + (("phases",) if phases else ())
+    L = {k: z_or_inp[k].detach().clone().to(d).requires_grad_(True) for k in names}
+    ren = fresnel_b200.TileBasedRenderer(W, H, background=bg, max_radius=max_radius, use_phase_blending=phases,
+                                         phase_amplitude=amp, t_eps=t_eps)
+    img, dep, alpha = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
+                          return_depth=True, phases=L["phases"] if phases else None, return_alpha=True)
+    grads = None
+    if gimg is not None:
+        torch.autograd.backward((img, dep), (gimg.to(d), gdep.to(d)))
+        grads = {k: L[k].grad.cpu().numpy() for k in names}
+    return img.detach().cpu().numpy(), dep.detach().cpu().numpy(), alpha.detach().cpu().numpy(), grads
+
+
+@pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
+@pytest.mark.parametrize("name", ["tile_allculled_64", "tile_edge_1k_96x80", "tile_rotcam_2k_144x120",
+                                  "c1_tile_16k_256"])
+def test_tile_renderer_matches_reference_golden(golden, name, t_eps):
+    z = golden(name)
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z)
+    cam = oracle_camera(z["cam"], W, H)
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, tuple(float(x) for x in z["bg"]), t_eps,
+                                        int(z["max_radius"]), torch.from_numpy(z["gimage"]),
+                                        torch.from_numpy(z["gdepth"]))
+    assert img.shape == (3, H, W) and dep.shape == (H, W)
+    assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
+    assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
+    assert rel(alpha, z["alpha"]) < IMG_TOL
+    for k in GRAD_NAMES:
+        assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
+
+
+def test_tile_renderer_matches_oracle_fresh_scene():
+    """Seeded scene not in the fixtures, oracle run live on the CPU (a few seconds)."""
+    W, H = 120, 88
+    inp = fo.synthetic_cloud(1500, seed=33, s_lo=0.01, s_hi=0.07)
+    cam = fo.camera_from_pose(math.radians(-15.0), math.radians(200.0), 96)
+    inp["positions"][:, 2] += 2.0
+    g = torch.Generator().manual_seed(2)
+    gi, gd = torch.rand(3, H, W, generator=g) * 2 - 1, torch.rand(H, W, generator=g) * 2 - 1
+    Lo = {k: inp[k].clone().requires_grad_(True) for k in GRAD_NAMES}
+    io, do, ao = fo.render_tile_based(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                                      Lo["opacities"], cam, W, H, background=(0.3, 0.1, 0.2))
+    ((io * gi).sum() + (do * gd).sum()).backward()
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, (0.3, 0.1, 0.2), 0.0, 64, gi, gd)
+    assert rel(img, io.detach()) < IMG_TOL and rel(dep, do.detach()) < IMG_TOL and rel(alpha, ao.detach()) < IMG_TOL
+    for k in GRAD_NAMES:
+        assert rel(grads[k], Lo[k].grad) < GRAD_TOL, k
+
+
+def test_alpha_gradient_and_batched_views_match_single_views():
+    """render_views(B views) == B single-view calls, and d(alpha) flows (alpha = 1 - T_final)."""
+    d = dev()
+    W, H, B, N = 96, 64, 3, 3000
+    cams = [fo.camera_from_pose(math.radians(10.0 * k), math.radians(40.0 * k), 80) for k in range(B)]
+    clouds = [fo.synthetic_cloud(N, seed=40 + k, s_lo=0.01, s_hi=0.05) for k in range(B)]
+    for c in clouds:
+        c["positions"][:, 2] += 2.0
+    stack = {k: torch.stack([c[k] for c in clouds]).to(d).requires_grad_(True) for k in GRAD_NAMES}
+    img, dep, alpha = fresnel_b200.render_views(stack["positions"], stack["scales"], stack["rotations"],
+                                                stack["colors"], stack["opacities"], cams, W, H,
+                                                background=(0.1, 0.2, 0.3), t_eps=0.0)
+    g = torch.Generator().manual_seed(3)
+    gi = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(d)
+    gd = (torch.rand(B, H, W, generator=g) * 2 - 1).to(d)
+    ga = (torch.rand(B, H, W, generator=g) * 2 - 1).to(d)
+    torch.autograd.backward((img, dep, alpha), (gi, gd, ga))
+    ren = fresnel_b200.TileBasedRenderer(W, H, background=(0.1, 0.2, 0.3), t_eps=0.0)
+    for k in range(B):
+        Ls = {n: clouds[k][n].to(d).requires_grad_(True) for n in GRAD_NAMES}
+        i1, d1, a1 = ren(Ls["positions"], Ls["scales"], Ls["rotations"], Ls["colors"], Ls["opacities"], cams[k],
+                         return_depth=True, return_alpha=True)
+        assert torch.equal(i1, img[k]) and torch.equal(d1, dep[k]) and torch.equal(a1, alpha[k])
+        torch.autograd.backward((i1, d1, a1), (gi[k], gd[k], ga[k]))
+        for n in GRAD_NAMES:
+            assert rel(stack[n].grad[k].cpu(), Ls[n].grad.cpu()) < 1e-5, n
+    # alpha gradient against the oracle on view 0
+    Lo = {n: clouds[0][n].clone().requires_grad_(True) for n in GRAD_NAMES}
+    io, do, ao = fo.render_tile_based(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                                      Lo["opacities"], cams[0], W, H, background=(0.1, 0.2, 0.3))
+    ((io * gi[0].cpu()).sum() + (do * gd[0].cpu()).sum() + (ao * ga[0].cpu()).sum()).backward()
+    for n in GRAD_NAMES:
+        assert rel(stack[n].grad[0].cpu(), Lo[n].grad) < GRAD_TOL, n
+
+
+def test_full_size_properties_config2():
+    """BASELINE.json configs[1] (100k Gaussians, 512x512): properties that need no oracle run.
+    (a) input permutation leaves image / depth bit-identical and permutes the gradients;
+    (b) early termination (default t_eps) stays within the image tolerance of the exhaustive loop;
+    (c) the backward pass is linear in the upstream gradients; (d) alpha = 1 - T in [0, 1]."""
+    d = dev()
+    W = H = 512
+    N = 100_000
+    inp = fo.synthetic_cloud(N, seed=0)
+    cam = fo.default_camera(W)
+    g = torch.Generator().manual_seed(1)
+    gi, gd = (torch.rand(3, H, W, generator=g) * 2 - 1), (torch.rand(H, W, generator=g) * 2 - 1)
+    img0, dep0, a0, gr0 = render_gpu(inp, cam, W, H, (0, 0, 0), 0.0, 64, gi, gd)
+    assert np.isfinite(img0).all() and np.isfinite(dep0).all()
+    assert a0.min() >= 0 and a0.max() <= 1 and img0.min() >= 0 and img0.max() <= 1
+    perm = torch.randperm(N, generator=g)
+    pin = {k: v[perm] for k, v in inp.items()}
+    img1, dep1, a1, gr1 = render_gpu(pin, cam, W, H, (0, 0, 0), 0.0, 64, gi, gd)
+    db = fo.depth_bits(fo.project(inp["positions"], inp["scales"], inp["rotations"], cam)["depth"])
+    if len(np.unique(db)) == N:                       # tie-free: order is input-order independent
+        assert np.array_equal(img0, img1) and np.array_equal(dep0, dep1)
+    else:
+        assert rel(img1, img0) < IMG_TOL and rel(dep1, dep0) < IMG_TOL
+    for k in GRAD_NAMES:
+        assert rel(gr1[k], gr0[k][perm.numpy()]) < 2e-5, k
+    img2, dep2, a2, gr2 = render_gpu(inp, cam, W, H, (0, 0, 0), fresnel_b200.DEFAULT_T_EPS, 64, gi, gd)
+    assert rel(img2, img0) < IMG_TOL and rel(dep2, dep0) < IMG_TOL and rel(a2, a0) < IMG_TOL
+    for k in GRAD_NAMES:
+        assert rel(gr2[k], gr0[k]) < GRAD_TOL, k
+    _, _, _, gr3 = render_gpu(inp, cam, W, H, (0, 0, 0), 0.0, 64, gi * 2.0, gd * -0.5)
+    _, _, _, gra = render_gpu(inp, cam, W, H, (0, 0, 0), 0.0, 64, gi, gd * 0.0)
+    _, _, _, grb = render_gpu(inp, cam, W, H, (0, 0, 0), 0.0, 64, gi * 0.0, gd)
+    for k in GRAD_NAMES:
+        assert rel(gr3[k], 2.0 * gra[k] - 0.5 * grb[k]) < 2e-5, k
