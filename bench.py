@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: differentiable Gaussian-splat render, forward + backward.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port)
+
+Workload (BASELINE.json configs[1]): 100,000 synthetic Gaussians, 512x512, one view per rank,
+forward + backward with upstream gradients for image and depth.  A "step" is one frame.
+At N > 1 every rank renders its own view of its own cloud (the path shards by view, no data-path
+collective) -> weak scaling, value = frames of all ranks / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the definitions of
+value / e2e / roofline / cpu_baseline.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "render fwd+bwd frames/sec at 512x512 (100k Gaussians)"
+UNIT = "frames/s"
+N_GAUSS = 100_000
+RES = 512
+GRAD_NAMES = ("positions", "scales", "rotations", "colors", "opacities")
+
+
+def synthetic_cloud(n, seed):
+    """SURVEY.md section 8d inputs (same generator as oracle.fresnel_oracle.synthetic_cloud)."""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.randn(n, 3, generator=g) * 0.5
+    pos[:, 2] -= 2.0
+    return dict(positions=pos,
+                scales=torch.rand(n, 3, generator=g) * (0.03 - 0.005) + 0.005,
+                rotations=torch.randn(n, 4, generator=g),
+                colors=torch.rand(n, 3, generator=g),
+                opacities=torch.rand(n, generator=g) * 0.8 + 0.1)
+
+
+def upstream(seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(3, RES, RES, generator=g) * 2 - 1, torch.rand(RES, RES, generator=g) * 2 - 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower() == "active":
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is a Python module and cannot travel to the GPU box)
+# --------------------------------------------------------------------------------------
+def cpu_frame_time(n_sample, seed=0):
+    """Seconds for one fwd+bwd frame of the first n_sample Gaussians of the workload, oracle port."""
+    from oracle import fresnel_oracle as fo
+    inp = synthetic_cloud(N_GAUSS, seed)
+    L = {k: inp[k][:n_sample].clone().requires_grad_(True) for k in GRAD_NAMES}
+    gi, gd = upstream()
+    cam = fo.default_camera(RES)
+    t0 = time.perf_counter()
+    img, dep, _ = fo.render_tile_based(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"],
+                                       cam, RES, RES)
+    torch.autograd.backward((img, dep), (gi, gd))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_probe = cpu_frame_time(200)
+    n_s = int(max(200, min(N_GAUSS, 200 * budget_s / max(t_probe, 1e-3) * 0.6)))
+    t = cpu_frame_time(n_s)
+    est = t * (N_GAUSS / n_s)
+    return {"value": 1.0 / est, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": (f"oracle port (reference is Python; restated in oracle/fresnel_oracle.py), first {n_s} of "
+                       f"{N_GAUSS} Gaussians at {RES}x{RES}, fwd+bwd {t:.2f} s, scaled linearly in N "
+                       "(favours the CPU: its backward cost grows faster than N)")}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total = args.steps + args.warmup
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(total, 1)))
+    t_probe = cpu_frame_time(200)
+    n_s = int(max(200, min(N_GAUSS, 200 * per_step_budget / max(t_probe, 1e-3) * 0.6)))
+    for _ in range(args.warmup):
+        cpu_frame_time(n_s)
+    times = [cpu_frame_time(n_s) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    est = t * (N_GAUSS / n_s)
+    value = 1.0 / est
+    sample = (f"oracle port of TileBasedRenderer (reference is Python and absent from the GPU box), first {n_s} "
+              f"of {N_GAUSS} Gaussians at {RES}x{RES} per step, fwd+bwd {t:.2f} s/step, scaled linearly in N")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single-view render fwd+bwd, {N_GAUSS} Gaussians, {RES}x{RES} (BASELINE configs[1])"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--t-eps", type=float, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import fresnel_b200
+    from fresnel_b200 import _lib
+    from fresnel_b200.renderer import StageTimer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    t_eps = fresnel_b200.DEFAULT_T_EPS if args.t_eps is None else args.t_eps
+    ren = fresnel_b200.TileBasedRenderer(RES, RES, t_eps=t_eps)
+    cam = fresnel_b200.Camera(0.8 * RES, 0.8 * RES, RES / 2, RES / 2, RES, RES)
+
+    host = synthetic_cloud(N_GAUSS, seed=rank)            # each rank: its own view / cloud
+    gi_h, gd_h = upstream(1 + rank)
+    host_pinned = {k: v.pin_memory() for k, v in host.items()}
+    gi_p, gd_p = gi_h.pin_memory(), gd_h.pin_memory()
+    resident = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+    gi, gd = gi_h.to(dev), gd_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        for v in resident.values():
+            v.grad = None
+        img, dep = ren(resident["positions"], resident["scales"], resident["rotations"], resident["colors"],
+                       resident["opacities"], cam, return_depth=True)
+        torch.autograd.backward((img, dep), (gi, gd))
+
+    out_pinned = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+    img_p, dep_p = torch.empty(3, RES, RES).pin_memory(), torch.empty(RES, RES).pin_memory()
+
+    def step_e2e():
+        t = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host_pinned.items()}
+        g1, g2 = gi_p.to(dev, non_blocking=True), gd_p.to(dev, non_blocking=True)
+        img, dep = ren(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"], cam,
+                       return_depth=True)
+        torch.autograd.backward((img, dep), (g1, g2))
+        img_p.copy_(img.detach(), non_blocking=True)
+        dep_p.copy_(dep.detach(), non_blocking=True)
+        for k in GRAD_NAMES:
+            out_pinned[k].copy_(t[k].grad, non_blocking=True)
+
+    h2d = sum(v.numel() * 4 for v in host.values()) + gi_h.numel() * 4 + gd_h.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host.values()) + 4 * RES * RES * 4
+
+    def timed(fn, steps):
+        """Per-step CUDA events on the launching stream; L2 flushed (256 MiB write) between steps."""
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    for _ in range(max(2, args.warmup // 2)):
+        step_e2e()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.frb_launch_count()
+    barrier()
+    ms = timed(step_resident, args.steps)
+    barrier()
+    launches = L.frb_launch_count() - launches0
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-stage timing for the roofline line (same workload, instrumented pass)
+    with StageTimer() as st:
+        timed(step_resident, args.steps)
+    stages = {k: sum(v) / len(v) for k, v in st.summary().items()}
+
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, tot_e2e_ms = tot.tolist()
+
+    if rank == 0:
+        # workload counts for the algorithmic bytes: M = tile instances
+        with torch.no_grad():
+            from fresnel_b200.renderer import build_bins
+            from fresnel_b200.camera import camera_vector
+            b = build_bins(resident["positions"].detach(), resident["scales"].detach(),
+                           resident["rotations"].detach(), resident["colors"].detach(),
+                           resident["opacities"].detach(), camera_vector(cam, RES, RES)[None], 1, RES, RES, 64.0)
+            M = b.m
+        peak, peak_src = peaks()
+        HW, N = RES * RES, N_GAUSS
+        alg = {   # algorithmic bytes per launch of each stage
+            "frb_project_fwd": 60 * N + 56 * N,
+            "frb_depth_order": 4 * (2 * 8 * N) + 8 * N,
+            "frb_tile_offsets": 3 * 4 * N,
+            "frb_bin_emit": 20 * N + 12 * M,
+            "frb_radix_sort_pairs": 2 * (2 * 12 * M),
+            "frb_tile_ranges": 8 * M,
+            "frb_gather_records": 4 * M + 96 * M,
+            "frb_composite_fwd": 48 * M + 28 * HW,
+            "frb_composite_bwd": 52 * M + 24 * HW + 48 * N,
+            "frb_project_bwd": 56 * N + 48 * N + 56 * N,
+        }
+        top = max(stages, key=stages.get)
+        achieved = alg[top] / (stages[top] * 1e-3) / 1e9
+        frame_bytes = 168 * N + 36 * HW + 96 * M
+        value = world * args.steps / (tot_ms * 1e-3)
+        e2e = world * args.steps / (tot_e2e_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"single-view render fwd+bwd, {N} Gaussians, {RES}x{RES} (BASELINE configs[1]); "
+                                   "one view per rank",
+                       "tile_instances": M, "t_eps": t_eps,
+                       "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
+                       "parallelism": f"views sharded over {world} rank(s), no data-path collective"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": tot_e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[top], "kernel_ms": stages[top],
+                         "frame_algorithmic_bytes": frame_bytes,
+                         "frame_frac": frame_bytes / (tot_ms / args.steps * 1e-3) / 1e9 / peak,
+                         "stage_ms": {k: round(v, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
+                         "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) for k, v in stages.items()}},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

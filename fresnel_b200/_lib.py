@@ -18,6 +18,7 @@ P = c_void_p
 _SIGNATURES = {
     "frb_version": (c_int, []),
     "frb_error_string": (c_char_p, [c_int]),
+    "frb_launch_count": (ctypes.c_ulonglong, []),
     "frb_project_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, c_float, P, P, P, P, P, P]),
     "frb_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "frb_sort_workspace_bytes": (c_size_t, [c_int]),

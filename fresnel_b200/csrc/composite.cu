@@ -316,6 +316,7 @@ extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32
     composite_fwd_kernel<false><<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, nullptr, phase_amplitude,
         bg, t_eps, image, depth, alpha, state_T, state_n);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -338,6 +339,7 @@ extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32
     composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, bg,
         state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }

@@ -29,6 +29,9 @@ int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs)
         if (_e != cudaSuccess) return (int)_e;     \
     } while (0)
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+void frb_note_launches(int k);
+
 static inline int frb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #if defined(__CUDACC__)

@@ -6,6 +6,11 @@
 // HBM-bound, one thread per Gaussian: 56 B in (+4 B opacity), 48 B record + 8 B sort inputs out.
 #include "frb_common.cuh"
 
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+void frb_note_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+extern "C" unsigned long long frb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs) {
     if (n < 0 || n_views < 1 || n_views > FRB_MAX_VIEWS || camera_host == nullptr) return FRB_E_INVALID;
     if (n % n_views != 0) return FRB_E_INVALID;
@@ -111,6 +116,7 @@ extern "C" int frb_project_fwd(int n, int n_views, const float* positions, const
     frb_project_fwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
         n, vs, positions, scales, rotations, colors, opacities, max_radius, (float4*)records,
         (int4*)rects, depth_bits, tiles_touched, (float4*)debug);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -128,6 +134,7 @@ extern "C" int frb_project_bwd(int n, int n_views, const float* positions, const
     frb_project_bwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
         n, vs, positions, scales, rotations, (const float4*)grad2d, g_positions, g_scales,
         (float4*)g_rotations, g_colors, g_opacities);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }

@@ -169,6 +169,7 @@ int radix_sort_impl(int m, KeyT* keys, uint32_t* vals, KeyT* keys_tmp, uint32_t*
         scan_single_block_kernel<<<1, 1024, 0, st>>>(hist, RADIX * n_blocks);
         radix_scatter_kernel<KeyT><<<n_blocks, SORT_THREADS, 0, st>>>(m, kin, vin, kout, vout, bit, mask, hist,
                                                                       n_blocks);
+        frb_note_launches(3);
         FRB_LAUNCH_CHECK();
         KeyT* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
@@ -346,6 +347,7 @@ extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* orde
     uint32_t* vals_tmp = (uint32_t*)(w + 2 * a);
     uint32_t* hist = (uint32_t*)(w + 3 * a);
     iota_copy_kernel<<<frb_div_up(n, 256), 256, 0, st>>>(n, depth_bits, keys, order);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return radix_sort_impl<uint32_t>(n, keys, order, keys_tmp, vals_tmp, 0, 32, hist, st);
 }
@@ -369,6 +371,7 @@ extern "C" int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint
     offsets_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, sums);
     scan_single_block_kernel<<<1, 1024, 0, st>>>(sums, nb);
     offsets_write_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, sums, offsets);
+    frb_note_launches(3);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -385,6 +388,7 @@ extern "C" int frb_bin_emit(int n, int n_views, int width, int height, const flo
     bin_emit_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
         n, n / n_views, tiles_x, tiles_x * tiles_y, (const float4*)records, depth_bits, order, offsets, keys,
         gids);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -396,6 +400,7 @@ extern "C" int frb_tile_ranges(int m, const uint64_t* keys, int n_tiles, int32_t
     if (m == 0) return 0;
     if (!keys) return FRB_E_INVALID;
     tile_ranges_kernel<<<frb_div_up(m, 256), 256, 0, st>>>(m, keys, (int2*)ranges);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -408,6 +413,7 @@ extern "C" int frb_gather_records(int m, const uint32_t* gids, const float* reco
     if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
     gather_records_kernel<<<frb_div_up(3ll * m, 256), 256, 0, (cudaStream_t)stream>>>(
         m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }

@@ -33,6 +33,47 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class StageTimer:
+    """Per-stage CUDA-event timing of the C-ABI calls (used by bench.py for the roofline line).
+
+    with StageTimer() as t: ...render...; t.summary() -> {stage: [ms, ...]} after a synchronize.
+    Events are recorded on the current stream, the one every kernel is launched on.
+    """
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        global _TIMER
+        self._prev, _TIMER = _TIMER, self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = self._prev
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+_TIMER: Optional[StageTimer] = None
+
+
+def _call(name, fn, *args):
+    if _TIMER is None:
+        _lib.check(fn(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _lib.check(fn(*args), name)
+    b.record()
+    _TIMER.events.append((name, a, b))
+
+
 def _check_inputs(**tensors):
     out = {}
     dev = None
@@ -85,21 +126,19 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     b.depth_bits = torch.empty(n, **i32)
     b.touched = torch.empty(n, **i32)
     b.rects = torch.empty(n, 4, **i32) if keep_debug else None
-    _lib.check(L.frb_project_fwd(n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), _ptr(colors),
+    _call("frb_project_fwd", L.frb_project_fwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), _ptr(colors),
                                  _ptr(opacities), cam.ctypes.data, float(max_radius), _ptr(b.records),
-                                 _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st),
-               "frb_project_fwd")
+                                 _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
 
     b.order = None
     if sort and n > 0:
         b.order = torch.empty(n, **i32)
         ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=dev)
-        _lib.check(L.frb_depth_order(n, _ptr(b.depth_bits), _ptr(b.order), _ptr(ws), st), "frb_depth_order")
+        _call("frb_depth_order", L.frb_depth_order, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(ws), st)
 
     offsets = torch.empty(n + 1, **i32)
     ws = torch.empty(max(L.frb_scan_workspace_bytes(n), 4), dtype=torch.uint8, device=dev)
-    _lib.check(L.frb_tile_offsets(n, _ptr(b.touched), _ptr(b.order), _ptr(offsets), _ptr(ws), st),
-               "frb_tile_offsets")
+    _call("frb_tile_offsets", L.frb_tile_offsets, n, _ptr(b.touched), _ptr(b.order), _ptr(offsets), _ptr(ws), st)
     m = int(offsets[n].item())          # the one host sync of the forward pass
     b.m = m
 
@@ -109,23 +148,21 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     b.sorted_records = torch.empty(max(m, 1), RECORD_FLOATS, dtype=torch.float32, device=dev)
     b.sorted_phases = None
     if m > 0:
-        _lib.check(L.frb_bin_emit(n, n_views, width, height, _ptr(b.records), _ptr(b.depth_bits),
-                                  _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st),
-                   "frb_bin_emit")
+        _call("frb_bin_emit", L.frb_bin_emit, n, n_views, width, height, _ptr(b.records), _ptr(b.depth_bits),
+                                  _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st)
         keys_tmp = torch.empty(m, dtype=torch.int64, device=dev)
         vals_tmp = torch.empty(m, **i32)
         ws = torch.empty(L.frb_sort_workspace_bytes(m), dtype=torch.uint8, device=dev)
         tile_bits = max(1, int(math.ceil(math.log2(max(n_tiles, 2)))))
         begin = 32 if sort else 0
-        _lib.check(L.frb_radix_sort_pairs(m, _ptr(b.keys), _ptr(b.sorted_gids), _ptr(keys_tmp),
-                                          _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st),
-                   "frb_radix_sort_pairs")
-    _lib.check(L.frb_tile_ranges(m, _ptr(b.keys), n_tiles, _ptr(b.ranges), st), "frb_tile_ranges")
+        _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs, m, _ptr(b.keys), _ptr(b.sorted_gids), _ptr(keys_tmp),
+                                          _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
+    _call("frb_tile_ranges", L.frb_tile_ranges, m, _ptr(b.keys), n_tiles, _ptr(b.ranges), st)
     if m > 0:
         if phases is not None:
             b.sorted_phases = torch.empty(m, dtype=torch.float32, device=dev)
-        _lib.check(L.frb_gather_records(m, _ptr(b.sorted_gids), _ptr(b.records), _ptr(b.sorted_records),
-                                        _ptr(phases), _ptr(b.sorted_phases), st), "frb_gather_records")
+        _call("frb_gather_records", L.frb_gather_records, m, _ptr(b.sorted_gids), _ptr(b.records), _ptr(b.sorted_records),
+                                        _ptr(phases), _ptr(b.sorted_phases), st)
     elif phases is not None:
         b.sorted_phases = torch.empty(1, dtype=torch.float32, device=dev)
     return b
@@ -154,10 +191,10 @@ class _TileRenderFn(torch.autograd.Function):
         if phases is not None:
             n_tiles = bins.ranges.shape[0]
             ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m, n_tiles), 1), **f32)
-        _lib.check(L.frb_composite_fwd(n_views, width, height, _ptr(bins.ranges), _ptr(bins.sorted_records),
+        _call("frb_composite_fwd", L.frb_composite_fwd, n_views, width, height, _ptr(bins.ranges), _ptr(bins.sorted_records),
                                        _ptr(bins.sorted_phases), float(phase_amp), bg_host.ctypes.data,
                                        float(t_eps), _ptr(image), _ptr(depth), _ptr(alpha), _ptr(state_T),
-                                       _ptr(state_n), _ptr(ckpt), st), "frb_composite_fwd")
+                                       _ptr(state_n), _ptr(ckpt), st)
         ctx.cfg = cfg
         ctx.n = n
         ctx.has_phase = phases is not None
@@ -184,20 +221,20 @@ class _TileRenderFn(torch.autograd.Function):
         grad2d = torch.zeros(n, RECORD_FLOATS, **f32)
         g_phases = torch.zeros(n, **f32) if ctx.has_phase else None
         bg_host = np.asarray(bg, np.float32)
-        _lib.check(L.frb_composite_bwd(n_views, width, height, _ptr(ranges), _ptr(sorted_records),
+        _call("frb_composite_bwd", L.frb_composite_bwd, n_views, width, height, _ptr(ranges), _ptr(sorted_records),
                                        _ptr(sorted_gids), _ptr(sorted_phases) if ctx.has_phase else None,
                                        float(phase_amp), bg_host.ctypes.data, _ptr(state_T), _ptr(state_n),
                                        _ptr(ckpt) if ctx.has_phase else None, _ptr(g_image), _ptr(g_depth),
-                                       _ptr(g_alpha), _ptr(grad2d), _ptr(g_phases), st), "frb_composite_bwd")
+                                       _ptr(g_alpha), _ptr(grad2d), _ptr(g_phases), st)
         g_pos = torch.empty(n, 3, **f32)
         g_scl = torch.empty(n, 3, **f32)
         g_rot = torch.empty(n, 4, **f32)
         g_col = torch.empty(n, 3, **f32)
         g_opa = torch.empty(n, **f32)
         cam = np.ascontiguousarray(cam_vecs, np.float32)
-        _lib.check(L.frb_project_bwd(n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), cam.ctypes.data,
+        _call("frb_project_bwd", L.frb_project_bwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), cam.ctypes.data,
                                      _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col),
-                                     _ptr(g_opa), st), "frb_project_bwd")
+                                     _ptr(g_opa), st)
         return g_pos, g_scl, g_rot, g_col, g_opa, g_phases, None
 
 

@@ -68,6 +68,8 @@ extern "C" {
 
 int frb_version(void);
 const char* frb_error_string(int code);
+/* Number of CUDA kernels launched by this library since it was loaded. */
+unsigned long long frb_launch_count(void);
 
 /* ---- projection ------------------------------------------------------- */
 /* rects, debug nullable.  debug: [cov a, b, c, d, radius, visible, 0, 0] per Gaussian. */
