@@ -149,32 +149,53 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 //   w_i = gC . rgb_i + gD * depth_i ; T_i = T_{i+1} / (1 - alpha_i) ;
 //   dL/dalpha_i = T_i w_i - (S + T_final X) / (1 - alpha_i),  S = sum_{j>i} c_j w_j,
 //   X = gC . bg - gA  (alpha_out = 1 - T_final)
-// gated by 0 <= g*o <= 0.99 (torch.clamp backward is inclusive).  The ten per-Gaussian
-// partials are summed over the warp with shuffles and added with one atomic per warp.
+// gated by 0 <= g*o <= 0.99 (torch.clamp backward is inclusive).
+//
+// The per-Gaussian sums over pixels are formed WITHOUT warp shuffles or per-pixel atomics.  Each
+// warp owns 32 pixels (a 16x2 block) and handles 32 Gaussians at a time in two phases:
+//   phase 1 (lane = pixel): walk the 32 Gaussians back to front, carrying (T, S); per pair store
+//           (c, gated dL/dalpha) into a 32x32 shared-memory tile;
+//   phase 2 (lane = Gaussian): read the tile transposed, walk the 32 pixels and accumulate the ten
+//           gradient sums of that Gaussian in registers.
+// The eight warps' partial sums are added across warps through shared memory and leave the CTA as
+// ONE atomic add per Gaussian value per tile.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS)
+constexpr int BWD_WARPS = CTA_THREADS / 32;
+constexpr int PAIR_STRIDE = 33;                 // float2 row stride: conflict-free both ways
+constexpr int N_GRADS = 10;
+
+struct BwdSmem {
+    StageBuf stage[STAGES];
+    float2 pair[BWD_WARPS][32 * PAIR_STRIDE];
+    float part[BWD_WARPS][N_GRADS][BATCH];
+    float4 pixc[BWD_WARPS][32];
+    uint32_t gid[STAGES][BATCH];
+    uint64_t full_bar[STAGES];
+    int max_n;
+};
+
+__global__ void __launch_bounds__(CTA_THREADS, 2)
 composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
                      const float4* __restrict__ sorted_records, const uint32_t* __restrict__ sorted_gids,
                      float3 bg, const float* __restrict__ state_T,
                      const int* __restrict__ state_n, const float* __restrict__ g_image,
                      const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
                      float* __restrict__ grad2d) {
-    __shared__ StageBuf stage[STAGES];
-    __shared__ uint32_t gid_s[STAGES][BATCH];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ int max_n_s;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
     const int tile = blockIdx.x;
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = tx * TILE + (threadIdx.x & (TILE - 1));
     const int py = ty * TILE + (threadIdx.x / TILE);
     const bool in_image = (px < width) && (py < height);
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
     const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
-    const int lane = threadIdx.x & 31;
+    const float wbx = (float)(tx * TILE), wby = (float)(ty * TILE + 2 * warp);   // warp's pixel block origin
 
     const int2 range = ranges[tile];
 
@@ -194,9 +215,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         gd = g_depth ? g_depth[pix] : 0.0f;
         ga = g_alpha ? g_alpha[pix] : 0.0f;
     }
-    if (threadIdx.x == 0) max_n_s = 0;
+    sm.pixc[warp][lane] = make_float4(gr, gg, gb, gd);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) frb_mbar_init(&full_bar[s], 1);
+        sm.max_n = 0;
+        for (int s = 0; s < STAGES; ++s) frb_mbar_init(&sm.full_bar[s], 1);
         frb_mbar_fence_init();
     }
     __syncthreads();
@@ -204,21 +226,21 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         int wmax = my_n;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        if (lane == 0) atomicMax(&max_n_s, wmax);
+        if (lane == 0) atomicMax(&sm.max_n, wmax);
     }
     __syncthreads();
-    const int count = min(max_n_s, range.y - range.x);
+    const int count = min(sm.max_n, range.y - range.x);
     const int n_batches = (count + BATCH - 1) / BATCH;
     if (n_batches == 0) return;
 
-    // batches are visited last to first; ring slot k holds visit k
+    // batches are visited last to first; ring slot (visit % STAGES) holds visit
     auto issue = [&](int visit) {
         int b = n_batches - 1 - visit;
         int s = visit % STAGES;
         int cnt = min(BATCH, count - b * BATCH);
-        frb_mbar_expect_tx(&full_bar[s], cnt * RECORD_BYTES);
-        frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
-                        &full_bar[s]);
+        frb_mbar_expect_tx(&sm.full_bar[s], cnt * RECORD_BYTES);
+        frb_tma_load_1d(sm.stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
+                        &sm.full_bar[s]);
     };
     if (threadIdx.x == 0)
         for (int v = 0; v < STAGES && v < n_batches; ++v) issue(v);
@@ -227,62 +249,104 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const float TX = T_final * X;
     float T = T_final;
     float S = 0.0f;
+    float2* my_pair = sm.pair[warp];
 
     for (int visit = 0; visit < n_batches; ++visit) {
         const int b = n_batches - 1 - visit;
         const int s = visit % STAGES;
         const int cnt = min(BATCH, count - b * BATCH);
-        if (threadIdx.x < cnt) gid_s[s][threadIdx.x] = sorted_gids[range.x + b * BATCH + threadIdx.x];
-        frb_mbar_wait(&full_bar[s], (visit / STAGES) & 1);
-        __syncthreads();  // gid_s visible
-        const float4* rec = stage[s].rec;
-        for (int j = cnt - 1; j >= 0; --j) {
-            float4 r0 = rec[3 * j + 0], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-            const int idx = b * BATCH + j;
-            bool active = (idx < my_n) &&
-                          rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+        if (threadIdx.x < cnt) sm.gid[s][threadIdx.x] = sorted_gids[range.x + b * BATCH + threadIdx.x];
+        frb_mbar_wait(&sm.full_bar[s], (visit / STAGES) & 1);
+        const float4* rec = sm.stage[s].rec;
+
+        for (int sb = (cnt - 1) >> 5; sb >= 0; --sb) {
+            const int sub_cnt = min(32, cnt - sb * 32);
+            // ---- phase 1: lane = pixel -------------------------------------------------
+            uint32_t gmask = 0;
+            for (int j = sub_cnt - 1; j >= 0; --j) {
+                const int jb = sb * 32 + j;
+                float4 r1 = rec[3 * jb + 1], r2 = rec[3 * jb + 2];
+                const int idx = b * BATCH + jb;
+                bool active = (idx < my_n) &&
+                              rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                if (!__any_sync(0xffffffffu, active)) continue;
+                gmask |= 1u << j;
+                float2 out = make_float2(0.f, 0.f);
+                if (active) {
+                    float4 r0 = rec[3 * jb + 0];
+                    float dx = fpx - r0.x, dy = fpy - r0.y;
+                    float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                    float g = frb_ex2(power);
+                    float araw = g * r1.y;
+                    float a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
+                    float inv_om = __fdividef(1.0f, 1.0f - a);
+                    float Ti = T * inv_om;
+                    float c = a * Ti;
+                    float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                    float dalpha = Ti * w - (S + TX) * inv_om;
+                    S = fmaf(c, w, S);
+                    T = Ti;
+                    out.x = c;
+                    out.y = (araw >= 0.0f && araw <= FRB_ALPHA_MAX) ? dalpha : 0.0f;
+                }
+                my_pair[j * PAIR_STRIDE + lane] = out;
+            }
+            __syncwarp();
+            // ---- phase 2: lane = Gaussian ------------------------------------------------
             float d_u = 0.f, d_v = 0.f, d_A = 0.f, d_B = 0.f, d_C = 0.f, d_o = 0.f, d_dep = 0.f, d_r = 0.f,
                   d_g = 0.f, d_b = 0.f;
-            if (active) {
-                float dx = fpx - r0.x, dy = fpy - r0.y;
-                float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
-                float g = frb_ex2(power);
-                float araw = g * r1.y;
-                float a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
-                float om = 1.0f - a;
-                float inv_om = __fdividef(1.0f, om);
-                float Ti = T * inv_om;
-                float c = a * Ti;
-                float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
-                float dalpha = Ti * w - (S + TX) * inv_om;
-                S = fmaf(c, w, S);
-                T = Ti;
-                d_r = c * gr; d_g = c * gg; d_b = c * gb; d_dep = c * gd;
-                if (araw >= 0.0f && araw <= FRB_ALPHA_MAX) {
-                    d_o = g * dalpha;
-                    float dpow = r1.y * dalpha * g * FRB_LN2;   // dL/d(power): g = 2^power
-                    d_A = dx * dx * dpow;
-                    d_B = dx * dy * dpow;
-                    d_C = dy * dy * dpow;
-                    d_u = -(2.0f * r0.z * dx + r0.w * dy) * dpow;
-                    d_v = -(r0.w * dx + 2.0f * r1.x * dy) * dpow;
+            if (gmask != 0) {
+                const bool mine = (gmask >> lane) & 1u;
+                const int jb = sb * 32 + (mine ? lane : 0);
+                const float4 r0 = rec[3 * jb + 0], r1 = rec[3 * jb + 1];
+                const float oln2 = r1.y * FRB_LN2;
+                const float2* row = my_pair + lane * PAIR_STRIDE;
+                const float4* pc = sm.pixc[warp];
+                if (mine) {
+#pragma unroll 8
+                    for (int p = 0; p < 32; ++p) {
+                        float2 cd = row[p];
+                        float4 gpix = pc[p];
+                        float dx = (wbx + (float)(p & 15)) - r0.x;
+                        float dy = (wby + (float)(p >> 4)) - r0.y;
+                        float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                        float gda = (cd.y != 0.0f) ? frb_ex2(power) * cd.y : 0.0f;   // g * gated dL/dalpha
+                        d_r = fmaf(cd.x, gpix.x, d_r);
+                        d_g = fmaf(cd.x, gpix.y, d_g);
+                        d_b = fmaf(cd.x, gpix.z, d_b);
+                        d_dep = fmaf(cd.x, gpix.w, d_dep);
+                        d_o += gda;
+                        float dpow = gda * oln2;                                      // dL/d(power): g = 2^power
+                        d_A = fmaf(dx * dx, dpow, d_A);
+                        d_B = fmaf(dx * dy, dpow, d_B);
+                        d_C = fmaf(dy * dy, dpow, d_C);
+                        d_u = fmaf(2.0f * r0.z * dx + r0.w * dy, dpow, d_u);
+                        d_v = fmaf(r0.w * dx + 2.0f * r1.x * dy, dpow, d_v);
+                    }
                 }
             }
-            if (__any_sync(0xffffffffu, active)) {
-                d_u = frb_warp_sum(d_u); d_v = frb_warp_sum(d_v);
-                d_A = frb_warp_sum(d_A); d_B = frb_warp_sum(d_B); d_C = frb_warp_sum(d_C);
-                d_o = frb_warp_sum(d_o); d_dep = frb_warp_sum(d_dep);
-                d_r = frb_warp_sum(d_r); d_g = frb_warp_sum(d_g); d_b = frb_warp_sum(d_b);
-                if (lane == 0) {
-                    float* g2 = grad2d + (size_t)gid_s[s][j] * FRB_GRAD_FLOATS;
-                    atomicAdd(g2 + 0, d_u); atomicAdd(g2 + 1, d_v); atomicAdd(g2 + 2, d_A);
-                    atomicAdd(g2 + 3, d_B); atomicAdd(g2 + 4, d_C); atomicAdd(g2 + 5, d_o);
-                    atomicAdd(g2 + 6, d_dep); atomicAdd(g2 + 8, d_r); atomicAdd(g2 + 9, d_g);
-                    atomicAdd(g2 + 10, d_b);
+            {
+                float* pw = &sm.part[warp][0][sb * 32 + lane];
+                pw[0 * BATCH] = -d_u; pw[1 * BATCH] = -d_v; pw[2 * BATCH] = d_A; pw[3 * BATCH] = d_B;
+                pw[4 * BATCH] = d_C; pw[5 * BATCH] = d_o; pw[6 * BATCH] = d_dep; pw[7 * BATCH] = d_r;
+                pw[8 * BATCH] = d_g; pw[9 * BATCH] = d_b;
+            }
+            __syncwarp();   // pair tile is reused by the next sub-block
+        }
+        __syncthreads();    // partial sums of all warps (and gid) visible
+        for (int i = threadIdx.x; i < N_GRADS * BATCH; i += CTA_THREADS) {
+            const int v = i / BATCH, jb = i - v * BATCH;
+            if (jb < cnt) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < BWD_WARPS; ++w) sum += sm.part[w][v][jb];
+                if (sum != 0.0f) {
+                    const int slot = v + (v >= 7 ? 1 : 0);      // [du dv dA dB | dC do ddepth _ | dr dg db _]
+                    atomicAdd(grad2d + (size_t)sm.gid[s][jb] * FRB_GRAD_FLOATS + slot, sum);
                 }
             }
         }
-        __syncthreads();  // stage s and gid_s[s] are free
+        __syncthreads();    // stage s, gid[s] and part are free
         if (threadIdx.x == 0 && visit + STAGES < n_batches) issue(visit + STAGES);
     }
 }
@@ -336,7 +400,13 @@ extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+    static bool attr_set = false;
+    if (!attr_set) {
+        FRB_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(BwdSmem)));
+        attr_set = true;
+    }
+    composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, bg,
         state_T, state_n, g_image, g_depth, g_alpha, grad2d);
     frb_note_launches(1);
