@@ -304,6 +304,7 @@ def main():
             "frb_radix_sort_pairs": 2 * (2 * 12 * M),
             "frb_tile_ranges": 8 * M,
             "frb_gather_records": 4 * M + 96 * M,
+            "frb_ranges_and_gather": 8 * M + 4 * M + 96 * M,
             "frb_composite_fwd": 48 * M + 28 * HW,
             "frb_composite_bwd": 52 * M + 24 * HW + 48 * N,
             "frb_project_bwd": 56 * N + 48 * N + 56 * N,
@@ -332,7 +333,7 @@ def main():
                          "frame_algorithmic_bytes": frame_bytes,
                          "frame_frac": frame_bytes / (tot_ms / args.steps * 1e-3) / 1e9 / peak,
                          "stage_ms": {k: round(v, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
-                         "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) for k, v in stages.items()}},
+                         "stage_gbs": {k: round(alg[k] / (v * 1e-3) / 1e9, 1) for k, v in stages.items() if k in alg}},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()

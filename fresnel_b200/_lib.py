@@ -30,6 +30,7 @@ _SIGNATURES = {
     "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "frb_tile_ranges": (c_int, [c_int, P, c_int, P, P]),
     "frb_gather_records": (c_int, [c_int, P, P, P, P, P, P]),
+    "frb_ranges_and_gather": (c_int, [c_int, P, P, c_int, P, P, P, P, P, P]),
     "frb_phase_ckpt_floats": (c_size_t, [c_int, c_int]),
     "frb_composite_fwd": (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),

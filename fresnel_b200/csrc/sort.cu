@@ -7,11 +7,15 @@
 // that are not already ordered: Gaussians are first put in stable depth order (32-bit keys, N
 // elements), instances are emitted in that order, and the 64-bit keys are then sorted on the
 // tile bits only.  The result is bit-identical to a full 64-bit stable sort of instances emitted
-// in index order (tests/test_binning.py checks both against oracle tile_keys()).
-// Nearest native code in the reference: src/core/compute/radix_sort.cpp (32-bit, unstable).
+// in index order (tests/test_gpu_parity.py checks both against oracle tile_keys()).
+// Nearest native code in the reference: src/core/compute/radix_sort.cpp (32-bit, unstable,
+// three dispatches and a host round trip per pass).
 //
-// All kernels here are HBM/L2-bound integer work: coalesced loads, shared-memory digit counters,
-// match.any ranking for stability.
+// Sort structure ("one sweep"): ONE kernel builds the global digit histograms of every pass,
+// then ONE kernel per 8-bit digit ranks its 2048-key tile with match.any (stable), obtains the
+// tile's per-digit offsets by decoupled look-back over the preceding tiles' published counts,
+// and scatters.  Keys and values are read once and written once per pass: HBM/L2-bound integer
+// work with coalesced loads and shared-memory digit counters.
 #include "frb_common.cuh"
 
 namespace {
@@ -23,102 +27,93 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT = 8;                                // items per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;         // 2048 items per block
 constexpr int SORT_WARP_ITEMS = 32 * SORT_IPT;
+constexpr int MAX_PASSES = 8;
+
+constexpr uint32_t FLAG_AGG = 1u << 30;      // tile count published
+constexpr uint32_t FLAG_PREFIX = 2u << 30;   // inclusive prefix over tiles 0..this published
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr int SPIN_LIMIT = 1 << 24;          // a look-back that spins this long reports an error instead of hanging
 
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, uint32_t mask) {
     return (uint32_t)(k >> shift) & mask;
 }
 
-// Per-block digit histogram, stored digit-major: hist[d * n_blocks + block].
+struct PassPlan {
+    int n_passes;
+    int shift[MAX_PASSES];
+    uint32_t mask[MAX_PASSES];
+};
+
+// Sort workspace layout (uint32 words): [hist: MAX_PASSES*256][tickets: MAX_PASSES][error: 1]
+// [pad to 16 words][status: n_passes * n_blocks * 256]
+constexpr int WS_HIST = 0;
+constexpr int WS_TICKET = MAX_PASSES * RADIX;
+constexpr int WS_ERROR = WS_TICKET + MAX_PASSES;
+constexpr int WS_STATUS = WS_ERROR + 8;
+
+// Global digit histograms of all passes in one read of the keys.
 template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(int m, const KeyT* __restrict__ keys, int shift, uint32_t mask, uint32_t* __restrict__ hist,
-                  int n_blocks) {
-    __shared__ uint32_t cnt[RADIX];
-    cnt[threadIdx.x] = 0;
+radix_hist_all_kernel(int m, const KeyT* __restrict__ keys, const __grid_constant__ PassPlan plan,
+                      uint32_t* __restrict__ hist) {
+    __shared__ uint32_t cnt[MAX_PASSES][RADIX];
+    for (int p = 0; p < plan.n_passes; ++p) cnt[p][threadIdx.x] = 0;
     __syncthreads();
-    long long base = (long long)blockIdx.x * SORT_TILE;
-#pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        long long i = base + r * SORT_THREADS + threadIdx.x;
-        if (i < m) atomicAdd(&cnt[digit_of(keys[i], shift, mask)], 1u);
+    for (long long i = (long long)blockIdx.x * SORT_THREADS + threadIdx.x; i < m;
+         i += (long long)gridDim.x * SORT_THREADS) {
+        KeyT k = keys[i];
+        for (int p = 0; p < plan.n_passes; ++p) atomicAdd(&cnt[p][digit_of(k, plan.shift[p], plan.mask[p])], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = cnt[threadIdx.x];
-}
-
-// Exclusive scan of `count` uint32 values in place, single block (count = 256 * n_blocks).
-__global__ void __launch_bounds__(1024) scan_single_block_kernel(uint32_t* __restrict__ data, int count) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PER = 4;
-    for (int base = 0; base < count; base += 1024 * PER) {
-        int i0 = base + threadIdx.x * PER;
-        uint32_t v[PER];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            v[k] = (i0 + k < count) ? data[i0 + k] : 0u;
-            sum += v[k];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_sums[warp] + incl - sum;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            if (i0 + k < count) data[i0 + k] = excl;
-            excl += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl;
-        __syncthreads();
+    for (int p = 0; p < plan.n_passes; ++p) {
+        uint32_t c = cnt[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * RADIX + threadIdx.x], c);
     }
 }
 
-// Stable scatter.  Warp w of a block owns the contiguous items [w*256, (w+1)*256) of the block's
-// tile, visited in 8 rounds of 32 consecutive items, so (warp, round, lane) order is input order.
-template <typename KeyT>
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One pass: rank (stable), look back, scatter.  Warp w of a block owns the contiguous items
+// [w*256, (w+1)*256) of the block's tile, visited in 8 rounds of 32 consecutive items, so
+// (tile, warp, round, lane) order is input order.  GEN_VALS: values are the input indices.
+template <typename KeyT, bool GEN_VALS>
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
-                     const uint32_t* __restrict__ hist_scanned, int n_blocks) {
+radix_onesweep_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
+                      const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
+                      uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag) {
     __shared__ uint32_t cnt[SORT_WARPS][RADIX];
+    __shared__ uint32_t digit_base[RADIX];
+    __shared__ uint32_t scan_ws[SORT_WARPS];
+    __shared__ uint32_t tile_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);   // tiles are numbered in start order
     for (int d = lane; d < RADIX; d += 32) cnt[warp][d] = 0;
-    __syncwarp();
+    __syncthreads();
+    const uint32_t tile = tile_s;
 
-    long long base = (long long)blockIdx.x * SORT_TILE + warp * SORT_WARP_ITEMS;
+    long long base = (long long)tile * SORT_TILE + warp * SORT_WARP_ITEMS;
     KeyT key[SORT_IPT];
-    uint32_t val[SORT_IPT];
     uint32_t rank[SORT_IPT];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
         long long i = base + r * 32 + lane;
+        key[r] = (i < m) ? keys_in[i] : (KeyT)0;
+    }
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        long long i = base + r * 32 + lane;
         bool valid = i < m;
-        key[r] = valid ? keys_in[i] : (KeyT)0;
-        val[r] = valid ? vals_in[i] : 0u;
         uint32_t d = valid ? digit_of(key[r], shift, mask) : RADIX;  // invalid lanes match each other only
         uint32_t peers = __match_any_sync(0xffffffffu, d);
         int leader = __ffs(peers) - 1;
@@ -132,111 +127,141 @@ radix_scatter_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* __
         __syncwarp();
     }
     __syncthreads();
-    {
-        // thread d: turn per-warp counts into starting positions (global base + earlier warps)
-        int d = threadIdx.x;
-        uint32_t run = hist_scanned[(size_t)d * n_blocks + blockIdx.x];
+
+    // thread d owns digit d: per-warp counts -> warp-exclusive offsets; tile count -> look-back
+    const int d = threadIdx.x;
+    uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            uint32_t c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
+    for (int w = 0; w < SORT_WARPS; ++w) {
+        uint32_t c = cnt[w][d];
+        cnt[w][d] = run;
+        run += c;
+    }
+    uint32_t* my_status = status + (size_t)tile * RADIX + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+        st_volatile_u32(my_status, run | FLAG_PREFIX);
+    } else {
+        st_volatile_u32(my_status, run | FLAG_AGG);
+        long long look = (long long)tile - 1;
+        int spins = 0;
+        while (true) {
+            uint32_t v = ld_volatile_u32(status + (size_t)look * RADIX + d);
+            uint32_t f = v & FLAG_MASK;
+            if (f == 0) {
+                if (++spins > SPIN_LIMIT) { *error_flag = 1; break; }
+                continue;
+            }
+            excl += v & VALUE_MASK;
+            if (f == FLAG_PREFIX) break;
+            --look;
         }
+        st_volatile_u32(my_status, (excl + run) | FLAG_PREFIX);
     }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        long long i = base + r * 32 + lane;
-        if (i < m) {
-            uint32_t d = digit_of(key[r], shift, mask);
-            uint32_t pos = cnt[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
-        }
-    }
-}
-
-template <typename KeyT>
-int radix_sort_impl(int m, KeyT* keys, uint32_t* vals, KeyT* keys_tmp, uint32_t* vals_tmp, int begin_bit,
-                    int end_bit, uint32_t* hist, cudaStream_t st) {
-    if (m <= 0 || end_bit <= begin_bit) return 0;
-    const int n_blocks = frb_div_up(m, SORT_TILE);
-    KeyT* kin = keys; uint32_t* vin = vals; KeyT* kout = keys_tmp; uint32_t* vout = vals_tmp;
-    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
-        int nb = min(RADIX_BITS, end_bit - bit);
-        uint32_t mask = (1u << nb) - 1u;
-        radix_hist_kernel<KeyT><<<n_blocks, SORT_THREADS, 0, st>>>(m, kin, bit, mask, hist, n_blocks);
-        scan_single_block_kernel<<<1, 1024, 0, st>>>(hist, RADIX * n_blocks);
-        radix_scatter_kernel<KeyT><<<n_blocks, SORT_THREADS, 0, st>>>(m, kin, vin, kout, vout, bit, mask, hist,
-                                                                      n_blocks);
-        frb_note_launches(3);
-        FRB_LAUNCH_CHECK();
-        KeyT* tk = kin; kin = kout; kout = tk;
-        uint32_t* tv = vin; vin = vout; vout = tv;
-    }
-    if (kin != keys) {
-        FRB_CUDA_OK(cudaMemcpyAsync(keys, kin, sizeof(KeyT) * (size_t)m, cudaMemcpyDeviceToDevice, st));
-        FRB_CUDA_OK(cudaMemcpyAsync(vals, vin, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToDevice, st));
-    }
-    return 0;
-}
-
-__global__ void iota_copy_kernel(int n, const uint32_t* __restrict__ src, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        keys[i] = src[i];
-        vals[i] = (uint32_t)i;
-    }
-}
-
-// ---- exclusive scan of tiles_touched[order[k]] : three phases ---------------------------
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_IPT = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t ws[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = v;
+    // exclusive scan of the global digit histogram (256 values, one per thread)
+    uint32_t h = hist_pass[d];
+    uint32_t incl = h;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) ws[warp] = incl;
+    if (lane == 31) scan_ws[warp] = incl;
     __syncthreads();
-    uint32_t off = 0, tot = 0;
+    uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        uint32_t s = ws[w];
-        if (w < warp) off += s;
-        tot += s;
-    }
+    for (int w = 0; w < SORT_WARPS; ++w)
+        if (w < warp) woff += scan_ws[w];
+    digit_base[d] = woff + incl - h + excl;
     __syncthreads();
-    *total = tot;
-    return off + incl - v;
+
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        long long i = base + r * 32 + lane;
+        if (i < m) {
+            uint32_t dg = digit_of(key[r], shift, mask);
+            uint32_t pos = digit_base[dg] + cnt[warp][dg] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = GEN_VALS ? (uint32_t)i : vals_in[i];
+        }
+    }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-offsets_reduce_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t* __restrict__ order,
-                      uint32_t* __restrict__ block_sums) {
-    long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k) {
-        long long i = base + k;
-        if (i < n) s += touched[order ? order[i] : (uint32_t)i];
-    }
-    uint32_t tot;
-    block_exclusive_scan_256(s, &tot);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+size_t sort_ws_words(int m, int n_passes) {
+    return (size_t)WS_STATUS + (size_t)n_passes * (size_t)frb_div_up(m, SORT_TILE) * RADIX;
 }
 
+// Sorts on bits [begin_bit, end_bit).  Pass p reads buffer (p even ? A : B) and writes the other;
+// when first_in is given, pass 0 reads keys from there (and generates values if vals_first is null).
+// Returns in *result_in_b whether the sorted data ended in the B buffers.
+template <typename KeyT>
+int radix_sort_impl(int m, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
+                    KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
+                    bool* result_in_b) {
+    PassPlan plan;
+    plan.n_passes = 0;
+    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
+        if (plan.n_passes == MAX_PASSES) return FRB_E_INVALID;
+        int nb = min(RADIX_BITS, end_bit - bit);
+        plan.shift[plan.n_passes] = bit;
+        plan.mask[plan.n_passes] = (1u << nb) - 1u;
+        ++plan.n_passes;
+    }
+    const int n_blocks = frb_div_up(m, SORT_TILE);
+    FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
+    radix_hist_all_kernel<KeyT><<<min(n_blocks, 592), SORT_THREADS, 0, st>>>(m, first_keys, plan, ws + WS_HIST);
+    frb_note_launches(1);
+    const KeyT* kin = first_keys;
+    const uint32_t* vin = first_vals;
+    bool to_b = (first_keys == keys_a);     // in-place start: A -> B; external start: -> A first
+    for (int p = 0; p < plan.n_passes; ++p) {
+        KeyT* kout = to_b ? keys_b : keys_a;
+        uint32_t* vout = to_b ? vals_b : vals_a;
+        uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RADIX;
+        if (vin == nullptr)
+            radix_onesweep_kernel<KeyT, true><<<n_blocks, SORT_THREADS, 0, st>>>(
+                m, kin, nullptr, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
+                ws + WS_TICKET + p, ws + WS_ERROR);
+        else
+            radix_onesweep_kernel<KeyT, false><<<n_blocks, SORT_THREADS, 0, st>>>(
+                m, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
+                ws + WS_TICKET + p, ws + WS_ERROR);
+        frb_note_launches(1);
+        FRB_LAUNCH_CHECK();
+        kin = kout; vin = vout;
+        *result_in_b = to_b;
+        to_b = !to_b;
+    }
+    return 0;
+}
+
+// ---- exclusive scan of tiles_touched[order[k]] : single pass, decoupled look-back ----------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+constexpr unsigned long long SFLAG_AGG = 1ull << 62, SFLAG_PREFIX = 2ull << 62, SFLAG_MASK = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// workspace: [ticket u64][error u64][status u64 x n_blocks]
 __global__ void __launch_bounds__(SCAN_THREADS)
-offsets_write_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t* __restrict__ order,
-                     const uint32_t* __restrict__ block_sums_scanned, uint32_t* __restrict__ offsets) {
-    long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+offsets_scan_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t* __restrict__ order,
+                    uint32_t* __restrict__ offsets, unsigned long long* __restrict__ ws) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    __shared__ uint32_t tile_s;
+    __shared__ uint32_t prefix_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_s = (uint32_t)atomicAdd(ws, 1ull);
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    long long base = (long long)tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
     uint32_t s = 0;
 #pragma unroll
@@ -245,8 +270,47 @@ offsets_write_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t
         v[k] = (i < n) ? touched[order ? order[i] : (uint32_t)i] : 0u;
         s += v[k];
     }
-    uint32_t tot;
-    uint32_t excl = block_exclusive_scan_256(s, &tot) + block_sums_scanned[blockIdx.x];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        uint32_t x = wsum[w];
+        if (w < warp) woff += x;
+        total += x;
+    }
+    unsigned long long* status = ws + 2;
+    if (threadIdx.x == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st_volatile_u64(status, (unsigned long long)total | SFLAG_PREFIX);
+        } else {
+            st_volatile_u64(status + tile, (unsigned long long)total | SFLAG_AGG);
+            long long look = (long long)tile - 1;
+            int spins = 0;
+            while (true) {
+                unsigned long long x = ld_volatile_u64(status + look);
+                unsigned long long f = x & SFLAG_MASK;
+                if (f == 0) {
+                    if (++spins > SPIN_LIMIT) { ws[1] = 1; break; }
+                    continue;
+                }
+                excl += (uint32_t)(x & ~SFLAG_MASK);
+                if (f == SFLAG_PREFIX) break;
+                --look;
+            }
+            st_volatile_u64(status + tile, (unsigned long long)(excl + total) | SFLAG_PREFIX);
+        }
+        prefix_s = excl;
+    }
+    __syncthreads();
+    uint32_t excl = prefix_s + woff + incl - s;
 #pragma unroll
     for (int k = 0; k < SCAN_IPT; ++k) {
         long long i = base + k;
@@ -280,10 +344,8 @@ bin_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const fl
         }
 }
 
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(int m, const uint64_t* __restrict__ keys, int2* __restrict__ ranges) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+__device__ __forceinline__ void range_boundary(int i, int m, const uint64_t* __restrict__ keys,
+                                               int2* __restrict__ ranges) {
     uint32_t t = (uint32_t)(keys[i] >> 32);
     if (i == 0) {
         ranges[t].x = 0;
@@ -297,24 +359,35 @@ tile_ranges_kernel(int m, const uint64_t* __restrict__ keys, int2* __restrict__ 
     if (i == m - 1) ranges[t].y = m;
 }
 
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(int m, const uint64_t* __restrict__ keys, int2* __restrict__ ranges) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) range_boundary(i, m, keys, ranges);
+}
+
 // 3 threads per instance, one float4 each: 48-byte records land contiguous and coalesced.
+// keys != NULL also writes the tile ranges (fused frb_tile_ranges).
 __global__ void __launch_bounds__(256)
 gather_records_kernel(int m, const uint32_t* __restrict__ gids, const float4* __restrict__ records,
                       float4* __restrict__ sorted_records, const float* __restrict__ phases,
-                      float* __restrict__ sorted_phases) {
+                      float* __restrict__ sorted_phases, const uint64_t* __restrict__ keys,
+                      int2* __restrict__ ranges) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 3ll * m) return;
     int i = (int)(t / 3), part = (int)(t - 3ll * i);
     uint32_t g = gids[i];
     sorted_records[t] = records[3 * (size_t)g + part];
-    if (sorted_phases && part == 0) sorted_phases[i] = phases[g];
+    if (part == 0 && sorted_phases) sorted_phases[i] = phases[g];
+    if (part == 1 && keys) range_boundary(i, m, keys, ranges);
 }
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 extern "C" size_t frb_sort_workspace_bytes(int m) {
     if (m < 0) m = 0;
-    return sizeof(uint32_t) * (size_t)RADIX * (size_t)(frb_div_up(m, SORT_TILE) + 1);
+    return sizeof(uint32_t) * sort_ws_words(m, MAX_PASSES);
 }
 
 extern "C" int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
@@ -323,15 +396,21 @@ extern "C" int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint6
     if (m < 0 || begin_bit < 0 || end_bit > 64) return FRB_E_INVALID;
     if (m == 0 || end_bit <= begin_bit) return 0;
     if (!keys || !vals || !keys_tmp || !vals_tmp || !workspace) return FRB_E_INVALID;
-    return radix_sort_impl<uint64_t>(m, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit, (uint32_t*)workspace,
-                                     (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool in_b = false;
+    int rc = radix_sort_impl<uint64_t>(m, keys, vals, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit,
+                                       (uint32_t*)workspace, st, &in_b);
+    if (rc) return rc;
+    if (in_b) {
+        FRB_CUDA_OK(cudaMemcpyAsync(keys, keys_tmp, sizeof(uint64_t) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+        FRB_CUDA_OK(cudaMemcpyAsync(vals, vals_tmp, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
 }
-
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t frb_depth_order_workspace_bytes(int n) {
     if (n < 0) n = 0;
-    return 3 * align256(sizeof(uint32_t) * (size_t)n) + align256(frb_sort_workspace_bytes(n));
+    return 3 * align256(sizeof(uint32_t) * (size_t)n) + align256(sizeof(uint32_t) * sort_ws_words(n, 4));
 }
 
 extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* workspace,
@@ -342,19 +421,21 @@ extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* orde
     cudaStream_t st = (cudaStream_t)stream;
     char* w = (char*)workspace;
     size_t a = align256(sizeof(uint32_t) * (size_t)n);
-    uint32_t* keys = (uint32_t*)w;
-    uint32_t* keys_tmp = (uint32_t*)(w + a);
-    uint32_t* vals_tmp = (uint32_t*)(w + 2 * a);
-    uint32_t* hist = (uint32_t*)(w + 3 * a);
-    iota_copy_kernel<<<frb_div_up(n, 256), 256, 0, st>>>(n, depth_bits, keys, order);
-    frb_note_launches(1);
-    FRB_LAUNCH_CHECK();
-    return radix_sort_impl<uint32_t>(n, keys, order, keys_tmp, vals_tmp, 0, 32, hist, st);
+    uint32_t* keys_a = (uint32_t*)w;
+    uint32_t* keys_b = (uint32_t*)(w + a);
+    uint32_t* vals_a = (uint32_t*)(w + 2 * a);
+    uint32_t* ws = (uint32_t*)(w + 3 * a);
+    // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
+    bool in_b = false;
+    int rc = radix_sort_impl<uint32_t>(n, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b);
+    if (rc) return rc;
+    if (!in_b) return FRB_E_INVALID;   // cannot happen with an even number of passes
+    return 0;
 }
 
 extern "C" size_t frb_scan_workspace_bytes(int n) {
     if (n < 0) n = 0;
-    return sizeof(uint32_t) * (size_t)(frb_div_up(n, SCAN_TILE) + 1);
+    return sizeof(unsigned long long) * (size_t)(frb_div_up(n, SCAN_TILE) + 2);
 }
 
 extern "C" int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint32_t* order,
@@ -367,11 +448,10 @@ extern "C" int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint
     }
     if (!tiles_touched || !workspace) return FRB_E_INVALID;
     int nb = frb_div_up(n, SCAN_TILE);
-    uint32_t* sums = (uint32_t*)workspace;
-    offsets_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, sums);
-    scan_single_block_kernel<<<1, 1024, 0, st>>>(sums, nb);
-    offsets_write_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, sums, offsets);
-    frb_note_launches(3);
+    FRB_CUDA_OK(cudaMemsetAsync(workspace, 0, frb_scan_workspace_bytes(n), st));
+    offsets_scan_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, offsets,
+                                                     (unsigned long long*)workspace);
+    frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
@@ -412,7 +492,23 @@ extern "C" int frb_gather_records(int m, const uint32_t* gids, const float* reco
     if (!gids || !records || !sorted_records) return FRB_E_INVALID;
     if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
     gather_records_kernel<<<frb_div_up(3ll * m, 256), 256, 0, (cudaStream_t)stream>>>(
-        m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases);
+        m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, nullptr, nullptr);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int frb_ranges_and_gather(int m, const uint64_t* keys, const uint32_t* gids, int n_tiles,
+                                     int32_t* ranges, const float* records, float* sorted_records,
+                                     const float* phases, float* sorted_phases, void* stream) {
+    if (m < 0 || n_tiles < 0 || !ranges) return FRB_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, st));
+    if (m == 0) return 0;
+    if (!keys || !gids || !records || !sorted_records) return FRB_E_INVALID;
+    if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
+    gather_records_kernel<<<frb_div_up(3ll * m, 256), 256, 0, st>>>(
+        m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, keys, (int2*)ranges);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

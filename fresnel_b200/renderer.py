@@ -157,14 +157,10 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
         begin = 32 if sort else 0
         _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs, m, _ptr(b.keys), _ptr(b.sorted_gids), _ptr(keys_tmp),
                                           _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
-    _call("frb_tile_ranges", L.frb_tile_ranges, m, _ptr(b.keys), n_tiles, _ptr(b.ranges), st)
-    if m > 0:
-        if phases is not None:
-            b.sorted_phases = torch.empty(m, dtype=torch.float32, device=dev)
-        _call("frb_gather_records", L.frb_gather_records, m, _ptr(b.sorted_gids), _ptr(b.records), _ptr(b.sorted_records),
-                                        _ptr(phases), _ptr(b.sorted_phases), st)
-    elif phases is not None:
-        b.sorted_phases = torch.empty(1, dtype=torch.float32, device=dev)
+    if phases is not None:
+        b.sorted_phases = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+    _call("frb_ranges_and_gather", L.frb_ranges_and_gather, m, _ptr(b.keys), _ptr(b.sorted_gids), n_tiles,
+          _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases), _ptr(b.sorted_phases), st)
     return b
 
 

@@ -109,6 +109,11 @@ int frb_tile_ranges(int m, const uint64_t* keys, int n_tiles, int32_t* ranges, v
 int frb_gather_records(int m, const uint32_t* gids, const float* records, float* sorted_records,
                        const float* phases, float* sorted_phases, void* stream);
 
+/* frb_tile_ranges + frb_gather_records in one launch (what the renderer calls). */
+int frb_ranges_and_gather(int m, const uint64_t* keys, const uint32_t* gids, int n_tiles,
+                          int32_t* ranges, const float* records, float* sorted_records,
+                          const float* phases, float* sorted_phases, void* stream);
+
 /* ---- compositing ------------------------------------------------------ */
 /* t_eps: a pixel stops once its transmittance has fallen below max(t_eps, 1e-20).
  * sorted_phases == NULL selects plain alpha compositing; otherwise Fresnel phase blending
