@@ -23,6 +23,9 @@ constexpr int BATCH = 64;                       // records per stage
 constexpr int STAGES = 4;
 constexpr int RECORD_BYTES = FRB_RECORD_FLOATS * 4;
 constexpr float T_FLOOR = 1e-20f;
+constexpr int CHUNK = 4;                        // records between early-termination tests
+constexpr uint32_t NULL_RECT_LO = 0x7fff7fffu;  // x0 = y0 = 32767: contains no pixel
+constexpr uint32_t NULL_RECT_HI = 0x80008000u;  // x1 = y1 = 0
 constexpr int STATE_GATE_SHIFT = 28;            // state_n = entries consumed | clamp gates << 28
 constexpr int STATE_N_MASK = (1 << STATE_GATE_SHIFT) - 1;
 
@@ -78,33 +81,52 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     }
 
     float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;
-    int consumed = 0;
+    int consumed = count;               // list entries walked; lowered when the pixel stops early
     bool done = !in_image;
     const float stop = fmaxf(t_eps, T_FLOOR);
 
     for (int b = 0; b < n_batches; ++b) {
         const int s = b % STAGES;
         const int cnt = min(BATCH, count - b * BATCH);
+        const int cnt_pad = (cnt + CHUNK - 1) & ~(CHUNK - 1);
         frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
+        if (cnt_pad != cnt) {
+            // last batch: pad to a whole chunk with records whose rectangle contains no pixel
+            if (threadIdx.x < (cnt_pad - cnt) * 3) {
+                const int k = threadIdx.x % 3;
+                stage[s].rec[3 * cnt + threadIdx.x] =
+                    make_float4(0.f, 0.f, 0.f, k == 1 ? __uint_as_float(NULL_RECT_LO)
+                                                      : (k == 2 ? __uint_as_float(NULL_RECT_HI) : 0.f));
+            }
+            __syncthreads();
+        }
         if (!done) {
             const float4* rec = stage[s].rec;
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                float4 r0 = rec[3 * j + 0], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                bool inside = rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
-                if (inside && !done) {
-                    float dx = fpx - r0.x, dy = fpy - r0.y;
-                    float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
-                    float a = frb_ex2(power) * r1.y;
-                    a = fminf(fmaxf(a, 0.0f), FRB_ALPHA_MAX);
-                    float c = a * T;
-                    cr = fmaf(c, r2.x, cr);
-                    cg = fmaf(c, r2.y, cg);
-                    cb = fmaf(c, r2.z, cb);
-                    cd = fmaf(c, r1.z, cd);
-                    T = T * (1.0f - a);
-                    consumed = b * BATCH + j + 1;
-                    done = T < stop;
+            for (int j0 = 0; j0 < cnt_pad; j0 += CHUNK) {
+#pragma unroll
+                for (int k = 0; k < CHUNK; ++k) {
+                    const int j = j0 + k;
+                    float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                    if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                        float4 r0 = rec[3 * j + 0];
+                        float dx = fpx - r0.x, dy = fpy - r0.y;
+                        float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                        float a = frb_ex2(power) * r1.y;
+                        a = fminf(fmaxf(a, 0.0f), FRB_ALPHA_MAX);
+                        float c = a * T;
+                        cr = fmaf(c, r2.x, cr);
+                        cg = fmaf(c, r2.y, cg);
+                        cb = fmaf(c, r2.z, cb);
+                        cd = fmaf(c, r1.z, cd);
+                        T = fmaf(-a, T, T);
+                    }
+                }
+                // early termination is tested once per chunk; the backward pass replays exactly
+                // the entries [0, consumed)
+                if (T < stop) {
+                    done = true;
+                    consumed = min(b * BATCH + j0 + CHUNK, count);
+                    break;
                 }
             }
         }
@@ -263,23 +285,24 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             const int sub_cnt = min(32, cnt - sb * 32);
             // ---- phase 1: lane = pixel -------------------------------------------------
             uint32_t gmask = 0;
-            for (int j = sub_cnt - 1; j >= 0; --j) {
+            const int local_n = my_n - (b * BATCH + sb * 32);    // entries j < local_n were applied
+            uint32_t bit = 1u << (sub_cnt - 1);
+            for (int j = sub_cnt - 1; j >= 0; --j, bit >>= 1) {
                 const int jb = sb * 32 + j;
                 float4 r1 = rec[3 * jb + 1], r2 = rec[3 * jb + 2];
-                const int idx = b * BATCH + jb;
-                bool active = (idx < my_n) &&
+                bool active = (j < local_n) &&
                               rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
                 if (!__any_sync(0xffffffffu, active)) continue;
-                gmask |= 1u << j;
+                gmask |= bit;
                 float2 out = make_float2(0.f, 0.f);
                 if (active) {
                     float4 r0 = rec[3 * jb + 0];
                     float dx = fpx - r0.x, dy = fpy - r0.y;
-                    float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                    float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                     float g = frb_ex2(power);
                     float araw = g * r1.y;
                     float a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
-                    float inv_om = __fdividef(1.0f, 1.0f - a);
+                    float inv_om = frb_rcp(1.0f - a);
                     float Ti = T * inv_om;
                     float c = a * Ti;
                     float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
@@ -287,7 +310,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                     S = fmaf(c, w, S);
                     T = Ti;
                     out.x = c;
-                    out.y = (araw >= 0.0f && araw <= FRB_ALPHA_MAX) ? dalpha : 0.0f;
+                    out.y = (a == araw) ? dalpha : 0.0f;      // clamp gate: 0 <= g*o <= 0.99
                 }
                 my_pair[j * PAIR_STRIDE + lane] = out;
             }
@@ -300,29 +323,34 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const int jb = sb * 32 + (mine ? lane : 0);
                 const float4 r0 = rec[3 * jb + 0], r1 = rec[3 * jb + 1];
                 const float oln2 = r1.y * FRB_LN2;
+                const float ux = wbx - r0.x, uy = wby - r0.y;
                 const float2* row = my_pair + lane * PAIR_STRIDE;
                 const float4* pc = sm.pixc[warp];
                 if (mine) {
-#pragma unroll 8
+                    float sx = 0.f, sy = 0.f;                 // sum dx*dpow, sum dy*dpow
+#pragma unroll
                     for (int p = 0; p < 32; ++p) {
                         float2 cd = row[p];
                         float4 gpix = pc[p];
-                        float dx = (wbx + (float)(p & 15)) - r0.x;
-                        float dy = (wby + (float)(p >> 4)) - r0.y;
-                        float power = r0.z * dx * dx + r0.w * dx * dy + r1.x * dy * dy;
+                        float dx = ux + (float)(p & 15);
+                        float dy = uy + (float)(p >> 4);
+                        float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                         float gda = (cd.y != 0.0f) ? frb_ex2(power) * cd.y : 0.0f;   // g * gated dL/dalpha
                         d_r = fmaf(cd.x, gpix.x, d_r);
                         d_g = fmaf(cd.x, gpix.y, d_g);
                         d_b = fmaf(cd.x, gpix.z, d_b);
                         d_dep = fmaf(cd.x, gpix.w, d_dep);
                         d_o += gda;
-                        float dpow = gda * oln2;                                      // dL/d(power): g = 2^power
-                        d_A = fmaf(dx * dx, dpow, d_A);
-                        d_B = fmaf(dx * dy, dpow, d_B);
-                        d_C = fmaf(dy * dy, dpow, d_C);
-                        d_u = fmaf(2.0f * r0.z * dx + r0.w * dy, dpow, d_u);
-                        d_v = fmaf(r0.w * dx + 2.0f * r1.x * dy, dpow, d_v);
+                        float tx_ = dx * gda, ty_ = dy * gda;
+                        sx += tx_; sy += ty_;
+                        d_A = fmaf(dx, tx_, d_A);
+                        d_B = fmaf(dx, ty_, d_B);
+                        d_C = fmaf(dy, ty_, d_C);
                     }
+                    // dL/d(power) = gda * o * ln2 (g = 2^power); u, v enter through dx, dy
+                    d_A *= oln2; d_B *= oln2; d_C *= oln2;
+                    d_u = (2.0f * r0.z * sx + r0.w * sy) * oln2;
+                    d_v = (r0.w * sx + 2.0f * r1.x * sy) * oln2;
                 }
             }
             {

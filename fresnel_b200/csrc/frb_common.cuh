@@ -82,6 +82,17 @@ __device__ __forceinline__ float frb_ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ float frb_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Orders generic-proxy shared-memory writes before later async-proxy (TMA) accesses.
+__device__ __forceinline__ void frb_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ float frb_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
