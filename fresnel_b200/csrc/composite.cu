@@ -15,37 +15,13 @@
 // T is the reference's (1 - accumulated_alpha) in product form.
 #include "frb_common.cuh"
 
+#include "composite_common.cuh"
+
 namespace {
 
-constexpr int TILE = FRB_TILE;
-constexpr int CTA_THREADS = TILE * TILE;
-constexpr int BATCH = 64;                       // records per stage
-constexpr int STAGES = 4;
-constexpr int RECORD_BYTES = FRB_RECORD_FLOATS * 4;
-constexpr float T_FLOOR = 1e-20f;
-constexpr int CHUNK = 4;                        // records between early-termination tests
-constexpr uint32_t NULL_RECT_LO = 0x7fff7fffu;  // x0 = y0 = 32767: contains no pixel
-constexpr uint32_t NULL_RECT_HI = 0x80008000u;  // x1 = y1 = 0
-constexpr int STATE_GATE_SHIFT = 28;            // state_n = entries consumed | clamp gates << 28
-constexpr int STATE_N_MASK = (1 << STATE_GATE_SHIFT) - 1;
-
-struct __align__(16) StageBuf {
-    float4 rec[BATCH * 3];
-};
-
-__device__ __forceinline__ bool rect_contains(uint32_t pxy_guard, uint32_t pxy_plus1, uint32_t lo, uint32_t hi) {
-    // SWAR test of x0 <= px < x1 and y0 <= py < y1 on 15-bit halves with guard bits:
-    // (px | G) - x0 keeps G iff px >= x0 ; (x1 | G) - (px + 1) keeps G iff px < x1.
-    uint32_t a = pxy_guard - lo;
-    uint32_t b = hi - pxy_plus1;
-    return ((a & b) & 0x80008000u) == 0x80008000u;
-}
-
-template <bool PHASE>
 __global__ void __launch_bounds__(CTA_THREADS)
 composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
-                     const float4* __restrict__ sorted_records, const float* __restrict__ sorted_phases,
-                     float phase_amplitude, float3 bg, float t_eps, float* __restrict__ image,
+                     const float4* __restrict__ sorted_records, float3 bg, float t_eps, float* __restrict__ image,
                      float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
                      int* __restrict__ state_n) {
     __shared__ StageBuf stage[STAGES];
@@ -381,10 +357,17 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 
 }  // namespace
 
-extern "C" size_t frb_phase_ckpt_floats(int m, int n_tiles) {
-    (void)m; (void)n_tiles;
-    return 0;
-}
+// composite_phase.cu
+int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* ranges,
+                                   const float* sorted_records, const float* sorted_phases, float phase_amplitude,
+                                   const float* background_host, float t_eps, float* image, float* depth,
+                                   float* alpha, float* state_T, int32_t* state_n, float* ckpt, cudaStream_t st);
+int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int32_t* ranges,
+                                   const float* sorted_records, const uint32_t* sorted_gids,
+                                   const float* sorted_phases, float phase_amplitude, const float* background_host,
+                                   const float* state_T, const int32_t* state_n, const float* ckpt,
+                                   const float* g_image, const float* g_depth, const float* g_alpha, float* grad2d,
+                                   float* g_phases, cudaStream_t st);
 
 static int check_image_args(int n_views, int width, int height) {
     if (n_views < 1 || n_views > FRB_MAX_VIEWS || width < 1 || height < 1) return FRB_E_INVALID;
@@ -400,14 +383,16 @@ extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32
     int rc = check_image_args(n_views, width, height);
     if (rc) return rc;
     if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n) return FRB_E_INVALID;
-    if (sorted_phases) return FRB_E_INVALID;  // phase blending: see composite_phase.cu
-    (void)ckpt;
+    if (sorted_phases)
+        return frb_composite_phase_fwd_launch(n_views, width, height, ranges, sorted_records, sorted_phases,
+                                              phase_amplitude, background_host, t_eps, image, depth, alpha,
+                                              state_T, state_n, ckpt, (cudaStream_t)stream);
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    composite_fwd_kernel<false><<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, nullptr, phase_amplitude,
-        bg, t_eps, image, depth, alpha, state_T, state_n);
+    composite_fwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps, image, depth,
+        alpha, state_T, state_n);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -423,8 +408,11 @@ extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32
     int rc = check_image_args(n_views, width, height);
     if (rc) return rc;
     if (!ranges || !background_host || !state_T || !state_n || !g_image || !grad2d) return FRB_E_INVALID;
-    if (sorted_phases) return FRB_E_INVALID;
-    (void)ckpt; (void)g_phases; (void)phase_amplitude;
+    if (sorted_phases)
+        return frb_composite_phase_bwd_launch(n_views, width, height, ranges, sorted_records, sorted_gids,
+                                              sorted_phases, phase_amplitude, background_host, state_T, state_n,
+                                              ckpt, g_image, g_depth, g_alpha, grad2d, g_phases,
+                                              (cudaStream_t)stream);
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);

@@ -273,3 +273,42 @@ def test_full_size_properties_config2():
     _, _, _, grb = render_gpu(inp, cam, W, H, (0, 0, 0), 0.0, 64, gi * 0.0, gd)
     for k in GRAD_NAMES:
         assert rel(gr3[k], 2.0 * gra[k] - 0.5 * grb[k]) < 2e-5, k
+
+
+@pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
+def test_phase_blending_matches_reference_golden(golden, t_eps):
+    """use_phase_blending=True: forward against the reference's own output, gradients against the
+    oracle's .clone() restatement (the reference raises inside autograd on this path)."""
+    z = golden("tile_phase_2k_128")
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z, with_phases=True)
+    cam = oracle_camera(z["cam"], W, H)
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, tuple(float(x) for x in z["bg"]), t_eps,
+                                        int(z["max_radius"]), torch.from_numpy(z["gimage"]),
+                                        torch.from_numpy(z["gdepth"]), phases=True,
+                                        amp=float(z["phase_amplitude"]))
+    assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
+    assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
+    assert rel(alpha, z["alpha"]) < IMG_TOL
+    for k in GRAD_NAMES + ("phases",):
+        assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
+
+
+def test_phase_blending_fresh_scene_long_lists():
+    """Many overlaps per pixel (several 32-entry checkpoint blocks and TMA batches), coloured background,
+    oracle run live; phases of all Gaussians receive gradients."""
+    W, H = 64, 48
+    inp = fo.synthetic_cloud(1200, seed=51, s_lo=0.03, s_hi=0.12)
+    cam = fo.default_camera(W, H)
+    g = torch.Generator().manual_seed(4)
+    gi, gd = torch.rand(3, H, W, generator=g) * 2 - 1, torch.rand(H, W, generator=g) * 2 - 1
+    names = GRAD_NAMES + ("phases",)
+    Lo = {k: inp[k].clone().requires_grad_(True) for k in names}
+    io, do, ao = fo.render_tile_based(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                                      Lo["opacities"], cam, W, H, background=(0.2, 0.4, 0.1),
+                                      use_phase_blending=True, phase_amplitude=0.4, phases=Lo["phases"])
+    ((io * gi).sum() + (do * gd).sum()).backward()
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, (0.2, 0.4, 0.1), 0.0, 64, gi, gd, phases=True, amp=0.4)
+    assert rel(img, io.detach()) < IMG_TOL and rel(dep, do.detach()) < IMG_TOL and rel(alpha, ao.detach()) < IMG_TOL
+    for k in names:
+        assert rel(grads[k], Lo[k].grad) < GRAD_TOL, (k, rel(grads[k], Lo[k].grad))
