@@ -9,6 +9,8 @@ importing this package does not need a GPU, rendering does.
 
 from .camera import Camera, camera_vector, create_camera_from_pose
 from .renderer import DEFAULT_T_EPS, TileBasedRenderer, build_bins, render_views
+from .wave import ASMWaveFieldRenderer, WaveFieldRenderer
 
-__all__ = ["Camera", "camera_vector", "create_camera_from_pose", "TileBasedRenderer", "render_views",
+__all__ = ["Camera", "camera_vector", "create_camera_from_pose", "TileBasedRenderer", "WaveFieldRenderer",
+           "ASMWaveFieldRenderer", "render_views",
            "build_bins", "DEFAULT_T_EPS"]

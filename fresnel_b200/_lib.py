@@ -34,9 +34,19 @@ _SIGNATURES = {
     "frb_phase_ckpt_floats": (c_size_t, [c_int, c_int]),
     "frb_composite_fwd": (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),
+    "frb_wave_prepare": (c_int, [c_int, P, P, c_int, P, P]),
+    "frb_wave_gather": (c_int, [c_int, P, P, P, P]),
+    "frb_wave_splat_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "frb_wave_finish_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "frb_wave_finish_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "frb_wave_splat_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float, P, P, P]),
+    "frb_wave_chain_bwd": (c_int, [c_int, P, P, c_int, P, P, P, P]),
+    "frb_asm_assign_planes": (c_int, [c_int, P, c_int, P, P, P]),
+    "frb_asm_splat_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "frb_asm_propagate_fwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P]),
+    "frb_asm_propagate_bwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P, P, P]),
 }
 
-# Entry points of later build stages; bound when the library exports them.
 _OPTIONAL = {}
 
 

@@ -105,12 +105,16 @@ class TileBins:
 
 def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
                width: int, height: int, max_radius: float, phases=None, keep_debug: bool = False,
-               sort: bool = True) -> TileBins:
+               sort: bool = True, low_word_fn=None, presort: bool = True) -> TileBins:
     """Projection + binning: everything up to the per-tile sorted record lists.
 
     Sequences frb_project_fwd -> frb_depth_order -> frb_tile_offsets -> frb_bin_emit ->
     frb_radix_sort_pairs (tile bits only) -> frb_tile_ranges -> frb_gather_records.
     One device->host read (the instance count M) sizes the instance buffers.
+
+    ``sort=False`` emits in index order and sorts all 64 key bits (test path).  ``low_word_fn(bins)``
+    replaces the depth bits as the low key word (ASM: the depth-plane index).  ``presort=False`` skips
+    the depth order altogether (order-free renderers): lists come out in ascending Gaussian index.
     """
     L = _lib.lib()
     dev = positions.device
@@ -130,8 +134,10 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
                                  _ptr(opacities), cam.ctypes.data, float(max_radius), _ptr(b.records),
                                  _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
 
+    if low_word_fn is not None:
+        b.depth_bits = low_word_fn(b)
     b.order = None
-    if sort and n > 0:
+    if sort and presort and n > 0:
         b.order = torch.empty(n, **i32)
         ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=dev)
         _call("frb_depth_order", L.frb_depth_order, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(ws), st)

@@ -137,6 +137,53 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
                       const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
                       void* stream);
 
+/* ---- complex wave field: WaveFieldRenderer DR:747-926 ------------------------------------ */
+/* wc: 8 floats per Gaussian [colour_c cos(phi_c) x3, colour_c sin(phi_c) x3, 0, 0];
+ * phases: n x phase_stride floats, phase_stride = 1 (scalar phase) or 3 (per channel), radians.
+ * accum / gpix: [n_views][8][H][W] planar (Re rgb, Im rgb, sum amp*depth, sum amp) and its gradient.
+ * rmax_bits: per view, bits of max over pixels and channels of sqrt(I + 1e-8) (DR:902).
+ * red: 2 floats per view of scratch. */
+int frb_wave_prepare(int n, const float* colors, const float* phases, int phase_stride, float* wc,
+                     void* stream);
+int frb_wave_gather(int m, const uint32_t* gids, const float* wc, float* sorted_wc, void* stream);
+int frb_wave_splat_fwd(int n_views, int width, int height, const int32_t* ranges,
+                       const float* sorted_records, const float* sorted_wc, float* accum,
+                       uint32_t* rmax_bits, void* stream);
+int frb_wave_finish_fwd(int n_views, int width, int height, const float* accum,
+                        const uint32_t* rmax_bits, const float* background_host, float* image,
+                        float* depth, void* stream);
+int frb_wave_finish_bwd(int n_views, int width, int height, const float* accum,
+                        const uint32_t* rmax_bits, const float* background_host, const float* g_image,
+                        const float* g_depth, float* red, float* gpix, void* stream);
+/* n_planes == 0: wave (gpix as above); n_planes > 0: ASM (gpix = d_fields, see below, times scale).
+ * grad2d (slots 0..6) and gwc (8 floats per Gaussian) must be zeroed by the caller. */
+int frb_wave_splat_bwd(int n_views, int width, int height, int n_planes, const int32_t* ranges,
+                       const float* sorted_records, const float* sorted_wc, const uint32_t* sorted_gids,
+                       const uint64_t* keys, const float* gpix, float scale, float* grad2d, float* gwc,
+                       void* stream);
+/* colour / phase gradients from gwc: writes grad2d slots 8..10 and g_phases (n x phase_stride). */
+int frb_wave_chain_bwd(int n, const float* colors, const float* phases, int phase_stride,
+                       const float* gwc, float* grad2d, float* g_phases, void* stream);
+
+/* ---- angular spectrum: AngularSpectrumPropagator DR:929-1065, ASMWaveFieldRenderer DR:1150-1344 */
+/* plane_idx[i] = argmin_p |depth_i - depth_planes[p]| (DR:1136-1148); it replaces the depth bits as
+ * the low word of the sort key, so every tile list is grouped by plane.
+ * fields / d_fields: [n_views][n_planes][3][H][W] complex64; total / g_total: [n_views][3][H][W]. */
+int frb_asm_assign_planes(int n, const float* records, int n_planes, const float* depth_planes_host,
+                          uint32_t* plane_idx, void* stream);
+int frb_asm_splat_fwd(int n_views, int width, int height, int n_planes, const int32_t* ranges,
+                      const float* sorted_records, const float* sorted_wc, const uint64_t* keys,
+                      float* fields, void* stream);
+int frb_asm_propagate_fwd(int n_views, int width, int height, int n_planes,
+                          const float* depth_planes_host, float focal_depth, float pixel_pitch,
+                          const float* wavelengths_host, const float* background_host, float* fields,
+                          float* total, uint32_t* rmax_bits, float* image, void* stream);
+int frb_asm_propagate_bwd(int n_views, int width, int height, int n_planes,
+                          const float* depth_planes_host, float focal_depth, float pixel_pitch,
+                          const float* wavelengths_host, const float* background_host,
+                          const float* total, const uint32_t* rmax_bits, const float* g_image, float* red,
+                          float* g_total, float* d_fields, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
