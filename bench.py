@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -128,11 +128,18 @@ def cpu_frame_time(n_sample, seed=0):
     return time.perf_counter() - t0
 
 
+def calibrate_sample(budget_s):
+    """Number of Gaussians whose fwd+bwd takes about budget_s on this host (second probe: the first pays
+    one-off import / allocator costs; cost grows a little faster than linearly, hence the 0.7)."""
+    cpu_frame_time(100)
+    t_probe = cpu_frame_time(400)
+    return int(max(400, min(N_GAUSS, 400 * budget_s / max(t_probe, 1e-3) * 0.7)))
+
+
 def cpu_baseline(budget_s=20.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t_probe = cpu_frame_time(200)
-    n_s = int(max(200, min(N_GAUSS, 200 * budget_s / max(t_probe, 1e-3) * 0.6)))
+    n_s = calibrate_sample(budget_s)
     t = cpu_frame_time(n_s)
     est = t * (N_GAUSS / n_s)
     return {"value": 1.0 / est, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -148,8 +155,7 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     total = args.steps + args.warmup
     per_step_budget = max(2.0, min(20.0, 150.0 / max(total, 1)))
-    t_probe = cpu_frame_time(200)
-    n_s = int(max(200, min(N_GAUSS, 200 * per_step_budget / max(t_probe, 1e-3) * 0.6)))
+    n_s = calibrate_sample(per_step_budget)
     for _ in range(args.warmup):
         cpu_frame_time(n_s)
     times = [cpu_frame_time(n_s) for _ in range(args.steps)]
@@ -170,6 +176,163 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------
+# Second workload (BASELINE.json configs[2]): data-parallel decoder training step, views/s
+#   python bench.py --workload train [--gpus N via torchrun]      (fast_mode: 64x64, K=256)
+#   python bench.py --workload train_full                         (256x256, all 5,476 Gaussians)
+# --------------------------------------------------------------------------------------
+TRAIN_B = 16
+
+
+def train_batch(rank, seed=0):
+    g = torch.Generator().manual_seed(seed + 1000 * rank)
+    return (torch.randn(TRAIN_B, 384, 37, 37, generator=g), torch.rand(TRAIN_B, 1, 256, 256, generator=g),
+            torch.rand(TRAIN_B, 3, 256, 256, generator=g))
+
+
+def run_train_reference(args, rank, full):
+    """CPU arm of the training step: same decoder on the CPU, oracle renderer called once per view
+    (the reference's loop, train_gaussian_decoder.py:1209-1223)."""
+    if rank != 0:
+        return
+    from oracle import fresnel_oracle as fo
+    from fresnel_b200.training import PatchGaussianDecoder, reconstruction_losses, subsample_by_opacity
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    res, k = (256, None) if full else (64, 256)
+    views = 2 if full else TRAIN_B                       # bounded sample: views per step
+    torch.manual_seed(0)
+    model = PatchGaussianDecoder(384, 4)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    feats, depth, images = (t[:views] for t in train_batch(0))
+    cam = fo.default_camera(res)
+
+    def step():
+        opt.zero_grad()
+        g = subsample_by_opacity(model(feats, depth), k)
+        imgs, deps = [], []
+        for b in range(views):
+            i, d, _ = fo.render_tile_based(g["positions"][b], g["scales"][b], g["rotations"][b], g["colors"][b],
+                                           g["opacities"][b], cam, res, res)
+            imgs.append(i); deps.append(d)
+        tgt = F.interpolate(images, size=(res, res), mode="bilinear", align_corners=False)
+        tdep = F.interpolate(depth, size=(res, res), mode="bilinear", align_corners=False).squeeze(1)
+        reconstruction_losses(torch.stack(imgs), tgt, torch.stack(deps), tdep).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+
+    steps = max(1, min(args.steps, 3 if full else 10))
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = views / dt
+    sample = (f"oracle port, {views} views per step at {res}x{res}, "
+              f"{'all 5476' if full else 256} Gaussians per view, {steps} timed steps, {dt:.2f} s/step")
+    print(json.dumps({
+        "impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": train_workload_name(full)},
+        "cpu_baseline": {"value": value, "unit": "views/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+TRAIN_METRIC = "decoder training views/sec (experiment 2, B=16 views per GPU)"
+
+
+def train_workload_name(full):
+    return ("Gaussian decoder training step, experiment 2, DINOv2-small-shaped synthetic features, batch of 16 views "
+            "per GPU, " + ("256x256, all 5476 Gaussians per view" if full else
+                           "fast_mode: 64x64 render, 256 stochastic Gaussians per view") +
+            " (BASELINE configs[2])")
+
+
+def run_train(args, rank, world, local, full):
+    import torch.distributed as dist
+    import fresnel_b200
+    from fresnel_b200 import _lib
+    from fresnel_b200.training import DecoderTrainer, PatchGaussianDecoder
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    torch.manual_seed(0)
+    model = PatchGaussianDecoder(384, 4).to(dev)
+    res, k = (256, None) if full else (64, 256)
+    trainer = DecoderTrainer(model, res, stochastic_k=k, seed=rank)
+    trainer.broadcast_parameters()
+    host = [t.pin_memory() for t in train_batch(rank)]
+    resident = [t.to(dev) for t in host]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_resident():
+        trainer.step(*resident)
+
+    def step_e2e():
+        f, d, i = (t.to(dev, non_blocking=True) for t in host)
+        loss_host.copy_(trainer.step(f, d, i), non_blocking=True)
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.frb_launch_count()
+    barrier()
+    ms = timed(step_resident, args.steps)
+    barrier()
+    launches = L.frb_launch_count() - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, tot_e2e = tot.tolist()
+    if rank == 0:
+        h2d = sum(t.numel() * 4 for t in host)
+        print(json.dumps({
+            "metric": TRAIN_METRIC, "value": world * TRAIN_B * args.steps / (tot_ms * 1e-3), "unit": "views/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": train_workload_name(full), "views_per_gpu": TRAIN_B,
+                       "decoder_parameters": sum(p.numel() for p in model.parameters()),
+                       "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
+                       "parallelism": f"dp{world}: view batch sharded by rank, one flat NCCL all-reduce of the "
+                                      "decoder gradients per step"},
+            "e2e": {"value": world * TRAIN_B * args.steps / (tot_e2e * 1e-3), "unit": "views/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": tot_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 def main():
@@ -180,12 +343,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--t-eps", type=float, default=None)
+    ap.add_argument("--workload", default="render", choices=["render", "train", "train_full"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "render":
+        full = args.workload == "train_full"
+        if args.impl == "reference":
+            run_train_reference(args, rank, full)
+        else:
+            run_train(args, rank, world, local, full)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

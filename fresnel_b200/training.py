@@ -1,0 +1,203 @@
+"""Data-parallel decoder-training step around the CUDA renderer (BASELINE.json configs[2]).
+
+What this file is: the caller side of the hot path, restated so that the benchmark and the tests can
+run the reference's experiment-2 step without the reference tree (which does not exist on the GPU
+box): a per-patch MLP decoder with the architecture and output head of ``DirectPatchDecoder``
+(scripts/models/gaussian_decoder_models.py:622-948; 632,257 parameters at 4 Gaussians per patch), the
+HFTS stochastic subsampling (scripts/training/train_gaussian_decoder.py:1154-1187), the RGB + depth
+losses (``compute_losses`` :838-930 with SSIM / LPIPS absent, as in this image) and the step
+(``train_epoch`` :1031-1266) with ONE batched render call instead of the per-view Python loop (:1209-1223).
+
+What it adds (the reference has no distributed code, SURVEY.md note 2): one process per GPU, the view
+batch sharded across ranks, decoder gradients averaged with a single flat NCCL all-reduce per step.
+The decoder itself is plain ``nn.Linear`` layers - plumbing, not a kernel target.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .camera import Camera
+from .renderer import TileBasedRenderer
+
+
+def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
+    """6D rotation (Zhou et al. 2019) -> quaternion (w, x, y, z); gaussian_decoder_models.py:186-276
+    without the random sign jitter (deterministic; the jitter is 1e-8)."""
+    a1, a2 = rot_6d[..., :3], rot_6d[..., 3:6]
+    b1 = F.normalize(a1, dim=-1, eps=1e-6)
+    b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1 + 1e-8, dim=-1, eps=1e-6)
+    b3 = torch.cross(b1, b2, dim=-1)
+    n3 = b3.norm(dim=-1, keepdim=True)
+    b3 = torch.where(n3 < 1e-6, torch.tensor([0.0, 0.0, 1.0], device=b3.device), b3)
+    b3 = F.normalize(b3, dim=-1, eps=1e-6)
+    R = torch.stack([b1, b2, b3], dim=-1)
+    R00, R01, R02 = R[..., 0, 0], R[..., 0, 1], R[..., 0, 2]
+    R10, R11, R12 = R[..., 1, 0], R[..., 1, 1], R[..., 1, 2]
+    R20, R21, R22 = R[..., 2, 0], R[..., 2, 1], R[..., 2, 2]
+    trace = R00 + R11 + R22
+
+    def s(x):
+        return torch.sqrt(torch.clamp(x, min=1e-10)) * 2
+
+    s1, s2, s3, s4 = s(trace + 1.0), s(1.0 + R00 - R11 - R22), s(1.0 + R11 - R00 - R22), s(1.0 + R22 - R00 - R11)
+    cases = (
+        (0.25 * s1, (R21 - R12) / s1, (R02 - R20) / s1, (R10 - R01) / s1),
+        ((R21 - R12) / s2, 0.25 * s2, (R01 + R10) / s2, (R02 + R20) / s2),
+        ((R02 - R20) / s3, (R01 + R10) / s3, 0.25 * s3, (R12 + R21) / s3),
+        ((R10 - R01) / s4, (R02 + R20) / s4, (R12 + R21) / s4, 0.25 * s4),
+    )
+    c1, c2, c3 = trace > 0, (R00 > R11) & (R00 > R22), R11 > R22
+    q = [torch.where(c1, cases[0][k], torch.where(c2, cases[1][k], torch.where(c3, cases[2][k], cases[3][k])))
+         for k in range(4)]
+    return F.normalize(torch.stack(q, dim=-1), dim=-1, eps=1e-6)
+
+
+class PatchGaussianDecoder(nn.Module):
+    """Per-patch MLP: (B, 384, 37, 37) features -> K Gaussians per patch (experiment 2 of the reference).
+
+    MLP 384 -> 512 -> 512 -> 256 -> 128 -> K*16 with ReLU + dropout, grid positions with a learned 0.25
+    offset, z locked to depth_offset - 2 * depth, softplus scales, 6D rotations, sigmoid colour / opacity
+    (gaussian_decoder_models.py:740-948, default flags).
+    """
+
+    def __init__(self, feature_dim: int = 384, gaussians_per_patch: int = 4, hidden_dims=(512, 512, 256, 128),
+                 dropout: float = 0.1):
+        super().__init__()
+        self.gaussians_per_patch = gaussians_per_patch
+        layers, prev = [], feature_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(prev, h), nn.ReLU(inplace=True)]
+            if dropout > 0:
+                layers.append(nn.Dropout(dropout))
+            prev = h
+        layers.append(nn.Linear(prev, gaussians_per_patch * 16))
+        self.mlp = nn.Sequential(*layers)
+        self.depth_offset = nn.Parameter(torch.tensor(-2.0))
+
+    def forward(self, features: torch.Tensor, depth: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        B, C, H, W = features.shape
+        K = self.gaussians_per_patch
+        out = self.mlp(features.permute(0, 2, 3, 1).reshape(B * H * W, C)).reshape(B, H, W, K, 16)
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device=features.device),
+                                torch.linspace(-1, 1, W, device=features.device), indexing="ij")
+        base_x = xs[None, :, :, None].expand(B, -1, -1, K)
+        base_y = ys[None, :, :, None].expand(B, -1, -1, K)
+        if depth is not None:
+            grid = F.interpolate(depth, (H, W), mode="bilinear", align_corners=False)
+            base_z = self.depth_offset + grid.squeeze(1).unsqueeze(-1).expand(-1, -1, -1, K) * (-2)
+        else:
+            base_z = self.depth_offset.expand(B, H, W, K)
+        positions = torch.stack([base_x + out[..., 0] * 0.25, base_y + out[..., 1] * 0.25, base_z], dim=-1)
+        scales = torch.clamp(F.softplus(torch.clamp(out[..., 3:6], min=-10, max=20) + 1.0) * 0.15, min=1e-6, max=2.0)
+        N = H * W * K
+        return {
+            "positions": positions.reshape(B, N, 3),
+            "scales": scales.reshape(B, N, 3),
+            "rotations": rotation_6d_to_quaternion(out[..., 6:12]).reshape(B, N, 4),
+            "colors": torch.sigmoid(out[..., 12:15]).reshape(B, N, 3),
+            "opacities": torch.sigmoid(out[..., 15]).reshape(B, N),
+        }
+
+
+def subsample_by_opacity(gaussians: Dict[str, torch.Tensor], k: int,
+                         generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+    """HFTS stochastic rendering: keep K Gaussians drawn without replacement with p ~ mean opacity
+    (train_gaussian_decoder.py:1154-1187)."""
+    n = gaussians["positions"].shape[1]
+    if k is None or k >= n:
+        return gaussians
+    with torch.no_grad():
+        w = gaussians["opacities"].mean(dim=0) + 1e-6
+        idx = torch.multinomial(w / w.sum(), k, replacement=False, generator=generator)
+    return {name: t[:, idx] for name, t in gaussians.items()}
+
+
+def reconstruction_losses(rendered, target, rendered_depth=None, target_depth=None, rgb_weight: float = 1.0,
+                          depth_weight: float = 0.1) -> torch.Tensor:
+    """L1 RGB + normalised depth L1 (compute_losses, train_gaussian_decoder.py:838-930 with the SSIM and
+    LPIPS terms absent - neither package is installed in this image, and the reference then drops them)."""
+    loss = rgb_weight * F.l1_loss(rendered, target)
+    if rendered_depth is not None and target_depth is not None:
+        rd = (rendered_depth - rendered_depth.mean()) / torch.clamp(rendered_depth.std(), min=1e-4)
+        td = (target_depth - target_depth.mean()) / torch.clamp(target_depth.std(), min=1e-4)
+        loss = loss + depth_weight * F.l1_loss(rd, td)
+    return loss
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: Optional[int] = None,
+                        group=None) -> int:
+    """Average gradients over ranks with ONE flat all-reduce (the decoder is 2.5 MB: a single bucket;
+    NVSwitch makes the collective latency-bound, so fewer launches beats overlap here).
+    Returns the number of elements reduced.  No-op outside a process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = world_size or dist.get_world_size(group)
+    if world == 1:
+        return 0
+    params = [p for p in params if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return off
+
+
+def shard_batch(n_items: int, rank: int, world: int) -> range:
+    """Indices of a global batch owned by ``rank`` (contiguous blocks, remainder to the low ranks)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+class DecoderTrainer:
+    """One optimisation step of experiment 2: decoder -> [subsample] -> batched render -> losses ->
+    backward -> gradient all-reduce -> clip -> AdamW (train_epoch, train_gaussian_decoder.py:1031-1266)."""
+
+    def __init__(self, model: nn.Module, render_size: int, lr: float = 1e-4, stochastic_k: Optional[int] = None,
+                 seed: int = 0, weight_decay: float = 0.01):
+        self.model = model
+        self.render_size = render_size
+        self.renderer = TileBasedRenderer(render_size, render_size)
+        self.camera = Camera(0.8 * render_size, 0.8 * render_size, render_size / 2, render_size / 2, render_size,
+                             render_size)                       # train_gaussian_decoder.py:1910-1917
+        self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.stochastic_k = stochastic_k
+        dev = next(model.parameters()).device
+        self.generator = torch.Generator(device=dev)
+        self.generator.manual_seed(seed)
+
+    def broadcast_parameters(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for p in self.model.parameters():
+                dist.broadcast(p.data, src=0)
+
+    def step(self, features: torch.Tensor, depth: torch.Tensor, images: torch.Tensor) -> torch.Tensor:
+        """features (B, 384, 37, 37), depth (B, 1, h, w), images (B, 3, h, w) on the device; returns the loss."""
+        R = self.render_size
+        self.optimizer.zero_grad(set_to_none=True)
+        g = self.model(features, depth)
+        g = subsample_by_opacity(g, self.stochastic_k, self.generator)
+        rendered, rendered_depth, _ = self.renderer.render_batch(g["positions"], g["scales"], g["rotations"],
+                                                                 g["colors"], g["opacities"], self.camera)
+        if images.shape[-1] != R:
+            images = F.interpolate(images, size=(R, R), mode="bilinear", align_corners=False)
+        target_depth = F.interpolate(depth, size=(R, R), mode="bilinear", align_corners=False).squeeze(1)
+        loss = reconstruction_losses(rendered, images, rendered_depth, target_depth)
+        loss.backward()
+        allreduce_gradients(self.model.parameters())
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+        self.optimizer.step()
+        return loss.detach()

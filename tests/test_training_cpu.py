@@ -1,0 +1,102 @@
+"""CPU tier: host-side logic of the data-parallel decoder step (gloo, world_size 2) and the decoder
+restatement against the reference module when the reference tree is present (this container only)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fresnel_b200.training import (PatchGaussianDecoder, allreduce_gradients, reconstruction_losses,
+                                   rotation_6d_to_quaternion, shard_batch, subsample_by_opacity)
+
+REF = "/root/reference/scripts"
+
+
+def test_decoder_parameter_count_and_shapes():
+    m = PatchGaussianDecoder(384, 4)
+    assert sum(p.numel() for p in m.parameters()) == 632_257          # SURVEY.md section 2, component 3
+    out = m(torch.randn(2, 384, 5, 7), torch.rand(2, 1, 32, 32))
+    n = 5 * 7 * 4
+    assert out["positions"].shape == (2, n, 3) and out["rotations"].shape == (2, n, 4)
+    assert out["opacities"].shape == (2, n) and float(out["scales"].min()) > 0
+    assert torch.allclose(out["rotations"].norm(dim=-1), torch.ones(2, n), atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_decoder_matches_reference_module():
+    sys.path.insert(0, REF)
+    from models.gaussian_decoder_models import DirectPatchDecoder
+    torch.manual_seed(0)
+    ref = DirectPatchDecoder(feature_dim=384, gaussians_per_patch=4).eval()
+    mine = PatchGaussianDecoder(384, 4).eval()
+    sd = {k.replace("mlp.net.", "mlp."): v for k, v in ref.state_dict().items()}
+    mine.load_state_dict(sd)
+    f, d = torch.randn(2, 384, 37, 37), torch.rand(2, 1, 64, 64)
+    with torch.no_grad():
+        a, b = ref(f, d), mine(f, d)
+    for k in ("positions", "scales", "rotations", "colors", "opacities"):
+        # rotations: the reference adds a random 1e-8 sign jitter before a normalise; near-degenerate
+        # matrix -> quaternion branches amplify it to a few 1e-5
+        assert torch.allclose(a[k], b[k], atol=3e-4 if k == "rotations" else 2e-5), k
+
+
+def test_quaternion_from_6d_is_a_rotation():
+    q = rotation_6d_to_quaternion(torch.randn(100, 6))
+    assert torch.allclose(q.norm(dim=-1), torch.ones(100), atol=1e-5)
+    ident = rotation_6d_to_quaternion(torch.tensor([[1.0, 0, 0, 0, 1.0, 0]]))
+    assert torch.allclose(ident, torch.tensor([[1.0, 0, 0, 0]]), atol=1e-5)
+
+
+def test_subsample_and_losses():
+    g = {"positions": torch.randn(3, 50, 3), "opacities": torch.rand(3, 50)}
+    s = subsample_by_opacity(g, 10, torch.Generator().manual_seed(0))
+    assert s["positions"].shape == (3, 10, 3) and s["opacities"].shape == (3, 10)
+    assert subsample_by_opacity(g, 50) is g
+    x = torch.rand(2, 3, 8, 8)
+    assert float(reconstruction_losses(x, x, torch.rand(2, 8, 8), torch.rand(2, 8, 8))) > 0
+    assert float(reconstruction_losses(x, x)) == 0.0
+
+
+def test_shard_batch_partitions():
+    for n, w in ((16, 2), (17, 4), (5, 8)):
+        parts = [list(shard_batch(n, r, w)) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        data = [torch.randn(4, 6, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        grads = []
+        for r in range(world):                     # every rank also computes the other ranks' gradients
+            model.zero_grad()
+            model(data[r]).pow(2).mean().backward()
+            grads.append([p.grad.clone() for p in model.parameters()])
+        model.zero_grad()
+        model(data[rank]).pow(2).mean().backward()
+        n = allreduce_gradients(model.parameters())
+        want = [sum(g[i] for g in grads) / world for i in range(len(grads[0]))]
+        ok = all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(model.parameters(), want))
+        q.put((rank, ok, n))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert res[0][2] == 6 * 5 + 5 + 5 * 2 + 2
