@@ -23,6 +23,8 @@ _SIGNATURES = {
     "frb_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "frb_sort_workspace_bytes": (c_size_t, [c_int]),
     "frb_radix_sort_pairs": (c_int, [c_int, P, P, P, P, c_int, c_int, P, P]),
+    "frb_radix_sort_pairs_dev": (c_int, [c_int, P, P, P, P, P, c_int, c_int, P, P]),
+    "frb_ranges_and_gather_dev": (c_int, [c_int, P, P, P, c_int, P, P, P, P, P, P]),
     "frb_depth_order_workspace_bytes": (c_size_t, [c_int]),
     "frb_depth_order": (c_int, [c_int, P, P, P, P]),
     "frb_scan_workspace_bytes": (c_size_t, [c_int]),

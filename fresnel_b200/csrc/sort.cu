@@ -28,6 +28,7 @@ constexpr int SORT_IPT = 8;                                // items per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;         // 2048 items per block
 constexpr int SORT_WARP_ITEMS = 32 * SORT_IPT;
 constexpr int MAX_PASSES = 8;
+constexpr int SORT_GRID_MAX = 148 * 6;                     // persistent grid: 6 resident blocks per SM
 
 constexpr uint32_t FLAG_AGG = 1u << 30;      // tile count published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;   // inclusive prefix over tiles 0..this published
@@ -56,9 +57,10 @@ constexpr int WS_STATUS = WS_ERROR + 8;
 // Global digit histograms of all passes in one read of the keys.
 template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_all_kernel(int m, const KeyT* __restrict__ keys, const __grid_constant__ PassPlan plan,
-                      uint32_t* __restrict__ hist) {
+radix_hist_all_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys,
+                      const __grid_constant__ PassPlan plan, uint32_t* __restrict__ hist) {
     __shared__ uint32_t cnt[MAX_PASSES][RADIX];
+    if (m_dev) m = min(m, (int)*m_dev);
     for (int p = 0; p < plan.n_passes; ++p) cnt[p][threadIdx.x] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * SORT_THREADS + threadIdx.x; i < m;
@@ -87,7 +89,8 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // (tile, warp, round, lane) order is input order.  GEN_VALS: values are the input indices.
 template <typename KeyT, bool GEN_VALS>
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_onesweep_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
+                      const uint32_t* __restrict__ vals_in,
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
                       const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag) {
@@ -96,10 +99,16 @@ radix_onesweep_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* _
     __shared__ uint32_t scan_ws[SORT_WARPS];
     __shared__ uint32_t tile_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);   // tiles are numbered in start order
+    if (m_dev) m = min(m, (int)*m_dev);                     // capacity mode: the true count lives on the device
+    // persistent blocks: keep drawing tiles (numbered in start order, so every predecessor of a tile has
+    // started) until the keys run out
+    while (true) {
+    __syncthreads();                                        // shared arrays of the previous tile are free
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     for (int d = lane; d < RADIX; d += 32) cnt[warp][d] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
+    if ((long long)tile * SORT_TILE >= m) return;           // past the end: nobody looks back at this tile
 
     long long base = (long long)tile * SORT_TILE + warp * SORT_WARP_ITEMS;
     KeyT key[SORT_IPT];
@@ -185,6 +194,7 @@ radix_onesweep_kernel(int m, const KeyT* __restrict__ keys_in, const uint32_t* _
             vals_out[pos] = GEN_VALS ? (uint32_t)i : vals_in[i];
         }
     }
+    }   // while: next tile
 }
 
 size_t sort_ws_words(int m, int n_passes) {
@@ -195,7 +205,7 @@ size_t sort_ws_words(int m, int n_passes) {
 // when first_in is given, pass 0 reads keys from there (and generates values if vals_first is null).
 // Returns in *result_in_b whether the sorted data ended in the B buffers.
 template <typename KeyT>
-int radix_sort_impl(int m, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
+int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
                     KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
                     bool* result_in_b) {
     PassPlan plan;
@@ -209,7 +219,8 @@ int radix_sort_impl(int m, const KeyT* first_keys, const uint32_t* first_vals, K
     }
     const int n_blocks = frb_div_up(m, SORT_TILE);
     FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
-    radix_hist_all_kernel<KeyT><<<min(n_blocks, 592), SORT_THREADS, 0, st>>>(m, first_keys, plan, ws + WS_HIST);
+    radix_hist_all_kernel<KeyT><<<min(n_blocks, 592), SORT_THREADS, 0, st>>>(m, m_dev, first_keys, plan,
+                                                                             ws + WS_HIST);
     frb_note_launches(1);
     const KeyT* kin = first_keys;
     const uint32_t* vin = first_vals;
@@ -219,12 +230,12 @@ int radix_sort_impl(int m, const KeyT* first_keys, const uint32_t* first_vals, K
         uint32_t* vout = to_b ? vals_b : vals_a;
         uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RADIX;
         if (vin == nullptr)
-            radix_onesweep_kernel<KeyT, true><<<n_blocks, SORT_THREADS, 0, st>>>(
-                m, kin, nullptr, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
+            radix_onesweep_kernel<KeyT, true><<<min(n_blocks, SORT_GRID_MAX), SORT_THREADS, 0, st>>>(
+                m, m_dev, kin, nullptr, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
                 ws + WS_TICKET + p, ws + WS_ERROR);
         else
-            radix_onesweep_kernel<KeyT, false><<<n_blocks, SORT_THREADS, 0, st>>>(
-                m, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
+            radix_onesweep_kernel<KeyT, false><<<min(n_blocks, SORT_GRID_MAX), SORT_THREADS, 0, st>>>(
+                m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
                 ws + WS_TICKET + p, ws + WS_ERROR);
         frb_note_launches(1);
         FRB_LAUNCH_CHECK();
@@ -368,17 +379,20 @@ tile_ranges_kernel(int m, const uint64_t* __restrict__ keys, int2* __restrict__ 
 // 3 threads per instance, one float4 each: 48-byte records land contiguous and coalesced.
 // keys != NULL also writes the tile ranges (fused frb_tile_ranges).
 __global__ void __launch_bounds__(256)
-gather_records_kernel(int m, const uint32_t* __restrict__ gids, const float4* __restrict__ records,
+gather_records_kernel(int m, const uint32_t* __restrict__ m_dev, const uint32_t* __restrict__ gids,
+                      const float4* __restrict__ records,
                       float4* __restrict__ sorted_records, const float* __restrict__ phases,
                       float* __restrict__ sorted_phases, const uint64_t* __restrict__ keys,
                       int2* __restrict__ ranges) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3ll * m) return;
-    int i = (int)(t / 3), part = (int)(t - 3ll * i);
-    uint32_t g = gids[i];
-    sorted_records[t] = records[3 * (size_t)g + part];
-    if (part == 0 && sorted_phases) sorted_phases[i] = phases[g];
-    if (part == 1 && keys) range_boundary(i, m, keys, ranges);
+    if (m_dev) m = min(m, (int)*m_dev);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 3ll * m;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / 3), part = (int)(t - 3ll * i);
+        uint32_t g = gids[i];
+        sorted_records[t] = records[3 * (size_t)g + part];
+        if (part == 0 && sorted_phases) sorted_phases[i] = phases[g];
+        if (part == 1 && keys) range_boundary(i, m, keys, ranges);
+    }
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -390,15 +404,14 @@ extern "C" size_t frb_sort_workspace_bytes(int m) {
     return sizeof(uint32_t) * sort_ws_words(m, MAX_PASSES);
 }
 
-extern "C" int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
-                                    uint32_t* vals_tmp, int begin_bit, int end_bit, void* workspace,
-                                    void* stream) {
+static int sort_pairs(int m, const uint32_t* m_dev, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
+                      uint32_t* vals_tmp, int begin_bit, int end_bit, void* workspace, void* stream) {
     if (m < 0 || begin_bit < 0 || end_bit > 64) return FRB_E_INVALID;
     if (m == 0 || end_bit <= begin_bit) return 0;
     if (!keys || !vals || !keys_tmp || !vals_tmp || !workspace) return FRB_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     bool in_b = false;
-    int rc = radix_sort_impl<uint64_t>(m, keys, vals, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit,
+    int rc = radix_sort_impl<uint64_t>(m, m_dev, keys, vals, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit,
                                        (uint32_t*)workspace, st, &in_b);
     if (rc) return rc;
     if (in_b) {
@@ -406,6 +419,19 @@ extern "C" int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint6
         FRB_CUDA_OK(cudaMemcpyAsync(vals, vals_tmp, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToDevice, st));
     }
     return 0;
+}
+
+extern "C" int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
+                                    uint32_t* vals_tmp, int begin_bit, int end_bit, void* workspace,
+                                    void* stream) {
+    return sort_pairs(m, nullptr, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit, workspace, stream);
+}
+
+extern "C" int frb_radix_sort_pairs_dev(int m_capacity, const uint32_t* m_dev, uint64_t* keys, uint32_t* vals,
+                                        uint64_t* keys_tmp, uint32_t* vals_tmp, int begin_bit, int end_bit,
+                                        void* workspace, void* stream) {
+    if (!m_dev) return FRB_E_INVALID;
+    return sort_pairs(m_capacity, m_dev, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit, workspace, stream);
 }
 
 extern "C" size_t frb_depth_order_workspace_bytes(int n) {
@@ -427,7 +453,7 @@ extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* orde
     uint32_t* ws = (uint32_t*)(w + 3 * a);
     // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
     bool in_b = false;
-    int rc = radix_sort_impl<uint32_t>(n, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b);
+    int rc = radix_sort_impl<uint32_t>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b);
     if (rc) return rc;
     if (!in_b) return FRB_E_INVALID;   // cannot happen with an even number of passes
     return 0;
@@ -491,8 +517,25 @@ extern "C" int frb_gather_records(int m, const uint32_t* gids, const float* reco
     if (m == 0) return 0;
     if (!gids || !records || !sorted_records) return FRB_E_INVALID;
     if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
-    gather_records_kernel<<<frb_div_up(3ll * m, 256), 256, 0, (cudaStream_t)stream>>>(
-        m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, nullptr, nullptr);
+    gather_records_kernel<<<min(frb_div_up(3ll * m, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        m, nullptr, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, nullptr, nullptr);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int ranges_and_gather(int m, const uint32_t* m_dev, const uint64_t* keys, const uint32_t* gids,
+                             int n_tiles, int32_t* ranges, const float* records, float* sorted_records,
+                             const float* phases, float* sorted_phases, void* stream) {
+    if (m < 0 || n_tiles < 0 || !ranges) return FRB_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, st));
+    if (m == 0) return 0;
+    if (!keys || !gids || !records || !sorted_records) return FRB_E_INVALID;
+    if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
+    gather_records_kernel<<<min(frb_div_up(3ll * m, 256), 148 * 32), 256, 0, st>>>(
+        m, m_dev, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, keys,
+        (int2*)ranges);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -501,15 +544,15 @@ extern "C" int frb_gather_records(int m, const uint32_t* gids, const float* reco
 extern "C" int frb_ranges_and_gather(int m, const uint64_t* keys, const uint32_t* gids, int n_tiles,
                                      int32_t* ranges, const float* records, float* sorted_records,
                                      const float* phases, float* sorted_phases, void* stream) {
-    if (m < 0 || n_tiles < 0 || !ranges) return FRB_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, st));
-    if (m == 0) return 0;
-    if (!keys || !gids || !records || !sorted_records) return FRB_E_INVALID;
-    if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
-    gather_records_kernel<<<frb_div_up(3ll * m, 256), 256, 0, st>>>(
-        m, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, keys, (int2*)ranges);
-    frb_note_launches(1);
-    FRB_LAUNCH_CHECK();
-    return 0;
+    return ranges_and_gather(m, nullptr, keys, gids, n_tiles, ranges, records, sorted_records, phases,
+                             sorted_phases, stream);
+}
+
+extern "C" int frb_ranges_and_gather_dev(int m_capacity, const uint32_t* m_dev, const uint64_t* keys,
+                                         const uint32_t* gids, int n_tiles, int32_t* ranges, const float* records,
+                                         float* sorted_records, const float* phases, float* sorted_phases,
+                                         void* stream) {
+    if (!m_dev) return FRB_E_INVALID;
+    return ranges_and_gather(m_capacity, m_dev, keys, gids, n_tiles, ranges, records, sorted_records, phases,
+                             sorted_phases, stream);
 }

@@ -23,6 +23,8 @@ from .camera import camera_vector
 TILE = 16
 RECORD_FLOATS = 12
 DEFAULT_T_EPS = 2.0 ** -20   # pixel stops once transmittance < t_eps; 0 = never (exact mode)
+INSTANCE_BYTES = 2 * 12 + 48 + 32            # keys+ids (two copies), sorted record, side record
+SYNC_FREE_BUDGET_BYTES = 4 << 30             # worst-case instance buffers above this use the host-sync path
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -99,18 +101,23 @@ def _check_inputs(**tensors):
 class TileBins:
     """Sorted tile instance lists of one batch of views (result of the binning stage)."""
 
-    __slots__ = ("m", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
+    __slots__ = ("m", "m_dev", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
                  "records", "rects", "depth_bits", "touched")
 
 
 def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
                width: int, height: int, max_radius: float, phases=None, keep_debug: bool = False,
-               sort: bool = True, low_word_fn=None, presort: bool = True) -> TileBins:
+               sort: bool = True, low_word_fn=None, presort: bool = True, sync: Optional[bool] = None) -> TileBins:
     """Projection + binning: everything up to the per-tile sorted record lists.
 
     Sequences frb_project_fwd -> frb_depth_order -> frb_tile_offsets -> frb_bin_emit ->
     frb_radix_sort_pairs (tile bits only) -> frb_tile_ranges -> frb_gather_records.
     One device->host read (the instance count M) sizes the instance buffers.
+
+    ``sync``: True reads the instance count M back (one 4-byte device->host read, buffers sized exactly);
+    False never synchronises: buffers are sized for the worst case (every Gaussian touching
+    ``max_tiles_per_gaussian`` tiles) and the kernels read M on the device; None (default) picks False
+    when the worst case fits in ``SYNC_FREE_BUDGET_BYTES``.
 
     ``sort=False`` emits in index order and sorts all 64 key bits (test path).  ``low_word_fn(bins)``
     replaces the depth bits as the low key word (ASM: the depth-plane index).  ``presort=False`` skips
@@ -145,7 +152,17 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     offsets = torch.empty(n + 1, **i32)
     ws = torch.empty(max(L.frb_scan_workspace_bytes(n), 4), dtype=torch.uint8, device=dev)
     _call("frb_tile_offsets", L.frb_tile_offsets, n, _ptr(b.touched), _ptr(b.order), _ptr(offsets), _ptr(ws), st)
-    m = int(offsets[n].item())          # the one host sync of the forward pass
+    span = -(-(2 * int(math.ceil(max_radius)) + 2) // TILE) + 1       # tiles a rectangle can span per axis
+    worst = n * min(tiles_x * tiles_y, span * span)
+    if sync is None:
+        sync = (keep_debug or not sort or phases is not None or low_word_fn is not None or not presort
+                or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES)
+    if sync:
+        m = int(offsets[n].item())      # the one host sync of the forward pass
+        m_dev = None
+    else:
+        m = worst                       # capacity; the true count stays on the device (offsets[n])
+        m_dev = offsets[n:]
     b.m = m
 
     b.ranges = torch.empty(n_tiles, 2, **i32)
@@ -155,18 +172,28 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     b.sorted_phases = None
     if m > 0:
         _call("frb_bin_emit", L.frb_bin_emit, n, n_views, width, height, _ptr(b.records), _ptr(b.depth_bits),
-                                  _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st)
+              _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st)
         keys_tmp = torch.empty(m, dtype=torch.int64, device=dev)
         vals_tmp = torch.empty(m, **i32)
         ws = torch.empty(L.frb_sort_workspace_bytes(m), dtype=torch.uint8, device=dev)
         tile_bits = max(1, int(math.ceil(math.log2(max(n_tiles, 2)))))
         begin = 32 if sort else 0
-        _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs, m, _ptr(b.keys), _ptr(b.sorted_gids), _ptr(keys_tmp),
-                                          _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
+        if sync:
+            _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs, m, _ptr(b.keys), _ptr(b.sorted_gids),
+                  _ptr(keys_tmp), _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
+        else:
+            _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs_dev, m, _ptr(m_dev), _ptr(b.keys),
+                  _ptr(b.sorted_gids), _ptr(keys_tmp), _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
     if phases is not None:
         b.sorted_phases = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
-    _call("frb_ranges_and_gather", L.frb_ranges_and_gather, m, _ptr(b.keys), _ptr(b.sorted_gids), n_tiles,
-          _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases), _ptr(b.sorted_phases), st)
+    if sync:
+        _call("frb_ranges_and_gather", L.frb_ranges_and_gather, m, _ptr(b.keys), _ptr(b.sorted_gids), n_tiles,
+              _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases), _ptr(b.sorted_phases), st)
+    else:
+        _call("frb_ranges_and_gather", L.frb_ranges_and_gather_dev, m, _ptr(m_dev), _ptr(b.keys),
+              _ptr(b.sorted_gids), n_tiles, _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases),
+              _ptr(b.sorted_phases), st)
+    b.m_dev = m_dev
     return b
 
 

@@ -114,6 +114,16 @@ int frb_ranges_and_gather(int m, const uint64_t* keys, const uint32_t* gids, int
                           int32_t* ranges, const float* records, float* sorted_records,
                           const float* phases, float* sorted_phases, void* stream);
 
+/* Capacity mode (no host synchronisation): buffers hold m_capacity instances, the true count is read
+ * on the device from *m_dev (= offsets[n] of frb_tile_offsets); entries past it are never touched. */
+int frb_radix_sort_pairs_dev(int m_capacity, const uint32_t* m_dev, uint64_t* keys, uint32_t* vals,
+                             uint64_t* keys_tmp, uint32_t* vals_tmp, int begin_bit, int end_bit,
+                             void* workspace, void* stream);
+int frb_ranges_and_gather_dev(int m_capacity, const uint32_t* m_dev, const uint64_t* keys,
+                              const uint32_t* gids, int n_tiles, int32_t* ranges, const float* records,
+                              float* sorted_records, const float* phases, float* sorted_phases,
+                              void* stream);
+
 /* ---- compositing ------------------------------------------------------ */
 /* t_eps: a pixel stops once its transmittance has fallen below max(t_eps, 1e-20).
  * sorted_phases == NULL selects plain alpha compositing; otherwise Fresnel phase blending
