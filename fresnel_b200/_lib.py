@@ -36,6 +36,11 @@ _SIGNATURES = {
     "frb_phase_ckpt_floats": (c_size_t, [c_int, c_int]),
     "frb_composite_fwd": (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),
+    "frb_tile_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, P]),
+    "frb_tile_render_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, c_float, c_int, c_int, P, c_float, c_int, P, P,
+                                    P, P, P, P]),
+    "frb_tile_render_bwd": (c_int, [c_int, c_int, P, P, P, P, c_int, c_int, P, c_int, P, P, P, P, P, P, P, P, P, P,
+                                    P]),
     "frb_wave_prepare": (c_int, [c_int, P, P, c_int, P, P]),
     "frb_wave_gather": (c_int, [c_int, P, P, P, P]),
     "frb_wave_splat_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
@@ -50,6 +55,14 @@ _SIGNATURES = {
 }
 
 _OPTIONAL = {}
+
+
+class TileLayout(ctypes.Structure):
+    """FrbTileLayout of include/fresnel_b200.h."""
+    _fields_ = [(name, c_size_t) for name in (
+        "ranges", "state_T", "state_n", "sorted_gids", "sorted_records", "persist_bytes", "records", "depth_bits",
+        "touched", "order", "offsets", "depth_ws", "scan_ws", "keys", "keys_tmp", "vals_tmp", "sort_ws",
+        "scratch_bytes")]
 
 
 class FresnelB200Error(RuntimeError):

@@ -220,16 +220,15 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         frb_mbar_fence_init();
     }
     __syncthreads();
-    {
-        int wmax = my_n;
+    int warp_n = my_n;                                       // entries applied by at least one pixel of the warp
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        if (lane == 0) atomicMax(&sm.max_n, wmax);
-    }
+    for (int o = 16; o > 0; o >>= 1) warp_n = max(warp_n, __shfl_xor_sync(0xffffffffu, warp_n, o));
+    if (lane == 0) atomicMax(&sm.max_n, warp_n);
     __syncthreads();
     const int count = min(sm.max_n, range.y - range.x);
     const int n_batches = (count + BATCH - 1) / BATCH;
     if (n_batches == 0) return;
+    const int wx0 = tx * TILE, wx1 = wx0 + TILE, wy0 = ty * TILE + 2 * warp, wy1 = wy0 + 2;
 
     // batches are visited last to first; ring slot (visit % STAGES) holds visit
     auto issue = [&](int visit) {
@@ -259,36 +258,70 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 
         for (int sb = (cnt - 1) >> 5; sb >= 0; --sb) {
             const int sub_cnt = min(32, cnt - sb * 32);
-            // ---- phase 1: lane = pixel -------------------------------------------------
-            uint32_t gmask = 0;
-            const int local_n = my_n - (b * BATCH + sb * 32);    // entries j < local_n were applied
-            uint32_t bit = 1u << (sub_cnt - 1);
-            for (int j = sub_cnt - 1; j >= 0; --j, bit >>= 1) {
+            // ---- candidates: lane l tests record l of the block against this warp's 16x2 pixels ----
+            const int base_n = b * BATCH + sb * 32;
+            uint32_t cand;
+            {
+                bool ok = false;
+                if (lane < sub_cnt) {
+                    const uint32_t lo = __float_as_uint(rec[3 * (sb * 32 + lane) + 1].w);
+                    const uint32_t hi = __float_as_uint(rec[3 * (sb * 32 + lane) + 2].w) & 0x7fff7fffu;
+                    ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
+                         (int)(hi >> 16) > wy0;
+                }
+                cand = __ballot_sync(0xffffffffu, ok);
+                const int wn = warp_n - base_n;              // entries >= wn were applied by no pixel of the warp
+                if (wn < 32) cand &= (wn <= 0) ? 0u : ((1u << wn) - 1u);
+            }
+            // ---- phase 1: lane = pixel, candidates back to front ----------------------------
+            const uint32_t gmask = cand;
+            const int local_n = my_n - base_n;                   // entries j < local_n were applied
+            // Two candidates per iteration: everything that does not depend on the running (T, S) is
+            // evaluated for both first (independent instruction streams hide the LDS / MUFU latency),
+            // then the two short serial tails run back to back.
+            struct Pre { float a, inv_om, w; bool active, pass; };
+            auto stage_a = [&](int j) {
+                Pre p;
                 const int jb = sb * 32 + j;
-                float4 r1 = rec[3 * jb + 1], r2 = rec[3 * jb + 2];
-                bool active = (j < local_n) &&
-                              rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
-                if (!__any_sync(0xffffffffu, active)) continue;
-                gmask |= bit;
+                const float4 r1 = rec[3 * jb + 1], r2 = rec[3 * jb + 2];
+                p.active = (j < local_n) &&
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                const float4 r0 = rec[3 * jb + 0];
+                const float dx = fpx - r0.x, dy = fpy - r0.y;
+                const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                const float araw = frb_ex2(power) * r1.y;
+                p.a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
+                p.pass = (p.a == araw);                       // clamp gate: 0 <= g*o <= 0.99
+                p.inv_om = frb_rcp(1.0f - p.a);
+                p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                return p;
+            };
+            auto stage_b = [&](int j, const Pre& p) {
                 float2 out = make_float2(0.f, 0.f);
-                if (active) {
-                    float4 r0 = rec[3 * jb + 0];
-                    float dx = fpx - r0.x, dy = fpy - r0.y;
-                    float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                    float g = frb_ex2(power);
-                    float araw = g * r1.y;
-                    float a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
-                    float inv_om = frb_rcp(1.0f - a);
-                    float Ti = T * inv_om;
-                    float c = a * Ti;
-                    float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
-                    float dalpha = Ti * w - (S + TX) * inv_om;
-                    S = fmaf(c, w, S);
+                if (p.active) {
+                    const float Ti = T * p.inv_om;
+                    const float c = p.a * Ti;
+                    const float dalpha = Ti * p.w - (S + TX) * p.inv_om;
+                    S = fmaf(c, p.w, S);
                     T = Ti;
                     out.x = c;
-                    out.y = (a == araw) ? dalpha : 0.0f;      // clamp gate: 0 <= g*o <= 0.99
+                    out.y = p.pass ? dalpha : 0.0f;
                 }
                 my_pair[j * PAIR_STRIDE + lane] = out;
+            };
+            while (cand) {
+                const int j0 = 31 - __clz(cand);
+                cand ^= 1u << j0;
+                if (cand) {
+                    const int j1 = 31 - __clz(cand);
+                    cand ^= 1u << j1;
+                    const Pre p0 = stage_a(j0), p1 = stage_a(j1);
+                    stage_b(j0, p0);
+                    stage_b(j1, p1);
+                } else {
+                    const Pre p0 = stage_a(j0);
+                    stage_b(j0, p0);
+                }
             }
             __syncwarp();
             // ---- phase 2: lane = Gaussian ------------------------------------------------

@@ -1,0 +1,116 @@
+// Whole-pass entry points of the tile renderer: one C call enqueues every stage of the forward
+// (or backward) pass on the stream, carving its buffers out of two caller-provided arenas.
+// This is the capacity (sync-free) mode of DESIGN.md section 3: instance buffers are sized for
+// m_capacity entries, the true count stays on the device, and nothing here touches the host.
+// The stage functions it sequences are the ones declared in include/fresnel_b200.h.
+#include "frb_common.cuh"
+
+namespace {
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += align256(bytes);
+        return o;
+    }
+};
+
+}  // namespace
+
+// Byte offsets inside the arenas.  persist: needed again by the backward pass.  scratch: forward only.
+extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_capacity, FrbTileLayout* L) {
+    if (n < 0 || n_views < 1 || width < 1 || height < 1 || m_capacity < 0 || !L) return FRB_E_INVALID;
+    const size_t hw = (size_t)width * height * n_views;
+    const size_t tiles = (size_t)n_views * frb_div_up(width, FRB_TILE) * frb_div_up(height, FRB_TILE);
+    const size_t m = (size_t)m_capacity;
+    Carver p;
+    L->ranges = p.take(8 * tiles);
+    L->state_T = p.take(4 * hw);
+    L->state_n = p.take(4 * hw);
+    L->sorted_gids = p.take(4 * m);
+    L->sorted_records = p.take(48 * (m + 1));
+    L->persist_bytes = p.off;
+    Carver s;
+    L->records = s.take(48 * (size_t)n);
+    L->depth_bits = s.take(4 * (size_t)n);
+    L->touched = s.take(4 * (size_t)n);
+    L->order = s.take(4 * (size_t)n);
+    L->offsets = s.take(4 * ((size_t)n + 1));
+    L->depth_ws = s.take(frb_depth_order_workspace_bytes(n));
+    L->scan_ws = s.take(frb_scan_workspace_bytes(n));
+    L->keys = s.take(8 * m);
+    L->keys_tmp = s.take(8 * m);
+    L->vals_tmp = s.take(4 * m);
+    L->sort_ws = s.take(frb_sort_workspace_bytes(m_capacity));
+    L->scratch_bytes = s.off;
+    return 0;
+}
+
+extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, const float* scales,
+                                   const float* rotations, const float* colors, const float* opacities,
+                                   const float* camera_host, float max_radius, int width, int height,
+                                   const float* background_host, float t_eps, int m_capacity, void* persist,
+                                   void* scratch, float* image, float* depth, float* alpha, void* stream) {
+    FrbTileLayout L;
+    int rc = frb_tile_layout(n, n_views, width, height, m_capacity, &L);
+    if (rc) return rc;
+    if (!persist || !scratch) return FRB_E_INVALID;
+    char* P = (char*)persist;
+    char* S = (char*)scratch;
+    const int tiles = n_views * frb_div_up(width, FRB_TILE) * frb_div_up(height, FRB_TILE);
+    int tile_bits = 1;
+    while ((1 << tile_bits) < tiles) ++tile_bits;
+    float* records = (float*)(S + L.records);
+    uint32_t* depth_bits = (uint32_t*)(S + L.depth_bits);
+    uint32_t* touched = (uint32_t*)(S + L.touched);
+    uint32_t* order = (uint32_t*)(S + L.order);
+    uint32_t* offsets = (uint32_t*)(S + L.offsets);
+    uint64_t* keys = (uint64_t*)(S + L.keys);
+    uint32_t* gids = (uint32_t*)(P + L.sorted_gids);
+    int32_t* ranges = (int32_t*)(P + L.ranges);
+    float* sorted_records = (float*)(P + L.sorted_records);
+
+    if ((rc = frb_project_fwd(n, n_views, positions, scales, rotations, colors, opacities, camera_host, max_radius,
+                              records, nullptr, depth_bits, touched, nullptr, stream))) return rc;
+    if ((rc = frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream))) return rc;
+    if ((rc = frb_tile_offsets(n, touched, order, offsets, S + L.scan_ws, stream))) return rc;
+    if (n > 0 && m_capacity > 0) {
+        if ((rc = frb_bin_emit(n, n_views, width, height, records, depth_bits, order, offsets, keys, gids, stream)))
+            return rc;
+        if ((rc = frb_radix_sort_pairs_dev(m_capacity, offsets + n, keys, gids, (uint64_t*)(S + L.keys_tmp),
+                                           (uint32_t*)(S + L.vals_tmp), 32, 32 + tile_bits, S + L.sort_ws, stream)))
+            return rc;
+        if ((rc = frb_ranges_and_gather_dev(m_capacity, offsets + n, keys, gids, tiles, ranges, records,
+                                            sorted_records, nullptr, nullptr, stream))) return rc;
+    } else {
+        FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
+    }
+    return frb_composite_fwd(n_views, width, height, ranges, sorted_records, nullptr, 0.0f, background_host, t_eps,
+                             image, depth, alpha, (float*)(P + L.state_T), (int32_t*)(P + L.state_n), nullptr,
+                             stream);
+}
+
+// grad2d: scratch of n * FRB_GRAD_FLOATS floats (zeroed here).
+extern "C" int frb_tile_render_bwd(int n, int n_views, const float* positions, const float* scales,
+                                   const float* rotations, const float* camera_host, int width, int height,
+                                   const float* background_host, int m_capacity, const void* persist,
+                                   const float* g_image, const float* g_depth, const float* g_alpha, float* grad2d,
+                                   float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
+                                   float* g_opacities, void* stream) {
+    FrbTileLayout L;
+    int rc = frb_tile_layout(n, n_views, width, height, m_capacity, &L);
+    if (rc) return rc;
+    if (!persist || !grad2d) return FRB_E_INVALID;
+    const char* P = (const char*)persist;
+    FRB_CUDA_OK(cudaMemsetAsync(grad2d, 0, sizeof(float) * FRB_GRAD_FLOATS * (size_t)n, (cudaStream_t)stream));
+    if ((rc = frb_composite_bwd(n_views, width, height, (const int32_t*)(P + L.ranges),
+                                (const float*)(P + L.sorted_records), (const uint32_t*)(P + L.sorted_gids), nullptr,
+                                0.0f, background_host, (const float*)(P + L.state_T),
+                                (const int32_t*)(P + L.state_n), nullptr, g_image, g_depth, g_alpha, grad2d, nullptr,
+                                stream))) return rc;
+    return frb_project_bwd(n, n_views, positions, scales, rotations, camera_host, grad2d, g_positions, g_scales,
+                           g_rotations, g_colors, g_opacities, stream);
+}

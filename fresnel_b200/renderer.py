@@ -10,6 +10,7 @@ as a ``torch.autograd.Function``.  There is no CPU path: non-CUDA inputs raise.
 
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -197,6 +198,68 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     return b
 
 
+def worst_case_instances(n: int, n_views: int, width: int, height: int, max_radius: float) -> int:
+    """Upper bound on the number of tile instances: a rectangle is at most 2*max_radius + 2 pixels wide."""
+    tiles_x, tiles_y = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    span = -(-(2 * int(math.ceil(max_radius)) + 2) // TILE) + 1
+    return n * min(tiles_x * tiles_y, span * span)
+
+
+FUSED_CALLS = True      # one C call per pass (frb_tile_render_fwd / _bwd); False = stage by stage
+
+
+class _TileRenderFusedFn(torch.autograd.Function):
+    """TileBasedRenderer through the whole-pass C entry points: sync-free, two ctypes calls per frame."""
+
+    @staticmethod
+    def forward(ctx, positions, scales, rotations, colors, opacities, cfg):
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
+        L = _lib.lib()
+        dev = positions.device
+        n = positions.shape[0]
+        cap = worst_case_instances(n, n_views, width, height, max_radius)
+        lay = _lib.TileLayout()
+        _lib.check(L.frb_tile_layout(n, n_views, width, height, cap, ctypes.byref(lay)), "frb_tile_layout")
+        persist = torch.empty(max(lay.persist_bytes, 256), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(max(lay.scratch_bytes, 256), dtype=torch.uint8, device=dev)
+        image = torch.empty(n_views, 3, height, width, dtype=torch.float32, device=dev)
+        depth = torch.empty(n_views, height, width, dtype=torch.float32, device=dev)
+        alpha = torch.empty(n_views, height, width, dtype=torch.float32, device=dev)
+        cam = np.ascontiguousarray(cam_vecs, np.float32)
+        bg_host = np.asarray(bg, np.float32)
+        img_p, dep_p, alp_p = image.data_ptr(), depth.data_ptr(), alpha.data_ptr()
+        _call("frb_tile_render_fwd", L.frb_tile_render_fwd, n, n_views, _ptr(positions), _ptr(scales),
+              _ptr(rotations), _ptr(colors), _ptr(opacities), cam.ctypes.data, float(max_radius), width, height,
+              bg_host.ctypes.data, float(t_eps), cap, _ptr(persist), _ptr(scratch), img_p, dep_p, alp_p, _stream())
+        ctx.cfg, ctx.n, ctx.cap = cfg, n, cap
+        ctx.save_for_backward(positions, scales, rotations, persist)
+        return image, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_alpha):
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
+        positions, scales, rotations, persist = ctx.saved_tensors
+        L = _lib.lib()
+        dev = positions.device
+        n = ctx.n
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_image = (torch.zeros(n_views, 3, height, width, **f32) if g_image is None
+                   else g_image.contiguous().float())
+        g_depth = None if g_depth is None else g_depth.contiguous().float()
+        g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
+        # one allocation: [grad2d 12 | positions 3 | scales 3 | rotations 4 | colors 3 | opacities 1] x n
+        buf = torch.empty(26 * n, **f32)
+        grad2d, g_pos, g_scl = buf[:12 * n], buf[12 * n:15 * n].view(n, 3), buf[15 * n:18 * n].view(n, 3)
+        g_rot, g_col, g_opa = buf[18 * n:22 * n].view(n, 4), buf[22 * n:25 * n].view(n, 3), buf[25 * n:]
+        cam = np.ascontiguousarray(cam_vecs, np.float32)
+        bg_host = np.asarray(bg, np.float32)
+        _call("frb_tile_render_bwd", L.frb_tile_render_bwd, n, n_views, _ptr(positions), _ptr(scales),
+              _ptr(rotations), cam.ctypes.data, width, height, bg_host.ctypes.data, ctx.cap, _ptr(persist),
+              _ptr(g_image), _ptr(g_depth), _ptr(g_alpha), _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot),
+              _ptr(g_col), _ptr(g_opa), _stream())
+        return g_pos, g_scl, g_rot, g_col, g_opa, None
+
+
 class _TileRenderFn(torch.autograd.Function):
     """Forward / backward of TileBasedRenderer for n_views views in one call."""
 
@@ -293,7 +356,14 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
     cam_vecs = np.stack([camera_vector(c, width, height) for c in cameras])
     cfg = (cam_vecs, B, int(width), int(height), tuple(float(x) for x in background), float(max_radius),
            float(t_eps), float(phase_amplitude))
+    n_total = B * N
+    fused = (FUSED_CALLS and _TIMER is None and t["phases"] is None and n_total > 0 and
+             worst_case_instances(n_total, B, int(width), int(height), float(max_radius)) * INSTANCE_BYTES
+             <= SYNC_FREE_BUDGET_BYTES)
     with torch.cuda.device(t["positions"].device):
+        if fused:
+            return _TileRenderFusedFn.apply(t["positions"], t["scales"], t["rotations"], t["colors"],
+                                            t["opacities"], cfg)
         return _TileRenderFn.apply(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"],
                                    t["phases"], cfg)
 

@@ -147,6 +147,29 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
                       const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
                       void* stream);
 
+/* ---- whole-pass entry points (capacity mode, no host synchronisation) ------------------ */
+/* One call enqueues projection, binning and compositing of TileBasedRenderer.forward (DR:489-686)
+ * for n_views views; buffers are carved from two arenas laid out by frb_tile_layout: `persist`
+ * (kept for the backward pass) and `scratch` (free after the call's work has run).  m_capacity bounds
+ * the number of tile instances (n * max tiles a rectangle can cover is always enough). */
+typedef struct FrbTileLayout {
+    size_t ranges, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
+    size_t records, depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,
+        sort_ws, scratch_bytes;
+} FrbTileLayout;
+int frb_tile_layout(int n, int n_views, int width, int height, int m_capacity, FrbTileLayout* layout);
+int frb_tile_render_fwd(int n, int n_views, const float* positions, const float* scales,
+                        const float* rotations, const float* colors, const float* opacities,
+                        const float* camera_host, float max_radius, int width, int height,
+                        const float* background_host, float t_eps, int m_capacity, void* persist,
+                        void* scratch, float* image, float* depth, float* alpha, void* stream);
+int frb_tile_render_bwd(int n, int n_views, const float* positions, const float* scales,
+                        const float* rotations, const float* camera_host, int width, int height,
+                        const float* background_host, int m_capacity, const void* persist,
+                        const float* g_image, const float* g_depth, const float* g_alpha, float* grad2d,
+                        float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
+                        float* g_opacities, void* stream);
+
 /* ---- complex wave field: WaveFieldRenderer DR:747-926 ------------------------------------ */
 /* wc: 8 floats per Gaussian [colour_c cos(phi_c) x3, colour_c sin(phi_c) x3, 0, 0];
  * phases: n x phase_stride floats, phase_stride = 1 (scalar phase) or 3 (per channel), radians.
