@@ -266,7 +266,7 @@ def run_train(args, rank, world, local, full):
     torch.manual_seed(0)
     model = PatchGaussianDecoder(384, 4).to(dev)
     res, k = (256, None) if full else (64, 256)
-    trainer = DecoderTrainer(model, res, stochastic_k=k, seed=rank)
+    trainer = DecoderTrainer(model, res, stochastic_k=k, seed=rank, cuda_graph=not args.no_cuda_graph)
     trainer.broadcast_parameters()
     host = [t.pin_memory() for t in train_batch(rank)]
     resident = [t.to(dev) for t in host]
@@ -307,6 +307,8 @@ def run_train(args, rank, world, local, full):
     ms = timed(step_resident, args.steps)
     barrier()
     launches = L.frb_launch_count() - l0
+    if trainer.cuda_graph:          # replayed kernels do not pass through the library's launch counter
+        launches = trainer.kernels_per_replay * args.steps
     ms_e2e = timed(step_e2e, args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -322,6 +324,7 @@ def run_train(args, rank, world, local, full):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": train_workload_name(full), "views_per_gpu": TRAIN_B,
                        "decoder_parameters": sum(p.numel() for p in model.parameters()),
+                       "cuda_graph": not args.no_cuda_graph,
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
                        "parallelism": f"dp{world}: view batch sharded by rank, one flat NCCL all-reduce of the "
                                       "decoder gradients per step"},
@@ -344,6 +347,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--t-eps", type=float, default=None)
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_full"])
+    ap.add_argument("--no-cuda-graph", action="store_true", help="train workloads: run the step eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -34,7 +34,9 @@ def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
     b2 = F.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1 + 1e-8, dim=-1, eps=1e-6)
     b3 = torch.cross(b1, b2, dim=-1)
     n3 = b3.norm(dim=-1, keepdim=True)
-    b3 = torch.where(n3 < 1e-6, torch.tensor([0.0, 0.0, 1.0], device=b3.device), b3)
+    ez = torch.zeros_like(b3)
+    ez[..., 2] = 1.0                                    # built on the device: CUDA-graph capturable
+    b3 = torch.where(n3 < 1e-6, ez, b3)
     b3 = F.normalize(b3, dim=-1, eps=1e-6)
     R = torch.stack([b1, b2, b3], dim=-1)
     R00, R01, R02 = R[..., 0, 0], R[..., 0, 1], R[..., 0, 2]
@@ -164,30 +166,43 @@ def shard_batch(n_items: int, rank: int, world: int) -> range:
 
 class DecoderTrainer:
     """One optimisation step of experiment 2: decoder -> [subsample] -> batched render -> losses ->
-    backward -> gradient all-reduce -> clip -> AdamW (train_epoch, train_gaussian_decoder.py:1031-1266)."""
+    backward -> gradient all-reduce -> clip -> AdamW (train_epoch, train_gaussian_decoder.py:1031-1266).
+
+    ``cuda_graph=True`` captures [decoder .. backward] and [clip + AdamW] as two CUDA graphs and replays
+    them (the renderer's forward is sync-free and allocation-static, so the whole step is capturable);
+    the gradient all-reduce runs between the two replays.  The step is launch-bound otherwise
+    (about 250 small kernels for 16 views of 256 Gaussians).
+    """
 
     def __init__(self, model: nn.Module, render_size: int, lr: float = 1e-4, stochastic_k: Optional[int] = None,
-                 seed: int = 0, weight_decay: float = 0.01):
+                 seed: int = 0, weight_decay: float = 0.01, cuda_graph: bool = False):
         self.model = model
         self.render_size = render_size
         self.renderer = TileBasedRenderer(render_size, render_size)
         self.camera = Camera(0.8 * render_size, 0.8 * render_size, render_size / 2, render_size / 2, render_size,
                              render_size)                       # train_gaussian_decoder.py:1910-1917
-        self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.cuda_graph = cuda_graph
+        self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay,
+                                           capturable=cuda_graph)
         self.stochastic_k = stochastic_k
         dev = next(model.parameters()).device
-        self.generator = torch.Generator(device=dev)
-        self.generator.manual_seed(seed)
+        self.generator = None
+        if not cuda_graph:                                      # graphs replay the default (graph-safe) generator
+            self.generator = torch.Generator(device=dev)
+            self.generator.manual_seed(seed)
+        elif dev.type == "cuda":
+            torch.cuda.manual_seed(seed)
+        self._graphs = None
+        self.kernels_per_replay = 0
 
     def broadcast_parameters(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             for p in self.model.parameters():
                 dist.broadcast(p.data, src=0)
 
-    def step(self, features: torch.Tensor, depth: torch.Tensor, images: torch.Tensor) -> torch.Tensor:
-        """features (B, 384, 37, 37), depth (B, 1, h, w), images (B, 3, h, w) on the device; returns the loss."""
+    # ---- the step, in the two halves that are captured separately --------------------------------
+    def _forward_backward(self, features, depth, images) -> torch.Tensor:
         R = self.render_size
-        self.optimizer.zero_grad(set_to_none=True)
         g = self.model(features, depth)
         g = subsample_by_opacity(g, self.stochastic_k, self.generator)
         rendered, rendered_depth, _ = self.renderer.render_batch(g["positions"], g["scales"], g["rotations"],
@@ -197,7 +212,50 @@ class DecoderTrainer:
         target_depth = F.interpolate(depth, size=(R, R), mode="bilinear", align_corners=False).squeeze(1)
         loss = reconstruction_losses(rendered, images, rendered_depth, target_depth)
         loss.backward()
-        allreduce_gradients(self.model.parameters())
+        return loss.detach()
+
+    def _update(self):
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
         self.optimizer.step()
-        return loss.detach()
+
+    def _capture(self, features, depth, images):
+        static = [torch.empty_like(t) for t in (features, depth, images)]
+        for s, t in zip(static, (features, depth, images)):
+            s.copy_(t)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                           # warm-up off the capture stream
+            for _ in range(3):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._forward_backward(*static)
+                self._update()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        from . import _lib
+        before = _lib.lib().frb_launch_count()
+        with torch.cuda.graph(g1):
+            loss = self._forward_backward(*static)
+        self.kernels_per_replay = int(_lib.lib().frb_launch_count() - before)   # renderer kernels in the graph
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._update()
+        self._graphs = (g1, g2, static, loss)
+
+    def step(self, features: torch.Tensor, depth: torch.Tensor, images: torch.Tensor) -> torch.Tensor:
+        """features (B, 384, 37, 37), depth (B, 1, h, w), images (B, 3, h, w) on the device; returns the loss."""
+        if self.cuda_graph:
+            if self._graphs is None:
+                self._capture(features, depth, images)
+            g1, g2, static, loss = self._graphs
+            for s, t in zip(static, (features, depth, images)):
+                s.copy_(t, non_blocking=True)
+            g1.replay()                                         # gradients are rewritten in place by the replay
+            allreduce_gradients(self.model.parameters())
+            g2.replay()
+            return loss
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self._forward_backward(features, depth, images)
+        allreduce_gradients(self.model.parameters())
+        self._update()
+        return loss
