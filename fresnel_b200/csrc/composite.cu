@@ -152,7 +152,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 // The per-Gaussian sums over pixels are formed WITHOUT warp shuffles or per-pixel atomics.  Each
 // warp owns 32 pixels (a 16x2 block) and handles 32 Gaussians at a time in two phases:
 //   phase 1 (lane = pixel): walk the 32 Gaussians back to front, carrying (T, S); per pair store
-//           (c, gated dL/dalpha) into a 32x32 shared-memory tile;
+//           (c, g * gated dL/dalpha) into a 32x32 shared-memory tile;
 //   phase 2 (lane = Gaussian): read the tile transposed, walk the 32 pixels and accumulate the ten
 //           gradient sums of that Gaussian in registers.
 // The eight warps' partial sums are added across warps through shared memory and leave the CTA as
@@ -279,7 +279,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             // Two candidates per iteration: everything that does not depend on the running (T, S) is
             // evaluated for both first (independent instruction streams hide the LDS / MUFU latency),
             // then the two short serial tails run back to back.
-            struct Pre { float a, inv_om, w; bool active, pass; };
+            struct Pre { float a, inv_om, w, gpass; bool active; };
             auto stage_a = [&](int j) {
                 Pre p;
                 const int jb = sb * 32 + j;
@@ -289,9 +289,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const float4 r0 = rec[3 * jb + 0];
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                const float araw = frb_ex2(power) * r1.y;
+                const float g = frb_ex2(power);
+                const float araw = g * r1.y;
                 p.a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
-                p.pass = (p.a == araw);                       // clamp gate: 0 <= g*o <= 0.99
+                p.gpass = (p.a == araw) ? g : 0.0f;           // g, or 0 behind the clamp gate 0 <= g*o <= 0.99
                 p.inv_om = frb_rcp(1.0f - p.a);
                 p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
                 return p;
@@ -305,7 +306,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                     S = fmaf(c, p.w, S);
                     T = Ti;
                     out.x = c;
-                    out.y = p.pass ? dalpha : 0.0f;
+                    out.y = p.gpass * dalpha;                 // g * gated dL/dalpha (= dL/dopacity part)
                 }
                 my_pair[j * PAIR_STRIDE + lane] = out;
             };
@@ -343,8 +344,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                         float4 gpix = pc[p];
                         float dx = ux + (float)(p & 15);
                         float dy = uy + (float)(p >> 4);
-                        float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                        float gda = (cd.y != 0.0f) ? frb_ex2(power) * cd.y : 0.0f;   // g * gated dL/dalpha
+                        const float gda = cd.y;                 // g * gated dL/dalpha, formed in phase 1
                         d_r = fmaf(cd.x, gpix.x, d_r);
                         d_g = fmaf(cd.x, gpix.y, d_g);
                         d_b = fmaf(cd.x, gpix.z, d_b);
