@@ -414,9 +414,12 @@ def main():
     h2d = sum(v.numel() * 4 for v in host.values()) + gi_h.numel() * 4 + gd_h.numel() * 4
     d2h = sum(v.numel() * 4 for v in host.values()) + 4 * RES * RES * 4
 
+    enqueue = {}
+
     def timed(fn, steps):
         """Per-step CUDA events on the launching stream; L2 flushed (256 MiB write) between steps."""
         evs = []
+        t0 = time.perf_counter()
         for _ in range(steps):
             flush.fill_(1.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -424,6 +427,7 @@ def main():
             fn()
             b.record()
             evs.append((a, b))
+        enqueue[fn.__name__] = (time.perf_counter() - t0) / steps * 1e3   # host time to enqueue one step
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
@@ -500,6 +504,9 @@ def main():
                        "parallelism": f"views sharded over {world} rank(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": tot_e2e_ms / args.steps},
+            "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms),
+                        "e2e_median": statistics.median(ms_e2e),
+                        "host_enqueue": enqueue.get("step_resident")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",

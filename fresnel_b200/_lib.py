@@ -41,6 +41,9 @@ _SIGNATURES = {
                                     P, P, P, P]),
     "frb_tile_render_bwd": (c_int, [c_int, c_int, P, P, P, P, c_int, c_int, P, c_int, P, P, P, P, P, P, P, P, P, P,
                                     P]),
+    "frb_tile_schedule": (c_int, [c_int, P, P, P]),
+    "frb_composite_fwd_sched": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
+    "frb_composite_bwd_sched": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),
     "frb_wave_prepare": (c_int, [c_int, P, P, c_int, P, P]),
     "frb_wave_gather": (c_int, [c_int, P, P, P, P]),
     "frb_wave_splat_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
@@ -60,7 +63,7 @@ _OPTIONAL = {}
 class TileLayout(ctypes.Structure):
     """FrbTileLayout of include/fresnel_b200.h."""
     _fields_ = [(name, c_size_t) for name in (
-        "ranges", "state_T", "state_n", "sorted_gids", "sorted_records", "persist_bytes", "records", "depth_bits",
+        "ranges", "tile_order", "state_T", "state_n", "sorted_gids", "sorted_records", "persist_bytes", "records", "depth_bits",
         "touched", "order", "offsets", "depth_ws", "scan_ws", "keys", "keys_tmp", "vals_tmp", "sort_ws",
         "scratch_bytes")]
 

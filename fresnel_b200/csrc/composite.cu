@@ -20,14 +20,14 @@
 namespace {
 
 __global__ void __launch_bounds__(CTA_THREADS)
-composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
-                     const float4* __restrict__ sorted_records, float3 bg, float t_eps, float* __restrict__ image,
+composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
+                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records, float3 bg, float t_eps, float* __restrict__ image,
                      float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
                      int* __restrict__ state_n) {
     __shared__ StageBuf stage[STAGES];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : blockIdx.x;   // heaviest tiles first
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
@@ -173,8 +173,9 @@ struct BwdSmem {
 };
 
 __global__ void __launch_bounds__(CTA_THREADS, 2)
-composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
-                     const float4* __restrict__ sorted_records, const uint32_t* __restrict__ sorted_gids,
+composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
+                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
+                     const uint32_t* __restrict__ sorted_gids,
                      float3 bg, const float* __restrict__ state_T,
                      const int* __restrict__ state_n, const float* __restrict__ g_image,
                      const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
@@ -182,7 +183,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : blockIdx.x;   // heaviest tiles first
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
@@ -388,7 +389,53 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     }
 }
 
+// Launch order of the tiles: descending list length (bucketed), so the long centre tiles start first
+// and the short ones fill the tail of the grid (longest-processing-time-first list scheduling).
+constexpr int SCHED_BUCKETS = 1024;
+__global__ void __launch_bounds__(1024) tile_schedule_kernel(int n_tiles, const int2* __restrict__ ranges,
+                                                             int* __restrict__ order) {
+    __shared__ int hist[SCHED_BUCKETS];
+    __shared__ int warp_tot[32];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [](int2 r) { return SCHED_BUCKETS - 1 - min((r.y - r.x) >> 3, SCHED_BUCKETS - 1); };
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) atomicAdd(&hist[bucket(ranges[t])], 1);
+    __syncthreads();
+    // exclusive scan of the 1024 buckets (bucket 0 = longest lists)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int v = hist[threadIdx.x], incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    hist[threadIdx.x] = warp_tot[warp] + incl - v;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) order[atomicAdd(&hist[bucket(ranges[t])], 1)] = t;
+}
+
 }  // namespace
+
+extern "C" int frb_tile_schedule(int n_tiles, const int32_t* ranges, int32_t* tile_order, void* stream) {
+    if (n_tiles < 0 || !ranges || !tile_order) return FRB_E_INVALID;
+    if (n_tiles == 0) return 0;
+    tile_schedule_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_tiles, (const int2*)ranges, tile_order);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
 
 // composite_phase.cu
 int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* ranges,
@@ -413,6 +460,16 @@ extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32
                                  float phase_amplitude, const float* background_host, float t_eps,
                                  float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
                                  float* ckpt, void* stream) {
+    return frb_composite_fwd_sched(n_views, width, height, nullptr, ranges, sorted_records, sorted_phases,
+                                   phase_amplitude, background_host, t_eps, image, depth, alpha, state_T, state_n,
+                                   ckpt, stream);
+}
+
+extern "C" int frb_composite_fwd_sched(int n_views, int width, int height, const int32_t* tile_order,
+                                 const int32_t* ranges, const float* sorted_records, const float* sorted_phases,
+                                 float phase_amplitude, const float* background_host, float t_eps,
+                                 float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
+                                 float* ckpt, void* stream) {
     int rc = check_image_args(n_views, width, height);
     if (rc) return rc;
     if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n) return FRB_E_INVALID;
@@ -424,8 +481,8 @@ extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     composite_fwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps, image, depth,
-        alpha, state_T, state_n);
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps,
+        image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -433,6 +490,18 @@ extern "C" int frb_composite_fwd(int n_views, int width, int height, const int32
 
 extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
                                  const float* sorted_records, const uint32_t* sorted_gids,
+                                 const float* sorted_phases, float phase_amplitude,
+                                 const float* background_host, const float* state_T,
+                                 const int32_t* state_n, const float* ckpt, const float* g_image,
+                                 const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
+                                 void* stream) {
+    return frb_composite_bwd_sched(n_views, width, height, nullptr, ranges, sorted_records, sorted_gids,
+                                   sorted_phases, phase_amplitude, background_host, state_T, state_n, ckpt, g_image,
+                                   g_depth, g_alpha, grad2d, g_phases, stream);
+}
+
+extern "C" int frb_composite_bwd_sched(int n_views, int width, int height, const int32_t* tile_order,
+                                 const int32_t* ranges, const float* sorted_records, const uint32_t* sorted_gids,
                                  const float* sorted_phases, float phase_amplitude,
                                  const float* background_host, const float* state_T,
                                  const int32_t* state_n, const float* ckpt, const float* g_image,
@@ -456,8 +525,8 @@ extern "C" int frb_composite_bwd(int n_views, int width, int height, const int32
         attr_set = true;
     }
     composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
-        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, bg,
-        state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
+        bg, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

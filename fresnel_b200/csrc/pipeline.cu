@@ -28,6 +28,7 @@ extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_
     const size_t m = (size_t)m_capacity;
     Carver p;
     L->ranges = p.take(8 * tiles);
+    L->tile_order = p.take(4 * tiles);
     L->state_T = p.take(4 * hw);
     L->state_n = p.take(4 * hw);
     L->sorted_gids = p.take(4 * m);
@@ -88,9 +89,11 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
     } else {
         FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
     }
-    return frb_composite_fwd(n_views, width, height, ranges, sorted_records, nullptr, 0.0f, background_host, t_eps,
-                             image, depth, alpha, (float*)(P + L.state_T), (int32_t*)(P + L.state_n), nullptr,
-                             stream);
+    int32_t* tile_order = (int32_t*)(P + L.tile_order);
+    if ((rc = frb_tile_schedule(tiles, ranges, tile_order, stream))) return rc;
+    return frb_composite_fwd_sched(n_views, width, height, tile_order, ranges, sorted_records, nullptr, 0.0f,
+                                   background_host, t_eps, image, depth, alpha, (float*)(P + L.state_T),
+                                   (int32_t*)(P + L.state_n), nullptr, stream);
 }
 
 // grad2d: scratch of n * FRB_GRAD_FLOATS floats (zeroed here).
@@ -106,7 +109,8 @@ extern "C" int frb_tile_render_bwd(int n, int n_views, const float* positions, c
     if (!persist || !grad2d) return FRB_E_INVALID;
     const char* P = (const char*)persist;
     FRB_CUDA_OK(cudaMemsetAsync(grad2d, 0, sizeof(float) * FRB_GRAD_FLOATS * (size_t)n, (cudaStream_t)stream));
-    if ((rc = frb_composite_bwd(n_views, width, height, (const int32_t*)(P + L.ranges),
+    if ((rc = frb_composite_bwd_sched(n_views, width, height, (const int32_t*)(P + L.tile_order),
+                                (const int32_t*)(P + L.ranges),
                                 (const float*)(P + L.sorted_records), (const uint32_t*)(P + L.sorted_gids), nullptr,
                                 0.0f, background_host, (const float*)(P + L.state_T),
                                 (const int32_t*)(P + L.state_n), nullptr, g_image, g_depth, g_alpha, grad2d, nullptr,

@@ -283,7 +283,10 @@ class _TileRenderFn(torch.autograd.Function):
         if phases is not None:
             n_tiles = bins.ranges.shape[0]
             ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m, n_tiles), 1), **f32)
-        _call("frb_composite_fwd", L.frb_composite_fwd, n_views, width, height, _ptr(bins.ranges), _ptr(bins.sorted_records),
+        tile_order = torch.empty(bins.ranges.shape[0], dtype=torch.int32, device=dev)
+        _call("frb_tile_schedule", L.frb_tile_schedule, bins.ranges.shape[0], _ptr(bins.ranges), _ptr(tile_order), st)
+        _call("frb_composite_fwd", L.frb_composite_fwd_sched, n_views, width, height, _ptr(tile_order),
+              _ptr(bins.ranges), _ptr(bins.sorted_records),
                                        _ptr(bins.sorted_phases), float(phase_amp), bg_host.ctypes.data,
                                        float(t_eps), _ptr(image), _ptr(depth), _ptr(alpha), _ptr(state_T),
                                        _ptr(state_n), _ptr(ckpt), st)
@@ -291,7 +294,7 @@ class _TileRenderFn(torch.autograd.Function):
         ctx.n = n
         ctx.has_phase = phases is not None
         ctx.save_for_backward(positions, scales, rotations, bins.ranges, bins.sorted_records, bins.sorted_gids,
-                              state_T, state_n,
+                              state_T, state_n, tile_order,
                               bins.sorted_phases if phases is not None else positions.new_empty(0),
                               ckpt if ckpt is not None else positions.new_empty(0))
         return image, depth, alpha
@@ -299,8 +302,8 @@ class _TileRenderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_image, g_depth, g_alpha):
         (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
-        (positions, scales, rotations, ranges, sorted_records, sorted_gids, state_T, state_n, sorted_phases,
-         ckpt) = ctx.saved_tensors
+        (positions, scales, rotations, ranges, sorted_records, sorted_gids, state_T, state_n, tile_order,
+         sorted_phases, ckpt) = ctx.saved_tensors
         L = _lib.lib()
         dev = positions.device
         st = _stream()
@@ -313,7 +316,8 @@ class _TileRenderFn(torch.autograd.Function):
         grad2d = torch.zeros(n, RECORD_FLOATS, **f32)
         g_phases = torch.zeros(n, **f32) if ctx.has_phase else None
         bg_host = np.asarray(bg, np.float32)
-        _call("frb_composite_bwd", L.frb_composite_bwd, n_views, width, height, _ptr(ranges), _ptr(sorted_records),
+        _call("frb_composite_bwd", L.frb_composite_bwd_sched, n_views, width, height, _ptr(tile_order),
+              _ptr(ranges), _ptr(sorted_records),
                                        _ptr(sorted_gids), _ptr(sorted_phases) if ctx.has_phase else None,
                                        float(phase_amp), bg_host.ctypes.data, _ptr(state_T), _ptr(state_n),
                                        _ptr(ckpt) if ctx.has_phase else None, _ptr(g_image), _ptr(g_depth),

@@ -137,6 +137,21 @@ int frb_composite_fwd(int n_views, int width, int height, const int32_t* ranges,
                       float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
                       float* ckpt, void* stream);
 
+/* Launch order: tile_order[k] = k-th tile to start, longest lists first (nullable = row-major order).
+ * The *_sched variants of the compositor take it as an extra argument. */
+int frb_tile_schedule(int n_tiles, const int32_t* ranges, int32_t* tile_order, void* stream);
+int frb_composite_fwd_sched(int n_views, int width, int height, const int32_t* tile_order,
+                            const int32_t* ranges, const float* sorted_records, const float* sorted_phases,
+                            float phase_amplitude, const float* background_host, float t_eps, float* image,
+                            float* depth, float* alpha, float* state_T, int32_t* state_n, float* ckpt,
+                            void* stream);
+int frb_composite_bwd_sched(int n_views, int width, int height, const int32_t* tile_order,
+                            const int32_t* ranges, const float* sorted_records, const uint32_t* sorted_gids,
+                            const float* sorted_phases, float phase_amplitude, const float* background_host,
+                            const float* state_T, const int32_t* state_n, const float* ckpt,
+                            const float* g_image, const float* g_depth, const float* g_alpha, float* grad2d,
+                            float* g_phases, void* stream);
+
 /* g_depth, g_alpha nullable (treated as zero).  grad2d (and g_phases) must be zeroed by the
  * caller; contributions are accumulated with atomics. */
 int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
@@ -153,7 +168,7 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
  * (kept for the backward pass) and `scratch` (free after the call's work has run).  m_capacity bounds
  * the number of tile instances (n * max tiles a rectangle can cover is always enough). */
 typedef struct FrbTileLayout {
-    size_t ranges, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
+    size_t ranges, tile_order, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
     size_t records, depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,
         sort_ws, scratch_bytes;
 } FrbTileLayout;
