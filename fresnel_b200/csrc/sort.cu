@@ -34,6 +34,7 @@ constexpr uint32_t FLAG_AGG = 1u << 30;      // tile count published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;   // inclusive prefix over tiles 0..this published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr int LOOK_WINDOW = 8;               // predecessors inspected per look-back round trip
 constexpr int SPIN_LIMIT = 1 << 24;          // a look-back that spins this long reports an error instead of hanging
 
 template <typename KeyT>
@@ -119,20 +120,27 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         long long i = base + r * 32 + lane;
         key[r] = (i < m) ? keys_in[i] : (KeyT)0;
     }
+    // the eight match.any operations are independent: issue them back to back, then update the counters
+    uint32_t peers[SORT_IPT];
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        long long i = base + r * 32 + lane;
+        uint32_t d = (i < m) ? digit_of(key[r], shift, mask) : RADIX;   // invalid lanes match each other only
+        peers[r] = __match_any_sync(0xffffffffu, d);
+    }
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
         long long i = base + r * 32 + lane;
         bool valid = i < m;
-        uint32_t d = valid ? digit_of(key[r], shift, mask) : RADIX;  // invalid lanes match each other only
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
+        uint32_t d = digit_of(key[r], shift, mask);
+        int leader = __ffs(peers[r]) - 1;
         uint32_t old = 0;
         if (valid && lane == leader) {
             old = cnt[warp][d];
-            cnt[warp][d] = old + __popc(peers);
+            cnt[warp][d] = old + __popc(peers[r]);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = old + __popc(peers & lt_mask);
+        rank[r] = old + __popc(peers[r] & lt_mask);
         __syncwarp();
     }
     __syncthreads();
@@ -152,18 +160,29 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         st_volatile_u32(my_status, run | FLAG_PREFIX);
     } else {
         st_volatile_u32(my_status, run | FLAG_AGG);
+        // Look back LOOK_WINDOW predecessors per round trip: the loads are independent, so a walk over k
+        // published counts costs k / LOOK_WINDOW L2 latencies instead of k.
         long long look = (long long)tile - 1;
         int spins = 0;
-        while (true) {
-            uint32_t v = ld_volatile_u32(status + (size_t)look * RADIX + d);
-            uint32_t f = v & FLAG_MASK;
-            if (f == 0) {
-                if (++spins > SPIN_LIMIT) { *error_flag = 1; break; }
-                continue;
+        bool done = false;
+        while (!done) {
+            uint32_t v[LOOK_WINDOW];
+#pragma unroll
+            for (int k = 0; k < LOOK_WINDOW; ++k)
+                v[k] = (look - k >= 0) ? ld_volatile_u32(status + (size_t)(look - k) * RADIX + d) : FLAG_PREFIX;
+#pragma unroll
+            for (int k = 0; k < LOOK_WINDOW; ++k) {
+                if (done) break;
+                const uint32_t f = v[k] & FLAG_MASK;
+                if (f == 0) {                      // not published yet: poll again from this tile
+                    look -= k;
+                    if (++spins > SPIN_LIMIT) { *error_flag = 1; done = true; }
+                    break;
+                }
+                excl += v[k] & VALUE_MASK;
+                if (f == FLAG_PREFIX) done = true;
+                else if (k == LOOK_WINDOW - 1) look -= LOOK_WINDOW;
             }
-            excl += v & VALUE_MASK;
-            if (f == FLAG_PREFIX) break;
-            --look;
         }
         st_volatile_u32(my_status, (excl + run) | FLAG_PREFIX);
     }
