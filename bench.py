@@ -276,9 +276,18 @@ def run_train(args, rank, world, local, full):
     def step_resident():
         trainer.step(*resident)
 
+    from fresnel_b200.host import BatchPrefetcher
+    prefetch = BatchPrefetcher(dev)
+    prefetch.submit(host)
+
     def step_e2e():
-        f, d, i = (t.to(dev, non_blocking=True) for t in host)
+        # double-buffered input staging: this step's batch was copied while the previous step computed, the
+        # next batch is copied (side stream) while this one computes; the fence puts that copy inside this
+        # step's timing bracket, so K timed steps contain K batch copies.
+        f, d, i = prefetch.take()
+        prefetch.submit(host)
         loss_host.copy_(trainer.step(f, d, i), non_blocking=True)
+        prefetch.fence()
 
     def timed(fn, steps):
         evs = []
@@ -397,22 +406,16 @@ def main():
                        resident["opacities"], cam, return_depth=True)
         torch.autograd.backward((img, dep), (gi, gd))
 
-    out_pinned = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
-    img_p, dep_p = torch.empty(3, RES, RES).pin_memory(), torch.empty(RES, RES).pin_memory()
+    from fresnel_b200.host import HostRenderSession
+    session = HostRenderSession(ren, N_GAUSS, dev)
 
     def step_e2e():
-        t = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host_pinned.items()}
-        g1, g2 = gi_p.to(dev, non_blocking=True), gd_p.to(dev, non_blocking=True)
-        img, dep = ren(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"], cam,
-                       return_depth=True)
-        torch.autograd.backward((img, dep), (g1, g2))
-        img_p.copy_(img.detach(), non_blocking=True)
-        dep_p.copy_(dep.detach(), non_blocking=True)
-        for k in GRAD_NAMES:
-            out_pinned[k].copy_(t[k].grad, non_blocking=True)
+        # the module called on pinned host buffers: H2D of the five parameter tensors and both upstream
+        # gradients, D2H of image, depth and the five gradients, all inside the step (copy streams overlap the
+        # kernels within the step; nothing is prefetched across steps)
+        session.step(host_pinned, cam, gi_p, gd_p)
 
-    h2d = sum(v.numel() * 4 for v in host.values()) + gi_h.numel() * 4 + gd_h.numel() * 4
-    d2h = sum(v.numel() * 4 for v in host.values()) + 4 * RES * RES * 4
+    h2d, d2h = session.h2d_bytes, session.d2h_bytes
 
     enqueue = {}
 
@@ -471,7 +474,8 @@ def main():
             from fresnel_b200.camera import camera_vector
             b = build_bins(resident["positions"].detach(), resident["scales"].detach(),
                            resident["rotations"].detach(), resident["colors"].detach(),
-                           resident["opacities"].detach(), camera_vector(cam, RES, RES)[None], 1, RES, RES, 64.0)
+                           resident["opacities"].detach(), camera_vector(cam, RES, RES)[None], 1, RES, RES, 64.0,
+                           sync=True)      # sync=True: b.m is the true instance count, not the capacity
             M = b.m
         peak, peak_src = peaks()
         HW, N = RES * RES, N_GAUSS
@@ -489,6 +493,10 @@ def main():
             "frb_project_bwd": 56 * N + 48 * N + 56 * N,
         }
         top = max(stages, key=stages.get)
+        traffic = None       # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(top)
         achieved = alg[top] / (stages[top] * 1e-3) / 1e9
         frame_bytes = 168 * N + 36 * HW + 96 * M
         value = world * args.steps / (tot_ms * 1e-3)
@@ -501,6 +509,8 @@ def main():
                                    "one view per rank",
                        "tile_instances": M, "t_eps": t_eps,
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
+                       "e2e": "HostRenderSession: pinned host buffers, copy streams overlap the kernels inside a step, "
+                              "no cross-step prefetch",
                        "parallelism": f"views sharded over {world} rank(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": tot_e2e_ms / args.steps},
@@ -510,7 +520,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[top], "kernel_ms": stages[top],
                          "frame_algorithmic_bytes": frame_bytes,
                          "frame_frac": frame_bytes / (tot_ms / args.steps * 1e-3) / 1e9 / peak,
