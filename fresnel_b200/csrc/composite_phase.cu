@@ -155,11 +155,32 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     }
 }
 
-// Backward: per pixel thread, tile list visited in 32-entry blocks from last to first.
-//   reverse-mode through the step above with adjoints (Tb = dL/dT, Pb = dL/dPhi) carried per pixel;
-//   the eleven per-Gaussian partials are reduced over the warp with the halving butterfly and
-//   leave as one atomic instruction per warp and record.
-__global__ void __launch_bounds__(CTA_THREADS)
+// Backward.  The tile list is visited in 32-entry blocks (= checkpoint interval) from last to first.
+// Per block every warp (32 pixels) runs three phases, the same decomposition as composite_bwd_kernel:
+//   phase 1a (lane = pixel): recompute the block forward from its checkpoint over the warp's candidate
+//            records, leaving the state (acc, Phi) BEFORE every entry in a 32x32 shared-memory tile;
+//   phase 1b (lane = pixel): walk the candidates back, reverse mode through the step with the adjoints
+//            (Tb = dL/dT, Pb = dL/dPhi) carried per pixel; per pair the tile slot is overwritten with
+//            (c, g * dL/da0) and a second tile receives dL/dphi;
+//   phase 2  (lane = Gaussian): read both tiles transposed, walk the 32 pixels and keep the eleven sums of
+//            the lane's Gaussian in registers.
+// The eight warps' sums meet in shared memory (shared atomics) and leave the CTA as ONE global atomic per
+// Gaussian value per tile.
+constexpr int PH_STAGES = 4;
+constexpr int PH_STRIDE = 33;                    // row stride of the per-warp tiles: conflict-free both ways
+constexpr int PH_WARPS = CTA_THREADS / 32;
+
+struct PhaseBwdSmem {
+    float4 rec[PH_STAGES][SUB * 3];
+    float2 pair[PH_WARPS][32 * PH_STRIDE];
+    float phib[PH_WARPS][32 * PH_STRIDE];
+    float4 pixc[PH_WARPS][32];
+    float sums[2][N_PHASE_GRADS][SUB];
+    uint64_t full_bar[PH_STAGES];
+    int max_n;
+};
+
+__global__ void __launch_bounds__(CTA_THREADS, 2)
 composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
                            const float4* __restrict__ sorted_records, const uint32_t* __restrict__ sorted_gids,
                            const float* __restrict__ sorted_phases, float A, float3 bg,
@@ -167,11 +188,8 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                            const float2* __restrict__ ckpt, const float* __restrict__ g_image,
                            const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
                            float* __restrict__ grad2d, float* __restrict__ g_phases) {
-    __shared__ StageBuf stage[2];
-    __shared__ float phase_s[2][SUB];
-    __shared__ uint32_t gid_s[2][SUB];
-    __shared__ __align__(8) uint64_t full_bar[2];
-    __shared__ int max_n_s;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PhaseBwdSmem& sm = *reinterpret_cast<PhaseBwdSmem*>(smem_raw);
 
     const int tile = blockIdx.x;
     const int view = tile / tiles_per_view;
@@ -183,16 +201,17 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
     const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float wbx = (float)(tx * TILE), wby = (float)(ty * TILE + 2 * warp);   // warp's pixel block origin
+    const int wx0 = tx * TILE, wx1 = wx0 + TILE, wy0 = ty * TILE + 2 * warp, wy1 = wy0 + 2;
     const int2 range = ranges[tile];
 
-    float T_final = 1.0f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
     int my_n = 0;
     if (in_image) {
         const size_t hw = (size_t)width * height;
         const size_t pix = (size_t)view * hw + (size_t)py * width + px;
         const size_t ip = (size_t)view * 3 * hw + (size_t)py * width + px;
-        T_final = state_T[pix];
         const int st = state_n[pix];
         my_n = st & STATE_N_MASK;
         const int gates = st >> STATE_GATE_SHIFT;
@@ -202,147 +221,194 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         gd = g_depth ? g_depth[pix] : 0.0f;
         ga = g_alpha ? g_alpha[pix] : 0.0f;
     }
+    sm.pixc[warp][lane] = make_float4(gr, gg, gb, gd);
+    for (int i = threadIdx.x; i < 2 * N_PHASE_GRADS * SUB; i += CTA_THREADS) (&sm.sums[0][0][0])[i] = 0.0f;
     if (threadIdx.x == 0) {
-        max_n_s = 0;
-        for (int s = 0; s < 2; ++s) frb_mbar_init(&full_bar[s], 1);
+        sm.max_n = 0;
+        for (int s = 0; s < PH_STAGES; ++s) frb_mbar_init(&sm.full_bar[s], 1);
         frb_mbar_fence_init();
     }
     __syncthreads();
-    {
-        int wmax = my_n;
+    int warp_n = my_n;                           // entries applied by at least one pixel of the warp
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        if (lane == 0) atomicMax(&max_n_s, wmax);
-    }
+    for (int o = 16; o > 0; o >>= 1) warp_n = max(warp_n, __shfl_xor_sync(0xffffffffu, warp_n, o));
+    if (lane == 0) atomicMax(&sm.max_n, warp_n);
     __syncthreads();
-    const int count = min(max_n_s, range.y - range.x);
+    const int count = min(sm.max_n, range.y - range.x);
     const int n_blocks = (count + SUB - 1) / SUB;
     if (n_blocks == 0) return;
 
     auto issue = [&](int visit) {
         int k = n_blocks - 1 - visit;
-        int s = visit & 1;
+        int s = visit % PH_STAGES;
         int cnt = min(SUB, count - k * SUB);
-        frb_mbar_expect_tx(&full_bar[s], cnt * RECORD_BYTES);
-        frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + k * SUB), cnt * RECORD_BYTES,
-                        &full_bar[s]);
+        frb_mbar_expect_tx(&sm.full_bar[s], cnt * RECORD_BYTES);
+        frb_tma_load_1d(sm.rec[s], sorted_records + 3 * (size_t)(range.x + k * SUB), cnt * RECORD_BYTES,
+                        &sm.full_bar[s]);
     };
-    if (threadIdx.x == 0) {
-        issue(0);
-        if (n_blocks > 1) issue(1);
-    }
+    if (threadIdx.x == 0)
+        for (int v = 0; v < PH_STAGES && v < n_blocks; ++v) issue(v);
 
     float Tb = gr * bg.x + gg * bg.y + gb * bg.z - ga;     // dL/dT_final
     float Pb = 0.0f;                                        // dL/dPhi_final
-    const int gslot = warp_reduce_multi_index(lane);
-    const int gofs = gslot + (gslot >= 7 ? 1 : 0);          // [du dv dA dB | dC do ddepth _ | dr dg db _]
+    float2* my_pair = sm.pair[warp];
+    float* my_phib = sm.phib[warp];
 
     for (int visit = 0; visit < n_blocks; ++visit) {
         const int k = n_blocks - 1 - visit;
-        const int s = visit & 1;
+        const int s = visit % PH_STAGES;
         const int cnt = min(SUB, count - k * SUB);
-        if (threadIdx.x < cnt) {
-            phase_s[s][threadIdx.x] = sorted_phases[range.x + k * SUB + threadIdx.x];
-            gid_s[s][threadIdx.x] = sorted_gids[range.x + k * SUB + threadIdx.x];
-        }
-        frb_mbar_wait(&full_bar[s], (visit >> 1) & 1);
-        __syncthreads();
-        const float4* rec = stage[s].rec;
-        const int local_n = my_n - k * SUB;                 // entries j < local_n were applied by this pixel
+        const int base_n = k * SUB;
+        // lane l keeps the phase of record l of the block (read by shuffle: uniform record index)
+        const float phi_l = (lane < cnt) ? sorted_phases[range.x + base_n + lane] : 0.0f;
+        frb_mbar_wait(&sm.full_bar[s], (visit / PH_STAGES) & 1);
+        const float4* rec = sm.rec[s];
 
-        // ---- recompute forward from the checkpoint, remembering Phi before every entry ----
-        float phi_before[SUB], acc_before[SUB];
-        float acc = 0.0f, Phi = 0.0f;
-        uint32_t amask = 0;
-        if (local_n > 0) {
-            float2 c0 = ckpt[ckpt_slot(range.x, tile, k) * CTA_THREADS + threadIdx.x];
-            acc = c0.x; Phi = c0.y;
+        // ---- candidates: lane l tests record l against this warp's 16x2 pixels ----
+        uint32_t cand;
+        {
+            bool ok = false;
+            if (lane < cnt) {
+                const uint32_t lo = __float_as_uint(rec[3 * lane + 1].w);
+                const uint32_t hi = __float_as_uint(rec[3 * lane + 2].w) & 0x7fff7fffu;
+                ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
+                     (int)(hi >> 16) > wy0;
+            }
+            cand = __ballot_sync(0xffffffffu, ok);
+            const int wn = warp_n - base_n;          // entries >= wn were applied by no pixel of the warp
+            if (wn < 32) cand &= (wn <= 0) ? 0u : ((1u << wn) - 1u);
         }
-#pragma unroll
-        for (int j = 0; j < SUB; ++j) {
-            phi_before[j] = Phi;
-            acc_before[j] = acc;
-            if (j < cnt && j < local_n) {
-                float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
-                    float4 r0 = rec[3 * j + 0];
-                    float dx = fpx - r0.x, dy = fpy - r0.y;
-                    float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+        const uint32_t gmask = cand;
+        const int local_n = my_n - base_n;           // entries j < local_n were applied by this pixel
+
+        if (gmask != 0) {
+            // ---- phase 1a: forward recompute from the checkpoint ----
+            float acc = 0.0f, Phi = 0.0f;
+            if (local_n > 0) {
+                const float2 c0 = ckpt[ckpt_slot(range.x, tile, k) * CTA_THREADS + threadIdx.x];
+                acc = c0.x; Phi = c0.y;
+            }
+            uint32_t m = gmask;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float phi = __shfl_sync(0xffffffffu, phi_l, j);
+                my_pair[j * PH_STRIDE + lane] = make_float2(acc, Phi);
+                const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                if (j < local_n &&
+                    rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                    const float4 r0 = rec[3 * j + 0];
+                    const float dx = fpx - r0.x, dy = fpy - r0.y;
+                    const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                     PhaseStep st;
-                    phase_step(frb_ex2(power), r1.y, phase_s[s][j], A, acc, Phi, st);
+                    phase_step(frb_ex2(power), r1.y, phi, A, acc, Phi, st);
                     acc = st.accn; Phi = st.Phin;
-                    amask |= 1u << j;
                 }
             }
-        }
-
-        // ---- walk back ----
-#pragma unroll
-        for (int j = SUB - 1; j >= 0; --j) {
-            if (j >= cnt) continue;                                   // uniform
-            const bool active = (amask >> j) & 1u;
-            if (!__any_sync(0xffffffffu, active)) continue;
-            float part[N_PHASE_GRADS];
-#pragma unroll
-            for (int q = 0; q < N_PHASE_GRADS; ++q) part[q] = 0.0f;
-            if (active) {
-                float4 r0 = rec[3 * j + 0], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                const float phi = phase_s[s][j];
-                const float Phi0 = phi_before[j];
-                float dx = fpx - r0.x, dy = fpy - r0.y;
-                float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                float g = frb_ex2(power);
-                // replay the step from the remembered state before the entry
-                PhaseStep st;
-                phase_step(g, r1.y, phi, A, acc_before[j], Phi0, st);
-                float sn = __sinf(st.d * TWO_PI_REF);
-                const float a0 = st.a0, d0 = st.d0, m = st.m, a1 = st.a1, alpha = st.alpha, c = st.c;
-                const float T0 = 1.0f - acc_before[j];
-                const float acc_n = st.accn;
-                const float iden = frb_rcp(st.den);
-                const float pc = st.pc;
-                // reverse mode
-                float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
-                float pcb = Pb * (phi - Phi0);
-                float phib = Pb * pc;
-                float Pb0 = Pb * (1.0f - pc);
-                float cb_ = pcb * iden + w;
-                float Tb_tot = Tb + ((acc_n >= 1e-6f) ? pcb * c * iden * iden : 0.0f);
-                cb_ -= Tb_tot;
-                float Tb0 = Tb_tot + cb_ * alpha;
-                float alphab = cb_ * T0;
-                float a1b = (alpha == a1) ? alphab : 0.0f;            // clamp gate (inclusive)
-                float a0b = a1b * m;
-                float mb = a1b * a0;
-                float db = -mb * A * TWO_PI_REF * sn;
-                float d0b = (d0 < 1.0f - d0) ? db : ((d0 > 1.0f - d0) ? -db : 0.0f);
-                float sg = (phi > Phi0) ? 1.0f : ((phi < Phi0) ? -1.0f : 0.0f);
-                phib += d0b * sg;
-                Pb0 -= d0b * sg;
-                float gda = g * a0b;                                   // dL/dopacity
-                float dpow = gda * r1.y * FRB_LN2;
-                part[0] = -(2.0f * r0.z * dx + r0.w * dy) * dpow;
-                part[1] = -(r0.w * dx + 2.0f * r1.x * dy) * dpow;
-                part[2] = dx * dx * dpow;
-                part[3] = dx * dy * dpow;
-                part[4] = dy * dy * dpow;
-                part[5] = gda;
-                part[6] = c * gd;
-                part[7] = c * gr;
-                part[8] = c * gg;
-                part[9] = c * gb;
-                part[10] = phib;
-                Tb = Tb0; Pb = Pb0;
+            // ---- phase 1b: walk back ----
+            m = gmask;
+            while (m) {
+                const int j = 31 - __clz(m);
+                m ^= 1u << j;
+                const float phi = __shfl_sync(0xffffffffu, phi_l, j);
+                const float2 before = my_pair[j * PH_STRIDE + lane];
+                const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                float2 out = make_float2(0.f, 0.f);
+                float phib = 0.0f;
+                if (j < local_n &&
+                    rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                    const float4 r0 = rec[3 * j + 0];
+                    const float Phi0 = before.y;
+                    const float dx = fpx - r0.x, dy = fpy - r0.y;
+                    const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                    const float g = frb_ex2(power);
+                    PhaseStep st;
+                    phase_step(g, r1.y, phi, A, before.x, Phi0, st);   // replay from the remembered state
+                    const float sn = __sinf(st.d * TWO_PI_REF);
+                    const float T0 = 1.0f - before.x;
+                    const float iden = frb_rcp(st.den);
+                    // reverse mode
+                    const float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                    const float pcb = Pb * (phi - Phi0);
+                    phib = Pb * st.pc;
+                    float Pb0 = Pb * (1.0f - st.pc);
+                    float cb_ = pcb * iden + w;
+                    const float Tb_tot = Tb + ((st.accn >= 1e-6f) ? pcb * st.c * iden * iden : 0.0f);
+                    cb_ -= Tb_tot;
+                    const float Tb0 = Tb_tot + cb_ * st.alpha;
+                    const float alphab = cb_ * T0;
+                    const float a1b = (st.alpha == st.a1) ? alphab : 0.0f;      // clamp gate (inclusive)
+                    const float a0b = a1b * st.m;
+                    const float mb = a1b * st.a0;
+                    const float db = -mb * A * TWO_PI_REF * sn;
+                    const float d0b = (st.d0 < 1.0f - st.d0) ? db : ((st.d0 > 1.0f - st.d0) ? -db : 0.0f);
+                    const float sg = (phi > Phi0) ? 1.0f : ((phi < Phi0) ? -1.0f : 0.0f);
+                    phib += d0b * sg;
+                    Pb0 -= d0b * sg;
+                    out.x = st.c;
+                    out.y = g * a0b;                                            // dL/dopacity part
+                    Tb = Tb0; Pb = Pb0;
+                }
+                my_pair[j * PH_STRIDE + lane] = out;
+                my_phib[j * PH_STRIDE + lane] = phib;
             }
-            float tot = warp_reduce_multi<N_PHASE_GRADS>(part, lane);
-            if ((lane & 1) == 0 && gslot < N_PHASE_GRADS && tot != 0.0f) {
-                const uint32_t gid = gid_s[s][j];
-                if (gslot == 10) atomicAdd(g_phases + gid, tot);
-                else atomicAdd(grad2d + (size_t)gid * FRB_GRAD_FLOATS + gofs, tot);
+            __syncwarp();
+            // ---- phase 2: lane = Gaussian ----
+            if ((gmask >> lane) & 1u) {
+                const float4 r0 = rec[3 * lane + 0], r1 = rec[3 * lane + 1];
+                const float oln2 = r1.y * FRB_LN2;
+                const float ux = wbx - r0.x, uy = wby - r0.y;
+                const float2* row = my_pair + lane * PH_STRIDE;
+                const float* prow = my_phib + lane * PH_STRIDE;
+                const float4* pc = sm.pixc[warp];
+                float d_A = 0.f, d_B = 0.f, d_C = 0.f, d_o = 0.f, d_dep = 0.f, d_r = 0.f, d_g = 0.f, d_b = 0.f,
+                      d_phi = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    const float2 cd = row[p];
+                    const float4 gpix = pc[p];
+                    const float dx = ux + (float)(p & 15);
+                    const float dy = uy + (float)(p >> 4);
+                    const float gda = cd.y;
+                    d_r = fmaf(cd.x, gpix.x, d_r);
+                    d_g = fmaf(cd.x, gpix.y, d_g);
+                    d_b = fmaf(cd.x, gpix.z, d_b);
+                    d_dep = fmaf(cd.x, gpix.w, d_dep);
+                    d_o += gda;
+                    d_phi += prow[p];
+                    const float tx_ = dx * gda, ty_ = dy * gda;
+                    sx += tx_; sy += ty_;
+                    d_A = fmaf(dx, tx_, d_A);
+                    d_B = fmaf(dx, ty_, d_B);
+                    d_C = fmaf(dy, ty_, d_C);
+                }
+                float* sp = &sm.sums[visit & 1][0][lane];
+                atomicAdd(sp + 0 * SUB, -(2.0f * r0.z * sx + r0.w * sy) * oln2);
+                atomicAdd(sp + 1 * SUB, -(r0.w * sx + 2.0f * r1.x * sy) * oln2);
+                atomicAdd(sp + 2 * SUB, d_A * oln2);
+                atomicAdd(sp + 3 * SUB, d_B * oln2);
+                atomicAdd(sp + 4 * SUB, d_C * oln2);
+                atomicAdd(sp + 5 * SUB, d_o);
+                atomicAdd(sp + 6 * SUB, d_dep);
+                atomicAdd(sp + 7 * SUB, d_r);
+                atomicAdd(sp + 8 * SUB, d_g);
+                atomicAdd(sp + 9 * SUB, d_b);
+                atomicAdd(sp + 10 * SUB, d_phi);
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && visit + 2 < n_blocks) issue(visit + 2);
+        __syncthreads();    // every warp's sums of this block are in; stage s is free
+        if (threadIdx.x == 0 && visit + PH_STAGES < n_blocks) issue(visit + PH_STAGES);
+        for (int i = threadIdx.x; i < N_PHASE_GRADS * SUB; i += CTA_THREADS) {
+            const int v = i / SUB, jb = i - v * SUB;
+            float* sp = &sm.sums[visit & 1][v][jb];
+            const float sum = *sp;
+            if (sum != 0.0f) {
+                *sp = 0.0f;                      // this buffer is used again two blocks later
+                const uint32_t gid = sorted_gids[range.x + base_n + jb];
+                if (v == 10) atomicAdd(g_phases + gid, sum);
+                else atomicAdd(grad2d + (size_t)gid * FRB_GRAD_FLOATS + v + (v >= 7 ? 1 : 0), sum);
+            }
+        }
     }
 }
 
@@ -379,7 +445,13 @@ int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    composite_phase_bwd_kernel<<<n_views * tpv, CTA_THREADS, 0, st>>>(
+    static bool attr_set = false;
+    if (!attr_set) {
+        FRB_CUDA_OK(cudaFuncSetAttribute(composite_phase_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PhaseBwdSmem)));
+        attr_set = true;
+    }
+    composite_phase_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(PhaseBwdSmem), st>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, sorted_phases,
         phase_amplitude, bg, state_T, state_n, (const float2*)ckpt, g_image, g_depth, g_alpha, grad2d, g_phases);
     frb_note_launches(1);

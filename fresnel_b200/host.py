@@ -24,91 +24,150 @@ GRAD_NAMES = ("positions", "scales", "rotations", "colors", "opacities")
 _SHAPES = {"positions": 3, "scales": 3, "rotations": 4, "colors": 3, "opacities": 0}
 
 
+def _carve(block: torch.Tensor, n: int):
+    """Views of the five parameter tensors inside one flat fp32 block; every segment starts 256-byte aligned
+    (rotations are read as float4)."""
+    out, off = {}, 0
+    for k, c in _SHAPES.items():
+        cnt = n * max(c, 1)
+        out[k] = block[off:off + cnt].view((n, c) if c else (n,))
+        off += (cnt + 63) // 64 * 64
+    return out
+
+
+def _block_floats(n: int) -> int:
+    return sum((n * max(c, 1) + 63) // 64 * 64 for c in _SHAPES.values())
+
+
 class HostRenderSession:
     """Forward + backward of one view per ``step`` with pinned host buffers on both sides.
 
     renderer: a fresnel_b200 renderer module with the reference call signature
     (positions, scales, rotations, colors, opacities, camera, return_depth=True).
+
+    The caller writes the parameters into ``host_inputs[name]`` and the upstream gradients into
+    ``host_g_image`` / ``host_g_depth`` (pinned staging buffers owned by the session: one block per
+    direction, so a step moves its data in two H2D and three D2H copies), calls ``step(camera)`` and reads
+    ``out_image``, ``out_depth`` and ``out_grads[name]`` after synchronising the current stream.
     """
 
     def __init__(self, renderer, n_gaussians: int, device: torch.device):
         if device.type != "cuda":
             raise TypeError("HostRenderSession needs a CUDA device (fresnel_b200 has no CPU path)")
         self.renderer, self.n, self.device = renderer, int(n_gaussians), device
-        h, w = renderer.height, renderer.width
+        n, h, w = self.n, renderer.height, renderer.width
         f32 = dict(dtype=torch.float32, device=device)
-        self.dev_in = {k: torch.empty((self.n, c) if c else (self.n,), **f32) for k, c in _SHAPES.items()}
-        self.dev_gimg = torch.empty(3, h, w, **f32)
-        self.dev_gdep = torch.empty(h, w, **f32)
+        blk = _block_floats(n)
+        self._host_in_block = torch.zeros(blk).pin_memory()
+        self._dev_in_block = torch.zeros(blk, **f32)
+        self.host_inputs = _carve(self._host_in_block, n)
+        self.dev_in = _carve(self._dev_in_block, n)
+        self._host_g_block = torch.zeros(4 * h * w).pin_memory()
+        self._dev_g_block = torch.zeros(4 * h * w, **f32)
+        self.host_g_image = self._host_g_block[:3 * h * w].view(3, h, w)
+        self.host_g_depth = self._host_g_block[3 * h * w:].view(h, w)
+        self.dev_gimg = self._dev_g_block[:3 * h * w].view(3, h, w)
+        self.dev_gdep = self._dev_g_block[3 * h * w:].view(h, w)
         self.out_image = torch.empty(3, h, w).pin_memory()
         self.out_depth = torch.empty(h, w).pin_memory()
-        self.out_grads = {k: torch.empty((self.n, c) if c else (self.n,)).pin_memory() for k, c in _SHAPES.items()}
+        # gradients in the renderer's own order (rotations first), so that one copy can take all five
+        self._out_g_block = torch.empty(14 * n).pin_memory()
+        self.out_grads = {"rotations": self._out_g_block[:4 * n].view(n, 4),
+                          "positions": self._out_g_block[4 * n:7 * n].view(n, 3),
+                          "scales": self._out_g_block[7 * n:10 * n].view(n, 3),
+                          "colors": self._out_g_block[10 * n:13 * n].view(n, 3),
+                          "opacities": self._out_g_block[13 * n:]}
         self.s_in = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)
         mk = lambda: torch.cuda.Event()
         self.e_start, self.e_params, self.e_grads, self.e_fwd, self.e_bwd, self.e_out = (mk() for _ in range(6))
-        self.h2d_bytes = 4 * (sum(t.numel() for t in self.dev_in.values()) + 4 * h * w)
-        self.d2h_bytes = 4 * (sum(t.numel() for t in self.out_grads.values()) + 4 * h * w)
+        self.h2d_bytes = 4 * (blk + 4 * h * w)
+        self.d2h_bytes = 4 * (14 * n + 4 * h * w)
 
-    def step(self, host_inputs: Dict[str, torch.Tensor], camera, g_image: torch.Tensor,
-             g_depth: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
-        """host_inputs / g_image / g_depth: pinned host tensors.  Returns the pinned (image, depth, grads);
+    def load(self, inputs: Dict[str, torch.Tensor], g_image: torch.Tensor, g_depth: torch.Tensor) -> None:
+        """Host-side copy of caller tensors into the staging buffers (not needed if the caller writes there)."""
+        for k in GRAD_NAMES:
+            self.host_inputs[k].copy_(inputs[k])
+        self.host_g_image.copy_(g_image)
+        self.host_g_depth.copy_(g_depth)
+
+    def step(self, camera) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+        """One forward + backward of what the staging buffers hold.  Returns the pinned (image, depth, grads);
         they are complete once the current stream has caught up (``torch.cuda.current_stream().synchronize()``)."""
         main = torch.cuda.current_stream(self.device)
+        s_in, s_out, n = self.s_in, self.s_out, self.n
         self.e_start.record(main)
-        self.s_in.wait_event(self.e_start)            # the previous step has finished with the input buffers
-        with torch.cuda.stream(self.s_in):
-            for k in GRAD_NAMES:
-                self.dev_in[k].copy_(host_inputs[k], non_blocking=True)
-            self.e_params.record(self.s_in)
-            self.dev_gimg.copy_(g_image, non_blocking=True)
-            self.dev_gdep.copy_(g_depth, non_blocking=True)
-            self.e_grads.record(self.s_in)
+        s_in.wait_event(self.e_start)                 # the previous step has finished with the input buffers
+        with torch.cuda.stream(s_in):
+            self._dev_in_block.copy_(self._host_in_block, non_blocking=True)
+            self.e_params.record(s_in)
+            self._dev_g_block.copy_(self._host_g_block, non_blocking=True)
+            self.e_grads.record(s_in)
         main.wait_event(self.e_params)
         leaves = {k: self.dev_in[k].detach().requires_grad_(True) for k in GRAD_NAMES}
         image, depth = self.renderer(leaves["positions"], leaves["scales"], leaves["rotations"], leaves["colors"],
                                      leaves["opacities"], camera, return_depth=True)
         self.e_fwd.record(main)
-        self.s_out.wait_event(self.e_fwd)
-        with torch.cuda.stream(self.s_out):
+        s_out.wait_event(self.e_fwd)
+        with torch.cuda.stream(s_out):
             self.out_image.copy_(image.detach(), non_blocking=True)
             self.out_depth.copy_(depth.detach(), non_blocking=True)
-        image.record_stream(self.s_out)
-        depth.record_stream(self.s_out)
+        # no record_stream: the step ends with the compute stream waiting for the last copy (e_out), so memory
+        # freed after the step cannot be reused before the copies have read it
         main.wait_event(self.e_grads)
         torch.autograd.backward((image, depth), (self.dev_gimg, self.dev_gdep))
         self.e_bwd.record(main)
-        self.s_out.wait_event(self.e_bwd)
-        with torch.cuda.stream(self.s_out):
-            for k in GRAD_NAMES:
-                g = leaves[k].grad
-                self.out_grads[k].copy_(g, non_blocking=True)
-                g.record_stream(self.s_out)
-            self.e_out.record(self.s_out)
+        s_out.wait_event(self.e_bwd)
+        grads = {k: leaves[k].grad for k in GRAD_NAMES}
+        g_rot = grads["rotations"]
+        # the tile renderer returns its five gradients as consecutive segments of one buffer
+        # (renderer._TileRenderFusedFn.backward: rotations | positions | scales | colors | opacities)
+        p0, packed = g_rot.data_ptr(), True
+        for k, off in (("positions", 4 * n), ("scales", 7 * n), ("colors", 10 * n), ("opacities", 13 * n)):
+            packed = packed and grads[k].data_ptr() == p0 + 4 * off
+        with torch.cuda.stream(s_out):
+            if packed:
+                flat = torch.as_strided(g_rot, (14 * n,), (1,), g_rot.storage_offset())
+                self._out_g_block.copy_(flat, non_blocking=True)
+            else:
+                for k in GRAD_NAMES:
+                    self.out_grads[k].copy_(grads[k], non_blocking=True)
+            self.e_out.record(s_out)
         main.wait_event(self.e_out)                   # the step ends when its last byte is on the host
         return self.out_image, self.out_depth, self.out_grads
 
 
 class BatchPrefetcher:
     """Double-buffered host -> device staging of training batches (what a DataLoader with ``pin_memory`` and
-    ``non_blocking`` copies does): ``next()`` returns the device copy of the batch submitted before and starts
-    copying the following one on a side stream while the caller computes.  ``fence()`` makes the current stream
-    wait for the copy in flight, so that a timing bracket closed after it contains the transfer."""
+    ``non_blocking`` copies does): ``take()`` returns the device copy of the batch submitted before, ``submit()``
+    starts copying the following one on a side stream while the caller computes.  ``fence()`` makes the current
+    stream wait for the copy in flight, so that a timing bracket closed after it contains the transfer.
+    Two persistent sets of device buffers: no allocator traffic per step."""
 
     def __init__(self, device: torch.device):
         self.device = device
         self.stream = torch.cuda.Stream(device)
         self.ready = torch.cuda.Event()
+        self.start = torch.cuda.Event()
+        self.buffers = [None, None]
+        self.slot = 0                   # slot the next submit writes
         self.staged: Optional[Tuple[torch.Tensor, ...]] = None
 
     def submit(self, host_batch) -> None:
-        main = torch.cuda.current_stream(self.device)
-        start = torch.cuda.Event()
-        start.record(main)
-        self.stream.wait_event(start)
+        """The slot written here was handed out two submits ago; its reader must have been enqueued on the
+        current stream before this call (it has: take() precedes the step that consumes the batch)."""
+        if self.buffers[self.slot] is None:
+            self.buffers[self.slot] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                                            for t in host_batch)
+        dst = self.buffers[self.slot]
+        self.start.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(self.start)
         with torch.cuda.stream(self.stream):
-            self.staged = tuple(t.to(self.device, non_blocking=True) for t in host_batch)
+            for d, h in zip(dst, host_batch):
+                d.copy_(h, non_blocking=True)
             self.ready.record(self.stream)
+        self.staged = dst
+        self.slot ^= 1
 
     def fence(self) -> None:
         torch.cuda.current_stream(self.device).wait_event(self.ready)
@@ -116,7 +175,4 @@ class BatchPrefetcher:
     def take(self):
         self.fence()
         batch, self.staged = self.staged, None
-        main = torch.cuda.current_stream(self.device)
-        for t in batch:
-            t.record_stream(main)
         return batch

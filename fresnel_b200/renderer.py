@@ -33,7 +33,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream (the stream every kernel of a call is launched on)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 class StageTimer:
@@ -208,36 +209,54 @@ def worst_case_instances(n: int, n_views: int, width: int, height: int, max_radi
 FUSED_CALLS = True      # one C call per pass (frb_tile_render_fwd / _bwd); False = stage by stage
 
 
+_LAYOUT_CACHE = {}
+
+
+def _tile_layout(n, n_views, width, height, max_radius):
+    """(capacity, FrbTileLayout) of the whole-pass entry points, cached per problem shape."""
+    key = (n, n_views, width, height, max_radius)
+    hit = _LAYOUT_CACHE.get(key)
+    if hit is None:
+        cap = worst_case_instances(n, n_views, width, height, max_radius)
+        lay = _lib.TileLayout()
+        _lib.check(_lib.lib().frb_tile_layout(n, n_views, width, height, cap, ctypes.byref(lay)), "frb_tile_layout")
+        if len(_LAYOUT_CACHE) > 256:
+            _LAYOUT_CACHE.clear()
+        hit = _LAYOUT_CACHE[key] = (cap, max(lay.persist_bytes, 256), max(lay.scratch_bytes, 256))
+    return hit
+
+
 class _TileRenderFusedFn(torch.autograd.Function):
     """TileBasedRenderer through the whole-pass C entry points: sync-free, two ctypes calls per frame."""
 
     @staticmethod
     def forward(ctx, positions, scales, rotations, colors, opacities, cfg):
-        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
+        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
         L = _lib.lib()
         dev = positions.device
         n = positions.shape[0]
-        cap = worst_case_instances(n, n_views, width, height, max_radius)
-        lay = _lib.TileLayout()
-        _lib.check(L.frb_tile_layout(n, n_views, width, height, cap, ctypes.byref(lay)), "frb_tile_layout")
-        persist = torch.empty(max(lay.persist_bytes, 256), dtype=torch.uint8, device=dev)
-        scratch = torch.empty(max(lay.scratch_bytes, 256), dtype=torch.uint8, device=dev)
-        image = torch.empty(n_views, 3, height, width, dtype=torch.float32, device=dev)
-        depth = torch.empty(n_views, height, width, dtype=torch.float32, device=dev)
-        alpha = torch.empty(n_views, height, width, dtype=torch.float32, device=dev)
-        cam = np.ascontiguousarray(cam_vecs, np.float32)
-        bg_host = np.asarray(bg, np.float32)
-        img_p, dep_p, alp_p = image.data_ptr(), depth.data_ptr(), alpha.data_ptr()
+        cap, persist_bytes, scratch_bytes = _tile_layout(n, n_views, width, height, max_radius)
+        persist = torch.empty(persist_bytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        # one buffer: [image 3 | depth 1 | alpha 1] x views x H x W (image and depth adjacent: one D2H copy)
+        hw = height * width
+        out = torch.empty(5 * n_views * hw, dtype=torch.float32, device=dev)
+        image = out[:3 * n_views * hw].view(n_views, 3, height, width)
+        depth = out[3 * n_views * hw:4 * n_views * hw].view(n_views, height, width)
+        alpha = out[4 * n_views * hw:].view(n_views, height, width)
+        base = out.data_ptr()
         _call("frb_tile_render_fwd", L.frb_tile_render_fwd, n, n_views, _ptr(positions), _ptr(scales),
               _ptr(rotations), _ptr(colors), _ptr(opacities), cam.ctypes.data, float(max_radius), width, height,
-              bg_host.ctypes.data, float(t_eps), cap, _ptr(persist), _ptr(scratch), img_p, dep_p, alp_p, _stream())
+              bg.ctypes.data, float(t_eps), cap, _ptr(persist), _ptr(scratch), base, base + 12 * n_views * hw,
+              base + 16 * n_views * hw, _stream())
         ctx.cfg, ctx.n, ctx.cap = cfg, n, cap
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(positions, scales, rotations, persist)
         return image, depth, alpha
 
     @staticmethod
     def backward(ctx, g_image, g_depth, g_alpha):
-        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
+        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
         positions, scales, rotations, persist = ctx.saved_tensors
         L = _lib.lib()
         dev = positions.device
@@ -247,14 +266,14 @@ class _TileRenderFusedFn(torch.autograd.Function):
                    else g_image.contiguous().float())
         g_depth = None if g_depth is None else g_depth.contiguous().float()
         g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
-        # one allocation: [grad2d 12 | positions 3 | scales 3 | rotations 4 | colors 3 | opacities 1] x n
+        # one allocation: [grad2d 12 | rotations 4 | positions 3 | scales 3 | colors 3 | opacities 1] x n
+        # (the float4-typed segments first: 16-byte aligned for every n; the 14 n gradient floats are contiguous)
         buf = torch.empty(26 * n, **f32)
-        grad2d, g_pos, g_scl = buf[:12 * n], buf[12 * n:15 * n].view(n, 3), buf[15 * n:18 * n].view(n, 3)
-        g_rot, g_col, g_opa = buf[18 * n:22 * n].view(n, 4), buf[22 * n:25 * n].view(n, 3), buf[25 * n:]
-        cam = np.ascontiguousarray(cam_vecs, np.float32)
-        bg_host = np.asarray(bg, np.float32)
+        grad2d, g_rot = buf[:12 * n], buf[12 * n:16 * n].view(n, 4)
+        g_pos, g_scl = buf[16 * n:19 * n].view(n, 3), buf[19 * n:22 * n].view(n, 3)
+        g_col, g_opa = buf[22 * n:25 * n].view(n, 3), buf[25 * n:]
         _call("frb_tile_render_bwd", L.frb_tile_render_bwd, n, n_views, _ptr(positions), _ptr(scales),
-              _ptr(rotations), cam.ctypes.data, width, height, bg_host.ctypes.data, ctx.cap, _ptr(persist),
+              _ptr(rotations), cam.ctypes.data, width, height, bg.ctypes.data, ctx.cap, _ptr(persist),
               _ptr(g_image), _ptr(g_depth), _ptr(g_alpha), _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot),
               _ptr(g_col), _ptr(g_opa), _stream())
         return g_pos, g_scl, g_rot, g_col, g_opa, None
@@ -278,7 +297,7 @@ class _TileRenderFn(torch.autograd.Function):
         alpha = torch.empty(n_views, height, width, **f32)
         state_T = torch.empty(n_views, height, width, **f32)
         state_n = torch.empty(n_views, height, width, dtype=torch.int32, device=dev)
-        bg_host = np.asarray(bg, np.float32)
+        bg_host = bg
         ckpt = None
         if phases is not None:
             n_tiles = bins.ranges.shape[0]
@@ -292,6 +311,7 @@ class _TileRenderFn(torch.autograd.Function):
                                        _ptr(state_n), _ptr(ckpt), st)
         ctx.cfg = cfg
         ctx.n = n
+        ctx.set_materialize_grads(False)
         ctx.has_phase = phases is not None
         ctx.save_for_backward(positions, scales, rotations, bins.ranges, bins.sorted_records, bins.sorted_gids,
                               state_T, state_n, tile_order,
@@ -315,7 +335,7 @@ class _TileRenderFn(torch.autograd.Function):
         g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
         grad2d = torch.zeros(n, RECORD_FLOATS, **f32)
         g_phases = torch.zeros(n, **f32) if ctx.has_phase else None
-        bg_host = np.asarray(bg, np.float32)
+        bg_host = bg
         _call("frb_composite_bwd", L.frb_composite_bwd_sched, n_views, width, height, _ptr(tile_order),
               _ptr(ranges), _ptr(sorted_records),
                                        _ptr(sorted_gids), _ptr(sorted_phases) if ctx.has_phase else None,
@@ -327,7 +347,7 @@ class _TileRenderFn(torch.autograd.Function):
         g_rot = torch.empty(n, 4, **f32)
         g_col = torch.empty(n, 3, **f32)
         g_opa = torch.empty(n, **f32)
-        cam = np.ascontiguousarray(cam_vecs, np.float32)
+        cam = cam_vecs
         _call("frb_project_bwd", L.frb_project_bwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), cam.ctypes.data,
                                      _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col),
                                      _ptr(g_opa), st)
@@ -357,8 +377,8 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
                       rotations=rotations.reshape(B * N, 4), colors=colors.reshape(B * N, 3),
                       opacities=opacities.reshape(B * N),
                       phases=None if phases is None else phases.reshape(B * N))
-    cam_vecs = np.stack([camera_vector(c, width, height) for c in cameras])
-    cfg = (cam_vecs, B, int(width), int(height), tuple(float(x) for x in background), float(max_radius),
+    cam_vecs = np.ascontiguousarray(np.stack([camera_vector(c, width, height) for c in cameras]), np.float32)
+    cfg = (cam_vecs, B, int(width), int(height), np.asarray(background, np.float32), float(max_radius),
            float(t_eps), float(phase_amplitude))
     n_total = B * N
     fused = (FUSED_CALLS and _TIMER is None and t["phases"] is None and n_total > 0 and
@@ -403,11 +423,12 @@ class TileBasedRenderer(nn.Module):
             positions.unsqueeze(0), scales.unsqueeze(0), rotations.unsqueeze(0), colors.unsqueeze(0),
             opacities.reshape(1, -1), [camera], self.width, self.height, bg, self.max_radius, self.t_eps,
             phases.reshape(1, -1) if use_phase else None, self.phase_amplitude)
-        out: List[torch.Tensor] = [image[0]]
+        # squeeze (a view: its backward launches nothing), not image[0] (select backward = fill + copy)
+        out: List[torch.Tensor] = [image.squeeze(0)]
         if return_depth:
-            out.append(depth[0])
+            out.append(depth.squeeze(0))
         if return_alpha:
-            out.append(alpha[0])
+            out.append(alpha.squeeze(0))
         return out[0] if len(out) == 1 else tuple(out)
 
     def render_batch(self, positions, scales, rotations, colors, opacities, cameras, phases=None):

@@ -228,7 +228,7 @@ class WaveFieldRenderer(nn.Module):
         image, depth = self.render_batch(positions.unsqueeze(0), scales.unsqueeze(0), rotations.unsqueeze(0),
                                          colors.unsqueeze(0), opacities.reshape(1, -1), [camera],
                                          phases.unsqueeze(0))
-        return (image[0], depth[0]) if return_depth else image[0]
+        return (image.squeeze(0), depth.squeeze(0)) if return_depth else image.squeeze(0)
 
 
 class ASMWaveFieldRenderer(nn.Module):
@@ -257,6 +257,9 @@ class ASMWaveFieldRenderer(nn.Module):
         self.wavelength = wavelength
         self.register_buffer("background", torch.tensor(background))
         self.register_buffer("depth_planes", torch.linspace(depth_range[0], depth_range[1], num_depth_planes))
+        # host copies for the C-ABI arguments (reading the buffers back would synchronise once per call)
+        self._planes_host = np.ascontiguousarray(self.depth_planes.numpy().astype(np.float32))
+        self._background_host = tuple(float(x) for x in background)
 
     def render_batch(self, positions, scales, rotations, colors, opacities, cameras, phases, wavelengths_rgb=None):
         """(B, N, .) inputs, B cameras -> image (B, 3, H, W)."""
@@ -270,9 +273,9 @@ class ASMWaveFieldRenderer(nn.Module):
             wl = np.full(3, self.wavelength, np.float32)
         else:
             wl = np.ascontiguousarray(torch.as_tensor(wavelengths_rgb).detach().float().cpu().numpy().reshape(3))
-        planes = np.ascontiguousarray(self.depth_planes.detach().float().cpu().numpy())
+        planes = self._planes_host
         cfg = (cam_vecs, B, int(self.width), int(self.height), float(self.max_radius),
-               tuple(float(x) for x in self.background.tolist()), planes, float(self.focal_depth),
+               self._background_host, planes, float(self.focal_depth),
                float(self.pixel_pitch), wl)
         with torch.cuda.device(t["positions"].device):
             return _AsmRenderFn.apply(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"],
@@ -284,7 +287,7 @@ class ASMWaveFieldRenderer(nn.Module):
             raise ValueError("ASMWaveFieldRenderer requires phases tensor.")            # DR:1187-1188
         image = self.render_batch(positions.unsqueeze(0), scales.unsqueeze(0), rotations.unsqueeze(0),
                                   colors.unsqueeze(0), opacities.reshape(1, -1), [camera], phases.unsqueeze(0),
-                                  wavelengths_rgb)[0]
+                                  wavelengths_rgb).squeeze(0)
         if return_depth:
             return image, torch.zeros(self.height, self.width, device=image.device)     # DR:1339-1342
         return image

@@ -21,3 +21,16 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(100): step()
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(22)
+from fresnel_b200.host import HostRenderSession
+sess = HostRenderSession(ren, 100000, dev)
+sess.load(host, *bench.upstream(1))
+for _ in range(10): sess.step(cam)
+torch.cuda.synchronize()
+t0=time.perf_counter()
+for _ in range(100): sess.step(cam)
+t1=time.perf_counter(); torch.cuda.synchronize(); t2=time.perf_counter()
+print('session enqueue ms/step', (t1-t0)*10, 'total ms/step', (t2-t0)*10)
+pr = cProfile.Profile(); pr.enable()
+for _ in range(100): sess.step(cam)
+pr.disable(); torch.cuda.synchronize()
+pstats.Stats(pr).sort_stats('tottime').print_stats(25)
