@@ -21,6 +21,8 @@ _SIGNATURES = {
     "frb_launch_count": (ctypes.c_ulonglong, []),
     "frb_project_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, c_float, P, P, P, P, P, P]),
     "frb_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
+    "frb_project_fwd_mode": (c_int, [c_int, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
+    "frb_project_bwd_mode": (c_int, [c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P]),
     "frb_sort_workspace_bytes": (c_size_t, [c_int]),
     "frb_radix_sort_pairs": (c_int, [c_int, P, P, P, P, c_int, c_int, P, P]),
     "frb_radix_sort_pairs_dev": (c_int, [c_int, P, P, P, P, P, c_int, c_int, P, P]),
@@ -51,6 +53,10 @@ _SIGNATURES = {
     "frb_wave_finish_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     "frb_wave_splat_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float, P, P, P]),
     "frb_wave_chain_bwd": (c_int, [c_int, P, P, c_int, P, P, P, P]),
+    "frb_fourier_finish_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "frb_fourier_finish_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_unpack_gaussians": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_pack_gaussians": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "frb_asm_assign_planes": (c_int, [c_int, P, c_int, P, P, P]),
     "frb_asm_splat_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "frb_asm_propagate_fwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P]),

@@ -49,6 +49,19 @@
 #define FRB_COV_EPS 1e-4f                   /* DR:578 */
 #define FRB_ALPHA_MAX 0.99f                 /* DR:647 */
 
+/* Projection modes: which renderer of differentiable_renderer.py the records are for.
+ *   TILE    TileBasedRenderer / WaveFieldRenderer / ASMWaveFieldRenderer (DR:452-487, 541-543, 594-600)
+ *   DENSE   DifferentiableGaussianRenderer DR:245-409: every visible Gaussian touches every pixel.  The
+ *           rectangle is the box where exp(-0.5 m) can exceed 2^-40 (FRB_DENSE_SIGMAS standard deviations of
+ *           the regularised covariance), clipped to the image; what is dropped is below 1e-12 per pair.
+ *   FOURIER FourierGaussianRenderer DR:1500-1774: isotropic Gaussian with sigma^2 = (a + d)/2 + 1e-8,
+ *           exp(-r^2 / (2 sigma^2 + 1e-8)), same support truncation. */
+#define FRB_MODE_TILE 0
+#define FRB_MODE_DENSE 1
+#define FRB_MODE_FOURIER 2
+#define FRB_DENSE_SIGMAS 7.5f               /* exp(-0.5 * 7.5^2) = 6e-13 */
+#define FRB_DENSE_MARGIN 100.0f             /* DR:316-318 */
+
 /* One view: rows 0..2 of the 4x4 world->camera matrix, intrinsics, image size, clip planes. */
 struct FrbCamera {
     float V[12];
@@ -157,20 +170,40 @@ FRB_HD void frb_project_core(const float p[3], const float s[3], const float q[4
     o.v = FRB_ADD(FRB_DIV(FRB_MUL(cam.fy, -t.pcy), -t.zs), cam.cy);
 }
 
-FRB_HD void frb_project_finish(const FrbCamera& cam, float max_radius, FrbProjected& o) {
-    /* radius from the UN-regularised covariance DR:452-487 */
-    float trace = FRB_ADD(o.a, o.d);
-    float det = frb_clamp_min(FRB_SUB(FRB_MUL(o.a, o.d), FRB_MUL(o.b, o.c)), 1e-6f);
-    float disc = frb_clamp_min(FRB_SUB(FRB_MUL(trace, trace), FRB_MUL(4.0f, det)), 0.0f);
-    float lam = FRB_DIV(FRB_ADD(trace, FRB_SQRT(disc)), 2.0f);
-    float r = FRB_MUL(3.0f, FRB_SQRT(frb_clamp_min(lam, 1e-6f)));
-    r = frb_clamp_max(r, max_radius);
-    o.radius = r;
-
-    /* DR:541-543, strict inequalities; NaN compares false */
+FRB_HD void frb_project_finish(const FrbCamera& cam, float max_radius, FrbProjected& o,
+                                int mode = FRB_MODE_TILE) {
+    float r;
     int vis = (o.depth > cam.near_) && (o.depth < cam.far_);
-    vis = vis && (FRB_ADD(o.u, r) > 0.0f) && (FRB_SUB(o.u, r) < cam.width);
-    vis = vis && (FRB_ADD(o.v, r) > 0.0f) && (FRB_SUB(o.v, r) < cam.height);
+    if (mode == FRB_MODE_TILE) {
+        /* radius from the UN-regularised covariance DR:452-487 */
+        float trace = FRB_ADD(o.a, o.d);
+        float det = frb_clamp_min(FRB_SUB(FRB_MUL(o.a, o.d), FRB_MUL(o.b, o.c)), 1e-6f);
+        float disc = frb_clamp_min(FRB_SUB(FRB_MUL(trace, trace), FRB_MUL(4.0f, det)), 0.0f);
+        float lam = FRB_DIV(FRB_ADD(trace, FRB_SQRT(disc)), 2.0f);
+        r = FRB_MUL(3.0f, FRB_SQRT(frb_clamp_min(lam, 1e-6f)));
+        r = frb_clamp_max(r, max_radius);
+        /* DR:541-543, strict inequalities; NaN compares false */
+        vis = vis && (FRB_ADD(o.u, r) > 0.0f) && (FRB_SUB(o.u, r) < cam.width);
+        vis = vis && (FRB_ADD(o.v, r) > 0.0f) && (FRB_SUB(o.v, r) < cam.height);
+    } else if (mode == FRB_MODE_DENSE) {
+        /* DR:315-318: frustum and a 100-pixel margin on the centre; support box from the largest
+         * eigenvalue of cov + 1e-4 I (the quadratic form is >= r^2 / lambda_max) */
+        vis = vis && (o.u > -FRB_DENSE_MARGIN) && (o.u < cam.width + FRB_DENSE_MARGIN);
+        vis = vis && (o.v > -FRB_DENSE_MARGIN) && (o.v < cam.height + FRB_DENSE_MARGIN);
+        float ar = o.a + FRB_COV_EPS, dr = o.d + FRB_COV_EPS, bs = 0.5f * (o.b + o.c);
+        float half_tr = 0.5f * (ar + dr), half_df = 0.5f * (ar - dr);
+        float lam = half_tr + sqrtf(half_df * half_df + bs * bs);
+        r = FRB_DENSE_SIGMAS * sqrtf(frb_clamp_min(lam, 0.0f)) + 1.0f;
+        if (!(r < 32000.0f)) r = 32000.0f;         /* also NaN: the rectangle becomes the whole image */
+    } else {
+        /* DR:1647-1649: frustum and one image size of margin on the centre */
+        vis = vis && (o.u > -cam.width) && (o.u < 2.0f * cam.width);
+        vis = vis && (o.v > -cam.height) && (o.v < 2.0f * cam.height);
+        float var = FRB_ADD(FRB_DIV(FRB_ADD(o.a, o.d), 2.0f), 1e-8f);        /* sigma^2  DR:1677 */
+        r = FRB_DENSE_SIGMAS * sqrtf(frb_clamp_min(var + 0.5e-8f, 0.0f)) + 1.0f;
+        if (!(r < 32000.0f)) r = 32000.0f;
+    }
+    o.radius = r;
     o.visible = vis;
 
     /* DR:594-597: Python floats (fp64) from .item(), int() truncation */
@@ -184,6 +217,16 @@ FRB_HD void frb_project_finish(const FrbCamera& cam, float max_radius, FrbProjec
         if (o.x0 >= o.x1 || o.y0 >= o.y1) { o.x0 = o.x1 = o.y0 = o.y1 = 0; } /* DR:599: skipped */
     }
 
+    if (mode == FRB_MODE_FOURIER) {
+        /* exp(-r^2 / (2 sigma^2 + 1e-8)) = exp2(A r^2)   DR:1725 */
+        float var = FRB_ADD(FRB_DIV(FRB_ADD(o.a, o.d), 2.0f), 1e-8f);
+        float sig = FRB_SQRT(var);                                           /* the reference squares the root */
+        float den = FRB_ADD(FRB_MUL(2.0f, FRB_MUL(sig, sig)), 1e-8f);
+        o.A = -FRB_LOG2E / den;
+        o.B = 0.0f;
+        o.C = o.A;
+        return;
+    }
     /* pinv(cov + 1e-4 I) for a full-rank 2x2 is the inverse DR:578-579; cross term DR:618 */
     float ar = o.a + FRB_COV_EPS, dr = o.d + FRB_COV_EPS;
     float detr = ar * dr - o.b * o.c;
@@ -201,23 +244,34 @@ FRB_HD void frb_project_finish(const FrbCamera& cam, float max_radius, FrbProjec
  */
 FRB_HD void frb_project_bwd_one(const float p[3], const float s[3], const float q[4],
                                 const FrbCamera& cam, float g_u, float g_v, float g_A, float g_B,
-                                float g_C, float g_depth, float gp[3], float gs[3], float gq[4]) {
+                                float g_C, float g_depth, float gp[3], float gs[3], float gq[4],
+                                int mode = FRB_MODE_TILE) {
     FrbProjTmp t;
     FrbProjected o;
     frb_project_core(p, s, q, cam, t, o);
     const float* V = cam.V;
 
-    /* conic -> regularised covariance X = cov + eps I; Y = X^-1; dX = -Y^T G Y^T */
-    float ar = o.a + FRB_COV_EPS, dr = o.d + FRB_COV_EPS;
-    float inv = 1.0f / (ar * dr - o.b * o.c);
-    float Y00 = dr * inv, Y01 = -o.b * inv, Y10 = -o.c * inv, Y11 = ar * inv;
-    float G00 = FRB_CONIC_SCALE * g_A, G01 = FRB_CONIC_SCALE * g_B, G10 = G01, G11 = FRB_CONIC_SCALE * g_C;
-    /* P = Y^T G */
-    float P00 = Y00 * G00 + Y10 * G10, P01 = Y00 * G01 + Y10 * G11;
-    float P10 = Y01 * G00 + Y11 * G10, P11 = Y01 * G01 + Y11 * G11;
-    /* dX = -(P Y^T) */
-    float ga = -(P00 * Y00 + P01 * Y01), gb = -(P00 * Y10 + P01 * Y11);
-    float gc = -(P10 * Y00 + P11 * Y01), gd = -(P10 * Y10 + P11 * Y11);
+    float ga, gb, gc, gd;
+    if (mode == FRB_MODE_FOURIER) {
+        /* A = C = -log2e / (2 sigma^2 + 1e-8), sigma^2 = (a + d)/2 + 1e-8: dA/da = dA/dd = log2e / den^2 */
+        float var = (o.a + o.d) * 0.5f + 1e-8f;
+        float den = 2.0f * var + 1e-8f;
+        float gvar = (g_A + g_C) * 2.0f * FRB_LOG2E / (den * den);
+        ga = gd = 0.5f * gvar;
+        gb = gc = 0.0f;
+    } else {
+        /* conic -> regularised covariance X = cov + eps I; Y = X^-1; dX = -Y^T G Y^T */
+        float ar = o.a + FRB_COV_EPS, dr = o.d + FRB_COV_EPS;
+        float inv = 1.0f / (ar * dr - o.b * o.c);
+        float Y00 = dr * inv, Y01 = -o.b * inv, Y10 = -o.c * inv, Y11 = ar * inv;
+        float G00 = FRB_CONIC_SCALE * g_A, G01 = FRB_CONIC_SCALE * g_B, G10 = G01, G11 = FRB_CONIC_SCALE * g_C;
+        /* P = Y^T G */
+        float P00 = Y00 * G00 + Y10 * G10, P01 = Y00 * G01 + Y10 * G11;
+        float P10 = Y01 * G00 + Y11 * G10, P11 = Y01 * G01 + Y11 * G11;
+        /* dX = -(P Y^T) */
+        ga = -(P00 * Y00 + P01 * Y01); gb = -(P00 * Y10 + P01 * Y11);
+        gc = -(P10 * Y00 + P11 * Y01); gd = -(P10 * Y10 + P11 * Y11);
+    }
 
     /* cov = J S3 J^T with J = [[j00, 0, j02], [0, j11, j12]] */
     float J[2][3] = {{t.j00, 0.0f, t.j02}, {0.0f, t.j11, t.j12}};

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256)
 frb_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float* __restrict__ positions,
                        const float* __restrict__ scales, const float* __restrict__ rotations,
                        const float* __restrict__ colors, const float* __restrict__ opacities,
-                       float max_radius, float4* __restrict__ records, int4* __restrict__ rects,
+                       float max_radius, int mode, float4* __restrict__ records, int4* __restrict__ rects,
                        uint32_t* __restrict__ depth_bits, uint32_t* __restrict__ tiles_touched,
                        float4* __restrict__ debug) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +47,7 @@ frb_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
     FrbProjTmp t;
     FrbProjected o;
     frb_project_core(p, s, q, cam, t, o);
-    frb_project_finish(cam, max_radius, o);
+    frb_project_finish(cam, max_radius, o, mode);
 
     uint32_t touched = 0;
     if (o.visible && o.x1 > o.x0) {
@@ -74,7 +74,7 @@ frb_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
 __global__ void __launch_bounds__(256)
 frb_project_bwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float* __restrict__ positions,
                        const float* __restrict__ scales, const float* __restrict__ rotations,
-                       const float4* __restrict__ grad2d, float* __restrict__ g_positions,
+                       const float4* __restrict__ grad2d, int mode, float* __restrict__ g_positions,
                        float* __restrict__ g_scales, float4* __restrict__ g_rotations,
                        float* __restrict__ g_colors, float* __restrict__ g_opacities) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +94,7 @@ frb_project_bwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
         float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
         float4 q4 = reinterpret_cast<const float4*>(rotations)[i];
         float q[4] = {q4.x, q4.y, q4.z, q4.w};
-        frb_project_bwd_one(p, s, q, cam, g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, gp, gs, gq);
+        frb_project_bwd_one(p, s, q, cam, g0.x, g0.y, g0.z, g0.w, g1.x, g1.z, gp, gs, gq, mode);
     }
     g_positions[3 * i] = gp[0]; g_positions[3 * i + 1] = gp[1]; g_positions[3 * i + 2] = gp[2];
     g_scales[3 * i] = gs[0]; g_scales[3 * i + 1] = gs[1]; g_scales[3 * i + 2] = gs[2];
@@ -106,6 +106,16 @@ extern "C" int frb_project_fwd(int n, int n_views, const float* positions, const
                                const float* camera_host, float max_radius, float* records,
                                int32_t* rects, uint32_t* depth_bits, uint32_t* tiles_touched,
                                float* debug, void* stream) {
+    return frb_project_fwd_mode(n, n_views, positions, scales, rotations, colors, opacities, camera_host,
+                                max_radius, FRB_MODE_TILE, records, rects, depth_bits, tiles_touched, debug, stream);
+}
+
+extern "C" int frb_project_fwd_mode(int n, int n_views, const float* positions, const float* scales,
+                                    const float* rotations, const float* colors, const float* opacities,
+                                    const float* camera_host, float max_radius, int mode, float* records,
+                                    int32_t* rects, uint32_t* depth_bits, uint32_t* tiles_touched,
+                                    float* debug, void* stream) {
+    if (mode < FRB_MODE_TILE || mode > FRB_MODE_FOURIER) return FRB_E_INVALID;
     FrbViewSet vs;
     int rc = frb_fill_views(n, n_views, camera_host, &vs);
     if (rc) return rc;
@@ -114,7 +124,7 @@ extern "C" int frb_project_fwd(int n, int n_views, const float* positions, const
         !tiles_touched)
         return FRB_E_INVALID;
     frb_project_fwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        n, vs, positions, scales, rotations, colors, opacities, max_radius, (float4*)records,
+        n, vs, positions, scales, rotations, colors, opacities, max_radius, mode, (float4*)records,
         (int4*)rects, depth_bits, tiles_touched, (float4*)debug);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
@@ -125,6 +135,15 @@ extern "C" int frb_project_bwd(int n, int n_views, const float* positions, const
                                const float* rotations, const float* camera_host, const float* grad2d,
                                float* g_positions, float* g_scales, float* g_rotations,
                                float* g_colors, float* g_opacities, void* stream) {
+    return frb_project_bwd_mode(n, n_views, positions, scales, rotations, camera_host, grad2d, FRB_MODE_TILE,
+                                g_positions, g_scales, g_rotations, g_colors, g_opacities, stream);
+}
+
+extern "C" int frb_project_bwd_mode(int n, int n_views, const float* positions, const float* scales,
+                                    const float* rotations, const float* camera_host, const float* grad2d,
+                                    int mode, float* g_positions, float* g_scales, float* g_rotations,
+                                    float* g_colors, float* g_opacities, void* stream) {
+    if (mode < FRB_MODE_TILE || mode > FRB_MODE_FOURIER) return FRB_E_INVALID;
     FrbViewSet vs;
     int rc = frb_fill_views(n, n_views, camera_host, &vs);
     if (rc) return rc;
@@ -132,7 +151,7 @@ extern "C" int frb_project_bwd(int n, int n_views, const float* positions, const
     if (!positions || !scales || !rotations || !grad2d || !g_positions || !g_scales || !g_rotations)
         return FRB_E_INVALID;
     frb_project_bwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        n, vs, positions, scales, rotations, (const float4*)grad2d, g_positions, g_scales,
+        n, vs, positions, scales, rotations, (const float4*)grad2d, mode, g_positions, g_scales,
         (float4*)g_rotations, g_colors, g_opacities);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();

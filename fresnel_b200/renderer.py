@@ -109,7 +109,8 @@ class TileBins:
 
 def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
                width: int, height: int, max_radius: float, phases=None, keep_debug: bool = False,
-               sort: bool = True, low_word_fn=None, presort: bool = True, sync: Optional[bool] = None) -> TileBins:
+               sort: bool = True, low_word_fn=None, presort: bool = True, sync: Optional[bool] = None,
+               mode: int = 0) -> TileBins:
     """Projection + binning: everything up to the per-tile sorted record lists.
 
     Sequences frb_project_fwd -> frb_depth_order -> frb_tile_offsets -> frb_bin_emit ->
@@ -124,6 +125,8 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     ``sort=False`` emits in index order and sorts all 64 key bits (test path).  ``low_word_fn(bins)``
     replaces the depth bits as the low key word (ASM: the depth-plane index).  ``presort=False`` skips
     the depth order altogether (order-free renderers): lists come out in ascending Gaussian index.
+    ``mode``: projection mode of frb_project_fwd_mode (0 tile, 1 dense, 2 Fourier); modes 1 and 2 have
+    image-sized rectangles, so they always take the exact-size (sync) path.
     """
     L = _lib.lib()
     dev = positions.device
@@ -139,9 +142,9 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     b.depth_bits = torch.empty(n, **i32)
     b.touched = torch.empty(n, **i32)
     b.rects = torch.empty(n, 4, **i32) if keep_debug else None
-    _call("frb_project_fwd", L.frb_project_fwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), _ptr(colors),
-                                 _ptr(opacities), cam.ctypes.data, float(max_radius), _ptr(b.records),
-                                 _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
+    _call("frb_project_fwd", L.frb_project_fwd_mode, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations),
+          _ptr(colors), _ptr(opacities), cam.ctypes.data, float(max_radius), int(mode), _ptr(b.records),
+          _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
 
     if low_word_fn is not None:
         b.depth_bits = low_word_fn(b)
@@ -158,7 +161,7 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     worst = n * min(tiles_x * tiles_y, span * span)
     if sync is None:
         sync = (keep_debug or not sort or phases is not None or low_word_fn is not None or not presort
-                or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES)
+                or mode != 0 or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES)
     if sync:
         m = int(offsets[n].item())      # the one host sync of the forward pass
         m_dev = None
@@ -231,7 +234,7 @@ class _TileRenderFusedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, positions, scales, rotations, colors, opacities, cfg):
-        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
+        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg[:8]
         L = _lib.lib()
         dev = positions.device
         n = positions.shape[0]
@@ -256,7 +259,7 @@ class _TileRenderFusedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_image, g_depth, g_alpha):
-        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
+        (cam, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg[:8]
         positions, scales, rotations, persist = ctx.saved_tensors
         L = _lib.lib()
         dev = positions.device
@@ -284,13 +287,14 @@ class _TileRenderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, positions, scales, rotations, colors, opacities, phases, cfg):
-        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = cfg[:8]
+        mode = cfg[8] if len(cfg) > 8 else 0
         L = _lib.lib()
         dev = positions.device
         st = _stream()
         n = positions.shape[0]
         bins = build_bins(positions, scales, rotations, colors, opacities, cam_vecs, n_views, width, height,
-                          max_radius, phases=phases)
+                          max_radius, phases=phases, mode=mode)
         f32 = dict(dtype=torch.float32, device=dev)
         image = torch.empty(n_views, 3, height, width, **f32)
         depth = torch.empty(n_views, height, width, **f32)
@@ -321,7 +325,8 @@ class _TileRenderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_image, g_depth, g_alpha):
-        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg
+        (cam_vecs, n_views, width, height, bg, max_radius, t_eps, phase_amp) = ctx.cfg[:8]
+        mode = ctx.cfg[8] if len(ctx.cfg) > 8 else 0
         (positions, scales, rotations, ranges, sorted_records, sorted_gids, state_T, state_n, tile_order,
          sorted_phases, ckpt) = ctx.saved_tensors
         L = _lib.lib()
@@ -348,15 +353,15 @@ class _TileRenderFn(torch.autograd.Function):
         g_col = torch.empty(n, 3, **f32)
         g_opa = torch.empty(n, **f32)
         cam = cam_vecs
-        _call("frb_project_bwd", L.frb_project_bwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations), cam.ctypes.data,
-                                     _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col),
-                                     _ptr(g_opa), st)
+        _call("frb_project_bwd", L.frb_project_bwd_mode, n, n_views, _ptr(positions), _ptr(scales),
+              _ptr(rotations), cam.ctypes.data, _ptr(grad2d), int(mode), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot),
+              _ptr(g_col), _ptr(g_opa), st)
         return g_pos, g_scl, g_rot, g_col, g_opa, g_phases, None
 
 
 def render_views(positions, scales, rotations, colors, opacities, cameras: Sequence, width: int, height: int,
                  background=(0.0, 0.0, 0.0), max_radius: float = 64, t_eps: float = DEFAULT_T_EPS,
-                 phases=None, phase_amplitude: float = 0.25
+                 phases=None, phase_amplitude: float = 0.25, mode: int = 0
                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Render B views in one pass of the kernels (the loop at train_gaussian_decoder.py:1209-1223).
 
@@ -370,7 +375,7 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
     if B > 32:
         outs = [render_views(positions[i:i + 32], scales[i:i + 32], rotations[i:i + 32], colors[i:i + 32],
                              opacities[i:i + 32], cameras[i:i + 32], width, height, background, max_radius,
-                             t_eps, None if phases is None else phases[i:i + 32], phase_amplitude)
+                             t_eps, None if phases is None else phases[i:i + 32], phase_amplitude, mode)
                 for i in range(0, B, 32)]
         return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
     t = _check_inputs(positions=positions.reshape(B * N, 3), scales=scales.reshape(B * N, 3),
@@ -379,9 +384,9 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
                       phases=None if phases is None else phases.reshape(B * N))
     cam_vecs = np.ascontiguousarray(np.stack([camera_vector(c, width, height) for c in cameras]), np.float32)
     cfg = (cam_vecs, B, int(width), int(height), np.asarray(background, np.float32), float(max_radius),
-           float(t_eps), float(phase_amplitude))
+           float(t_eps), float(phase_amplitude), int(mode))
     n_total = B * N
-    fused = (FUSED_CALLS and _TIMER is None and t["phases"] is None and n_total > 0 and
+    fused = (FUSED_CALLS and _TIMER is None and t["phases"] is None and n_total > 0 and mode == 0 and
              worst_case_instances(n_total, B, int(width), int(height), float(max_radius)) * INSTANCE_BYTES
              <= SYNC_FREE_BUDGET_BYTES)
     with torch.cuda.device(t["positions"].device):
@@ -441,3 +446,34 @@ class TileBasedRenderer(nn.Module):
         return render_views(positions, scales, rotations, colors, opacities, cams, self.width, self.height,
                             bg, self.max_radius, self.t_eps, phases if use_phase else None,
                             self.phase_amplitude)
+
+
+class DifferentiableGaussianRenderer(nn.Module):
+    """Differentiable 2D Gaussian splatting renderer - CUDA drop-in for the reference module of the same name
+    (scripts/models/differentiable_renderer.py:245-409): every visible Gaussian is evaluated at every pixel
+    and composited front to back.
+
+    The reference materialises (512, H, W) Gaussian images; here the dense evaluation runs through the tile
+    compositor with per-Gaussian support rectangles of 7.5 standard deviations (csrc/frb_math.h,
+    FRB_MODE_DENSE) - the dropped tail is below 1e-12 per Gaussian and pixel.  Visibility is the reference's
+    (frustum and a 100-pixel margin on the projected centre, DR:315-318); ``t_eps`` as in TileBasedRenderer.
+    """
+
+    def __init__(self, image_width: int, image_height: int,
+                 background: Tuple[float, float, float] = (0.0, 0.0, 0.0), *, t_eps: float = DEFAULT_T_EPS):
+        super().__init__()
+        self.width = image_width
+        self.height = image_height
+        self.background = torch.tensor(background)
+        self.t_eps = t_eps
+
+    def forward(self, positions: torch.Tensor, scales: torch.Tensor, rotations: torch.Tensor,
+                colors: torch.Tensor, opacities: torch.Tensor, camera, return_depth: bool = False):
+        bg = tuple(float(x) for x in self.background.tolist())
+        image, depth, _ = render_views(
+            positions.unsqueeze(0), scales.unsqueeze(0), rotations.unsqueeze(0), colors.unsqueeze(0),
+            opacities.reshape(1, -1), [camera], self.width, self.height, bg, 32000.0, self.t_eps, None, 0.25,
+            mode=1)
+        if return_depth:
+            return image.squeeze(0), depth.squeeze(0)
+        return image.squeeze(0)

@@ -27,7 +27,8 @@ def _phase_stride(phases: torch.Tensor, n: int) -> int:
     raise ValueError(f"phases must have shape (N,) or (N, 3); got {tuple(phases.shape)} for N={n}")
 
 
-def _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, stride, cfg, low_word_fn=None):
+def _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, stride, cfg, low_word_fn=None,
+                       mode: int = 0):
     """Projection, binning (no depth order needed) and the sorted 32-byte (colour cos/sin) side records."""
     cam_vecs, n_views, width, height, max_radius = cfg[:5]
     L = _lib.lib()
@@ -35,7 +36,7 @@ def _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, 
     n = positions.shape[0]
     st = _stream()
     bins = build_bins(positions, scales, rotations, colors, opacities, cam_vecs, n_views, width, height,
-                      max_radius, presort=low_word_fn is not None, low_word_fn=low_word_fn)
+                      max_radius, presort=low_word_fn is not None, low_word_fn=low_word_fn, mode=mode)
     wc = torch.empty(n, WC_FLOATS, dtype=torch.float32, device=dev)
     _call("frb_wave_prepare", L.frb_wave_prepare, n, _ptr(colors), _ptr(phases), stride, _ptr(wc), st)
     sorted_wc = torch.empty(max(bins.m, 1), WC_FLOATS, dtype=torch.float32, device=dev)
@@ -43,7 +44,7 @@ def _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, 
     return bins, sorted_wc
 
 
-def _project_backward(ctx_inputs, cam_vecs, n_views, grad2d):
+def _project_backward(ctx_inputs, cam_vecs, n_views, grad2d, mode: int = 0):
     positions, scales, rotations = ctx_inputs
     L = _lib.lib()
     n = positions.shape[0]
@@ -51,8 +52,8 @@ def _project_backward(ctx_inputs, cam_vecs, n_views, grad2d):
     g_pos, g_scl, g_rot = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 4, **f32)
     g_col, g_opa = torch.empty(n, 3, **f32), torch.empty(n, **f32)
     cam = np.ascontiguousarray(cam_vecs, np.float32)
-    _call("frb_project_bwd", L.frb_project_bwd, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations),
-          cam.ctypes.data, _ptr(grad2d), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col), _ptr(g_opa),
+    _call("frb_project_bwd", L.frb_project_bwd_mode, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations),
+          cam.ctypes.data, _ptr(grad2d), int(mode), _ptr(g_pos), _ptr(g_scl), _ptr(g_rot), _ptr(g_col), _ptr(g_opa),
           _stream())
     return g_pos, g_scl, g_rot, g_col, g_opa
 

@@ -84,6 +84,20 @@ int frb_project_bwd(int n, int n_views, const float* positions, const float* sca
                     float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
                     float* g_opacities, void* stream);
 
+/* Projection for the other renderers of the same reference file.  mode:
+ *   0 = FRB_MODE_TILE     TileBasedRenderer / WaveFieldRenderer / ASMWaveFieldRenderer (== the two functions above)
+ *   1 = FRB_MODE_DENSE    DifferentiableGaussianRenderer  differentiable_renderer.py:245-409
+ *   2 = FRB_MODE_FOURIER  FourierGaussianRenderer         differentiable_renderer.py:1500-1774
+ * Same record layout; only visibility, support rectangle and the conic differ (csrc/frb_math.h). */
+int frb_project_fwd_mode(int n, int n_views, const float* positions, const float* scales,
+                         const float* rotations, const float* colors, const float* opacities,
+                         const float* camera_host, float max_radius, int mode, float* records, int32_t* rects,
+                         uint32_t* depth_bits, uint32_t* tiles_touched, float* debug, void* stream);
+int frb_project_bwd_mode(int n, int n_views, const float* positions, const float* scales,
+                         const float* rotations, const float* camera_host, const float* grad2d, int mode,
+                         float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
+                         float* g_opacities, void* stream);
+
 /* ---- binning: depth order, offsets, keys, stable radix sort, ranges, gather -------- */
 /* Stable LSD radix sort of (key, value) pairs on key bits [begin_bit, end_bit).
  * The sorted result is always left in keys / vals; *_tmp are scratch of the same size. */
@@ -231,6 +245,25 @@ int frb_asm_propagate_bwd(int n_views, int width, int height, int n_planes,
                           const float* wavelengths_host, const float* background_host,
                           const float* total, const uint32_t* rmax_bits, const float* g_image, float* red,
                           float* g_total, float* d_fields, void* stream);
+
+/* ---- FourierGaussianRenderer epilogue (differentiable_renderer.py:1740-1753) and its backward ----
+ * accum: [view][8][H][W] as written by frb_wave_splat_fwd on FRB_MODE_FOURIER records with zero phases
+ * (planes 0..2 = channel sums); mx_key: n_views words (global maximum, order-preserving key);
+ * red: 2 * n_views floats scratch; gpix: [view][8][H][W] for frb_wave_splat_bwd. */
+int frb_fourier_finish_fwd(int n_views, int width, int height, const float* accum, uint32_t* mx_key,
+                           const float* background_host, float* image, void* stream);
+int frb_fourier_finish_bwd(int n_views, int width, int height, const float* accum, const uint32_t* mx_key,
+                           const float* background_host, const float* g_image, float* red, float* gpix,
+                           void* stream);
+
+/* ---- on-disk formats --------------------------------------------------------
+ * rows: n x 14 floats as stored in the file body [position 3 | scale 3 | rotation wxyz 4 | colour 3 | opacity 1].
+ * ply = 0: the reference's .bin (differentiable_renderer.py:1461-1497, renderer.cpp:557-647), a plain split;
+ * ply = 1: 3DGS .ply rows (renderer.cpp:649-793): exp / log scale, SH-DC colour, sigmoid / logit opacity. */
+int frb_unpack_gaussians(int n, int ply, const float* rows, float* positions, float* scales, float* rotations,
+                         float* colors, float* opacities, void* stream);
+int frb_pack_gaussians(int n, int ply, const float* positions, const float* scales, const float* rotations,
+                       const float* colors, const float* opacities, float* rows, void* stream);
 
 #ifdef __cplusplus
 }

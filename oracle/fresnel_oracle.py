@@ -519,6 +519,88 @@ def render_asm(positions, scales, rotations, colors, opacities, camera, width, h
 # --------------------------------------------------------------------------
 # Synthetic workloads
 # --------------------------------------------------------------------------
+# DifferentiableGaussianRenderer.forward (DR:245-409)
+# --------------------------------------------------------------------------
+def render_dense(positions, scales, rotations, colors, opacities, camera, width, height,
+                 background=(0.0, 0.0, 0.0)) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every visible Gaussian evaluated at every pixel, composited front to back.  DR:274-409.
+
+    Visibility is the frustum plus a 100-pixel margin on the projected centre (DR:315-318); the
+    quadratic form uses pinv(cov + 1e-4 I) with both off-diagonal terms (gaussian_2d, DR:198-242).
+    Returns (image (3,H,W), depth (H,W)).
+    """
+    H, W = height, width
+    bg = torch.tensor(background, dtype=torch.float32)
+    p = project(positions, scales, rotations, camera)
+    order = torch.argsort(p["depth"], stable=True)                           # DR:306 (stable)
+    vis = (p["depth"] > camera.near) & (p["depth"] < camera.far)             # DR:315
+    vis &= (p["u"] > -100) & (p["u"] < W + 100)                              # DR:316
+    vis &= (p["v"] > -100) & (p["v"] < H + 100)                              # DR:317
+    order = order[vis[order]]
+    if order.numel() == 0:                                                   # DR:319-325
+        anchor = _zero_anchor(colors, opacities, positions)
+        return bg.view(3, 1, 1).expand(3, H, W) + anchor, torch.zeros(H, W) + anchor
+    u, v, depth = p["u"][order], p["v"][order], p["depth"][order]
+    col, opa = colors[order], opacities[order]
+    cov = torch.stack([torch.stack([p["a"], p["b"]], -1), torch.stack([p["c"], p["d"]], -1)], -2)[order]
+    inv = torch.linalg.pinv(cov + 1e-4 * torch.eye(2).unsqueeze(0))          # DR:219-220
+    ly, lx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32),
+                            indexing="ij")
+    acc_c = torch.zeros(H, W, 3)
+    acc_a = torch.zeros(H, W)
+    acc_d = torch.zeros(H, W)
+    for i in range(order.numel()):                                           # DR:348-384
+        dx = lx - u[i]
+        dy = ly - v[i]
+        m = inv[i, 0, 0] * dx * dx + (inv[i, 0, 1] + inv[i, 1, 0]) * dx * dy + inv[i, 1, 1] * dy * dy
+        alpha = torch.clamp(torch.exp(-0.5 * m) * opa[i], 0, 0.99)           # DR:240, 362-365
+        contrib = alpha * (1.0 - acc_a)                                      # DR:370-373
+        acc_c = acc_c + contrib.unsqueeze(-1) * col[i].view(1, 1, 3)         # DR:376
+        acc_d = acc_d + contrib * depth[i]                                   # DR:379
+        acc_a = acc_a + contrib                                              # DR:382
+    acc_c = acc_c + (1.0 - acc_a).unsqueeze(-1) * bg.view(1, 1, 3)           # DR:386-387
+    return torch.clamp(acc_c.permute(2, 0, 1), 0, 1), acc_d                  # DR:390-393
+
+
+# --------------------------------------------------------------------------
+# FourierGaussianRenderer.forward (DR:1582-1766)
+# --------------------------------------------------------------------------
+def render_fourier(positions, scales, rotations, colors, opacities, camera, width, height,
+                   background=(0.0, 0.0, 0.0)) -> torch.Tensor:
+    """Isotropic additive splat over the whole image + global-max normalisation.  DR:1693-1753.
+
+    sigma^2 = (a + d)/2 + 1e-8 from the un-regularised projected covariance (DR:1673-1677); visibility is
+    the frustum plus one image size of margin on the centre (DR:1647-1649).  The wavelengths / phases of
+    the reference do not enter the image (DR:1686-1691 is dead code).  Returns the image (3,H,W).
+    """
+    H, W = height, width
+    bg = torch.tensor(background, dtype=torch.float32)
+    p = project(positions, scales, rotations, camera)
+    vis = (p["depth"] > camera.near) & (p["depth"] < camera.far)
+    vis &= (p["u"] > -W) & (p["u"] < 2 * W) & (p["v"] > -H) & (p["v"] < 2 * H)
+    idx = torch.nonzero(vis).squeeze(1)
+    if idx.numel() == 0:                                                     # DR:1651-1657
+        return bg.view(3, 1, 1).expand(3, H, W) + _zero_anchor(colors, opacities, positions)
+    u, v = p["u"][idx], p["v"][idx]
+    sigma = torch.sqrt((p["a"][idx] + p["d"][idx]) / 2 + 1e-8)               # DR:1677
+    col, opa = colors[idx], opacities[idx]
+    ly, lx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32),
+                            indexing="ij")
+    image = torch.zeros(3, H, W)
+    for s0 in range(0, idx.numel(), 16):                                     # DR:1701-1738
+        sl = slice(s0, min(s0 + 16, idx.numel()))
+        dx = lx.unsqueeze(0) - u[sl].view(-1, 1, 1)
+        dy = ly.unsqueeze(0) - v[sl].view(-1, 1, 1)
+        g = torch.exp(-(dx ** 2 + dy ** 2) / (2 * sigma[sl].view(-1, 1, 1) ** 2 + 1e-8)) * opa[sl].view(-1, 1, 1)
+        image = image + torch.stack([(col[sl, c].view(-1, 1, 1) * g).sum(0) for c in range(3)])
+    mx = image.max()                                                         # DR:1741
+    if mx > 1e-8:
+        image = image / mx
+    bgw = torch.clamp(1.0 - image.sum(dim=0, keepdim=True), 0, 1)            # DR:1746-1747
+    return torch.clamp(image + bg.view(3, 1, 1) * bgw, 0, 1)                 # DR:1748-1751
+
+
+# --------------------------------------------------------------------------
 def synthetic_cloud(n: int, seed: int = 0, s_lo: float = 0.005, s_hi: float = 0.03,
                     phase_hi: float = 1.0) -> Dict[str, torch.Tensor]:
     """The seeded synthetic Gaussian cloud every config uses (fp32, CPU)."""

@@ -248,6 +248,65 @@ def run_asm(name, inp, cam, W, H, bg, wl, depth_range, note=""):
     print(f"{name}: asm ok, img max {float(img_r.max()):.3f}")
 
 
+def run_dense(name, inp, cam, W, H, bg, note=""):
+    """DifferentiableGaussianRenderer (DR:245-409): reference forward + backward, oracle cross-check."""
+    gi, gd = upstream(H, W)
+    rc = ref_camera(cam)
+    ren = dr.DifferentiableGaussianRenderer(W, H, background=bg)
+    L = leafs(inp, GRAD_NAMES)
+    img_r, dep_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], rc,
+                       return_depth=True)
+    ((img_r * gi).sum() + (dep_r * gd).sum()).backward()
+    Lo = leafs(inp, GRAD_NAMES)
+    img_o, dep_o = fo.render_dense(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
+                                   Lo["opacities"], cam, W, H, background=bg)
+    ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
+    e_img, e_dep = rel(img_o.detach(), img_r.detach()), rel(dep_o.detach(), dep_r.detach())
+    assert e_img < 1e-5 and e_dep < 1e-5, (name, e_img, e_dep)
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32),
+               image=img_r.detach().numpy(), depth=dep_r.detach().numpy(),
+               gimage=gi.numpy(), gdepth=gd.numpy(), grad_source="reference", note=note)
+    worst = 0.0
+    for k in GRAD_NAMES:
+        out["in_" + k] = inp[k].numpy()
+        gr, go = L[k].grad.numpy(), Lo[k].grad.numpy()
+        worst = max(worst, rel(go, gr))
+        assert rel(go, gr) < 1e-4, (name, k, rel(go, gr))
+        out["grad_" + k] = gr
+    out["in_phases"] = inp["phases"].numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: dense ok, oracle-vs-ref img {e_img:.2e} depth {e_dep:.2e} grads {worst:.2e}")
+
+
+def run_fourier(name, inp, cam, W, H, bg, note=""):
+    """FourierGaussianRenderer (DR:1500-1774): reference forward + backward, oracle cross-check."""
+    gi, _ = upstream(H, W)
+    rc = ref_camera(cam)
+    ren = dr.FourierGaussianRenderer(W, H, background=bg)
+    L = leafs(inp, GRAD_NAMES)
+    img_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], rc)
+    (img_r * gi).sum().backward()
+    Lo = leafs(inp, GRAD_NAMES)
+    img_o = fo.render_fourier(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"], Lo["opacities"],
+                              cam, W, H, background=bg)
+    (img_o * gi).sum().backward()
+    e_img = rel(img_o.detach(), img_r.detach())
+    assert e_img < 1e-5, (name, e_img)
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), image=img_r.detach().numpy(),
+               gimage=gi.numpy(), grad_source="reference", note=note)
+    worst = 0.0
+    for k in GRAD_NAMES:
+        out["in_" + k] = inp[k].numpy()
+        gr = (L[k].grad if L[k].grad is not None else torch.zeros_like(L[k])).numpy()
+        go = (Lo[k].grad if Lo[k].grad is not None else torch.zeros_like(Lo[k])).numpy()
+        worst = max(worst, rel(go, gr))
+        assert rel(go, gr) < 1e-4, (name, k, rel(go, gr))
+        out["grad_" + k] = gr
+    out["in_phases"] = inp["phases"].numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: fourier ok, oracle-vs-ref img {e_img:.2e} grads {worst:.2e}, img max {float(img_r.max()):.3f}")
+
+
 # ---------------------------------------------------------------- fixtures
 def redraw_std(inp, idx, g):
     n = idx.numel()
@@ -353,7 +412,27 @@ def fx_asm():
             note="wavelengths_rgb=(0.0635,0.05,0.041), depth_range=(0.1,4.0), 16 planes")
 
 
-FIXTURES = dict(culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
+def fx_dense():
+    """DifferentiableGaussianRenderer: rotated look-at camera, some centres outside the image (100-px margin)."""
+    W, H = 96, 80
+    cam = fo.camera_from_pose(math.radians(20.0), math.radians(35.0), W)
+    cam.cx, cam.cy, cam.width, cam.height = W / 2, H / 2, W, H
+    inp = fo.synthetic_cloud(700, seed=17, s_lo=0.01, s_hi=0.08)
+    inp["positions"][:, 2] += 2.0                      # the look-at camera orbits the origin
+    inp["positions"][:60, 0] *= 4.0                    # far off-centre: in the margin or beyond it
+    run_dense("dense_700_96x80", inp, cam, W, H, (0.15, 0.05, 0.3),
+              note="DifferentiableGaussianRenderer, look-at camera el 20 az 35, non-zero background")
+
+
+def fx_fourier():
+    """FourierGaussianRenderer: identity view, non-zero background."""
+    W, H = 96, 80
+    cam = fo.default_camera(W, H)
+    inp = fo.synthetic_cloud(1500, seed=19, s_lo=0.005, s_hi=0.04)
+    run_fourier("fourier_1500_96x80", inp, cam, W, H, (0.2, 0.1, 0.05), note="FourierGaussianRenderer")
+
+
+FIXTURES = dict(dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
                 asm=fx_asm, c1=fx_c1)
 
 if __name__ == "__main__":

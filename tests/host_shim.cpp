@@ -44,4 +44,31 @@ void shim_project_bwd(int n, const float* p, const float* s, const float* q, con
                             gp + 3 * i, gs + 3 * i, gq + 4 * i);
     }
 }
+
+// mode-aware variants (FRB_MODE_DENSE / FRB_MODE_FOURIER: the other renderers of the reference file)
+void shim_project_fwd_mode(int n, const float* p, const float* s, const float* q, const float* cam20,
+                           float max_radius, int mode, float* out_f, int* out_i) {
+    FrbCamera cam = cam_from(cam20);
+    for (int i = 0; i < n; ++i) {
+        FrbProjTmp t;
+        FrbProjected o;
+        frb_project_core(p + 3 * i, s + 3 * i, q + 4 * i, cam, t, o);
+        frb_project_finish(cam, max_radius, o, mode);
+        float* f = out_f + 11 * i;
+        f[0] = o.u; f[1] = o.v; f[2] = o.depth; f[3] = o.a; f[4] = o.b; f[5] = o.c; f[6] = o.d;
+        f[7] = o.radius; f[8] = o.A; f[9] = o.B; f[10] = o.C;
+        int* k = out_i + 5 * i;
+        k[0] = o.visible; k[1] = o.x0; k[2] = o.x1; k[3] = o.y0; k[4] = o.y1;
+    }
+}
+
+void shim_project_bwd_mode(int n, const float* p, const float* s, const float* q, const float* cam20,
+                           const float* g2d, int mode, float* gp, float* gs, float* gq) {
+    FrbCamera cam = cam_from(cam20);
+    for (int i = 0; i < n; ++i) {
+        const float* g = g2d + 6 * i;
+        frb_project_bwd_one(p + 3 * i, s + 3 * i, q + 4 * i, cam, g[0], g[1], g[2], g[3], g[4], g[5],
+                            gp + 3 * i, gs + 3 * i, gq + 4 * i, mode);
+    }
+}
 }

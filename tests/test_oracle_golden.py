@@ -86,3 +86,33 @@ def test_oracle_asm_matches_reference(golden):
                                W, H, L["phases"], torch.from_numpy(z["wavelengths"]),
                                background=tuple(z["bg"]), depth_range=tuple(z["depth_range"]))
     assert rel(img, z["image"]) < 1e-5
+
+
+def test_oracle_dense_matches_reference(golden):
+    """DifferentiableGaussianRenderer restatement against the reference's own output and gradients."""
+    z = golden("dense_700_96x80")
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = golden_inputs(z, requires_grad=True)
+    img, dep = fo.render_dense(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, W, H,
+                               background=tuple(z["bg"]))
+    assert rel(img.detach(), z["image"]) < 1e-5
+    assert rel(dep.detach(), z["depth"]) < 1e-5
+    (img * torch.from_numpy(z["gimage"])).sum().add((dep * torch.from_numpy(z["gdepth"])).sum()).backward()
+    for k in GRAD_NAMES:
+        assert rel(L[k].grad, z["grad_" + k]) < 1e-4, k
+
+
+def test_oracle_fourier_matches_reference(golden):
+    """FourierGaussianRenderer restatement against the reference's own output and gradients."""
+    z = golden("fourier_1500_96x80")
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = golden_inputs(z, requires_grad=True)
+    img = fo.render_fourier(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, W, H,
+                            background=tuple(z["bg"]))
+    assert rel(img.detach(), z["image"]) < 1e-5
+    (img * torch.from_numpy(z["gimage"])).sum().backward()
+    for k in GRAD_NAMES:
+        g = L[k].grad if L[k].grad is not None else torch.zeros_like(L[k])
+        assert rel(g, z["grad_" + k]) < 1e-4, k
