@@ -57,6 +57,9 @@ _SIGNATURES = {
     "frb_fourier_finish_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "frb_unpack_gaussians": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "frb_pack_gaussians": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_decode_head_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, c_int, P, P, P, P, P, P]),
+    "frb_decode_head_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, c_float, c_float, P, c_int, P, P, P, P, P, P,
+                                    P, P]),
     "frb_asm_assign_planes": (c_int, [c_int, P, c_int, P, P, P]),
     "frb_asm_splat_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "frb_asm_propagate_fwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P]),

@@ -159,6 +159,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 // ONE atomic add per Gaussian value per tile.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = CTA_THREADS / 32;
+constexpr int BWD_FW = 8, BWD_FH = 4;           // pixel block of one warp (BWD_FW * BWD_FH = 32)
 constexpr int PAIR_STRIDE = 33;                 // float2 row stride: conflict-free both ways
 constexpr int N_GRADS = 10;
 
@@ -188,13 +189,17 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
-    const int py = ty * TILE + (threadIdx.x / TILE);
+    // a warp owns a BWD_FW x BWD_FH pixel block of the tile: the squarer the block, the fewer list entries
+    // whose rectangle touches it (phase 1 walks only those)
+    const int wx0 = tx * TILE + (warp % (TILE / BWD_FW)) * BWD_FW, wy0 = ty * TILE + (warp / (TILE / BWD_FW)) * BWD_FH;
+    const int wx1 = wx0 + BWD_FW, wy1 = wy0 + BWD_FH;
+    const int px = wx0 + (lane % BWD_FW);
+    const int py = wy0 + (lane / BWD_FW);
     const bool in_image = (px < width) && (py < height);
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
     const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
-    const float wbx = (float)(tx * TILE), wby = (float)(ty * TILE + 2 * warp);   // warp's pixel block origin
+    const float wbx = (float)wx0, wby = (float)wy0;                              // warp's pixel block origin
 
     const int2 range = ranges[tile];
 
@@ -229,7 +234,6 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const int count = min(sm.max_n, range.y - range.x);
     const int n_batches = (count + BATCH - 1) / BATCH;
     if (n_batches == 0) return;
-    const int wx0 = tx * TILE, wx1 = wx0 + TILE, wy0 = ty * TILE + 2 * warp, wy1 = wy0 + 2;
 
     // batches are visited last to first; ring slot (visit % STAGES) holds visit
     auto issue = [&](int visit) {
@@ -259,7 +263,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 
         for (int sb = (cnt - 1) >> 5; sb >= 0; --sb) {
             const int sub_cnt = min(32, cnt - sb * 32);
-            // ---- candidates: lane l tests record l of the block against this warp's 16x2 pixels ----
+            // ---- candidates: lane l tests record l of the block against this warp's pixel block ----
             const int base_n = b * BATCH + sb * 32;
             uint32_t cand;
             {
@@ -329,43 +333,41 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             // ---- phase 2: lane = Gaussian ------------------------------------------------
             float d_u = 0.f, d_v = 0.f, d_A = 0.f, d_B = 0.f, d_C = 0.f, d_o = 0.f, d_dep = 0.f, d_r = 0.f,
                   d_g = 0.f, d_b = 0.f;
-            if (gmask != 0) {
-                const bool mine = (gmask >> lane) & 1u;
-                const int jb = sb * 32 + (mine ? lane : 0);
+            if ((gmask >> lane) & 1u) {
+                const int jb = sb * 32 + lane;
                 const float4 r0 = rec[3 * jb + 0], r1 = rec[3 * jb + 1];
                 const float oln2 = r1.y * FRB_LN2;
                 const float ux = wbx - r0.x, uy = wby - r0.y;
                 const float2* row = my_pair + lane * PAIR_STRIDE;
                 const float4* pc = sm.pixc[warp];
-                if (mine) {
-                    float sx = 0.f, sy = 0.f;                 // sum dx*dpow, sum dy*dpow
+                float sx = 0.f, sy = 0.f;                 // sum dx*dpow, sum dy*dpow
 #pragma unroll
-                    for (int p = 0; p < 32; ++p) {
-                        float2 cd = row[p];
-                        float4 gpix = pc[p];
-                        float dx = ux + (float)(p & 15);
-                        float dy = uy + (float)(p >> 4);
-                        const float gda = cd.y;                 // g * gated dL/dalpha, formed in phase 1
-                        d_r = fmaf(cd.x, gpix.x, d_r);
-                        d_g = fmaf(cd.x, gpix.y, d_g);
-                        d_b = fmaf(cd.x, gpix.z, d_b);
-                        d_dep = fmaf(cd.x, gpix.w, d_dep);
-                        d_o += gda;
-                        float tx_ = dx * gda, ty_ = dy * gda;
-                        sx += tx_; sy += ty_;
-                        d_A = fmaf(dx, tx_, d_A);
-                        d_B = fmaf(dx, ty_, d_B);
-                        d_C = fmaf(dy, ty_, d_C);
-                    }
-                    // dL/d(power) = gda * o * ln2 (g = 2^power); u, v enter through dx, dy
-                    d_A *= oln2; d_B *= oln2; d_C *= oln2;
-                    d_u = (2.0f * r0.z * sx + r0.w * sy) * oln2;
-                    d_v = (r0.w * sx + 2.0f * r1.x * sy) * oln2;
+                for (int p = 0; p < 32; ++p) {
+                    float2 cd = row[p];
+                    float4 gpix = pc[p];
+                    float dx = ux + (float)(p % BWD_FW);
+                    float dy = uy + (float)(p / BWD_FW);
+                    const float gda = cd.y;                 // g * gated dL/dalpha, formed in phase 1
+                    d_r = fmaf(cd.x, gpix.x, d_r);
+                    d_g = fmaf(cd.x, gpix.y, d_g);
+                    d_b = fmaf(cd.x, gpix.z, d_b);
+                    d_dep = fmaf(cd.x, gpix.w, d_dep);
+                    d_o += gda;
+                    float tx_ = dx * gda, ty_ = dy * gda;
+                    sx += tx_; sy += ty_;
+                    d_A = fmaf(dx, tx_, d_A);
+                    d_B = fmaf(dx, ty_, d_B);
+                    d_C = fmaf(dy, ty_, d_C);
                 }
+                // dL/d(power) = gda * o * ln2 (g = 2^power); u, v enter through dx, dy
+                d_A *= oln2; d_B *= oln2; d_C *= oln2;
+                d_u = -(2.0f * r0.z * sx + r0.w * sy) * oln2;
+                d_v = -(r0.w * sx + 2.0f * r1.x * sy) * oln2;
             }
             {
+                // (shared-memory float atomics compile to CAS loops on sm_100a: plain stores, summed below)
                 float* pw = &sm.part[warp][0][sb * 32 + lane];
-                pw[0 * BATCH] = -d_u; pw[1 * BATCH] = -d_v; pw[2 * BATCH] = d_A; pw[3 * BATCH] = d_B;
+                pw[0 * BATCH] = d_u; pw[1 * BATCH] = d_v; pw[2 * BATCH] = d_A; pw[3 * BATCH] = d_B;
                 pw[4 * BATCH] = d_C; pw[5 * BATCH] = d_o; pw[6 * BATCH] = d_dep; pw[7 * BATCH] = d_r;
                 pw[8 * BATCH] = d_g; pw[9 * BATCH] = d_b;
             }

@@ -22,8 +22,9 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .camera import Camera
-from .renderer import TileBasedRenderer
+from .renderer import TileBasedRenderer, _ptr, _stream
 
 
 def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
@@ -60,6 +61,51 @@ def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
     return F.normalize(torch.stack(q, dim=-1), dim=-1, eps=1e-6)
 
 
+class _DecodeHeadFn(torch.autograd.Function):
+    """The decoder output head as one CUDA kernel per direction (csrc/head.cu):
+    raw (B, N, 16) -> positions / scales / rotations / colours / opacities of the Gaussians in ``idx`` (all N
+    when ``idx`` is None), written directly in the renderer's layout."""
+
+    @staticmethod
+    def forward(ctx, raw, depth_grid, depth_offset, idx, shape):
+        B, H, W, K = shape
+        L = _lib.lib()
+        dev = raw.device
+        n_out = H * W * K if idx is None else int(idx.numel())
+        f32 = dict(dtype=torch.float32, device=dev)
+        # one buffer, float4-typed segment first: [rotations 4 | positions 3 | scales 3 | colours 3 | opacities 1]
+        buf = torch.empty(14 * B * n_out, **f32)
+        m = B * n_out
+        rot = buf[:4 * m].view(B, n_out, 4)
+        pos = buf[4 * m:7 * m].view(B, n_out, 3)
+        scl = buf[7 * m:10 * m].view(B, n_out, 3)
+        col = buf[10 * m:13 * m].view(B, n_out, 3)
+        opa = buf[13 * m:].view(B, n_out)
+        _lib.check(L.frb_decode_head_fwd(B, H, W, K, _ptr(raw), _ptr(depth_grid), _ptr(depth_offset), None, 0.0, 0.0,
+                                         _ptr(idx), n_out if idx is not None else 0, _ptr(pos), _ptr(scl), _ptr(rot),
+                                         _ptr(col), _ptr(opa), _stream()), "frb_decode_head_fwd")
+        ctx.shape = shape
+        ctx.has_idx = idx is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(raw, idx if idx is not None else raw.new_empty(0))
+        return pos, scl, rot, col, opa
+
+    @staticmethod
+    def backward(ctx, g_pos, g_scl, g_rot, g_col, g_opa):
+        B, H, W, K = ctx.shape
+        raw, idx = ctx.saved_tensors
+        idx = idx if ctx.has_idx else None
+        n_out = H * W * K if idx is None else int(idx.numel())
+        L = _lib.lib()
+        g = [None if t is None else t.contiguous().float() for t in (g_pos, g_scl, g_rot, g_col, g_opa)]
+        g_raw = torch.empty_like(raw)
+        g_off = torch.empty(1, dtype=torch.float32, device=raw.device)
+        _lib.check(L.frb_decode_head_bwd(B, H, W, K, _ptr(raw), None, 0.0, 0.0, _ptr(idx),
+                                         n_out if idx is not None else 0, *(_ptr(t) for t in g), _ptr(g_raw),
+                                         _ptr(g_off), _stream()), "frb_decode_head_bwd")
+        return g_raw, None, g_off.reshape(()), None, None
+
+
 class PatchGaussianDecoder(nn.Module):
     """Per-patch MLP: (B, 384, 37, 37) features -> K Gaussians per patch (experiment 2 of the reference).
 
@@ -81,13 +127,37 @@ class PatchGaussianDecoder(nn.Module):
         layers.append(nn.Linear(prev, gaussians_per_patch * 16))
         self.mlp = nn.Sequential(*layers)
         self.depth_offset = nn.Parameter(torch.tensor(-2.0))
+        self.fused_head = True          # CUDA inputs: csrc/head.cu; False keeps the PyTorch ops (A/B checks)
 
-    def forward(self, features: torch.Tensor, depth: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def forward(self, features: torch.Tensor, depth: Optional[torch.Tensor] = None,
+                stochastic_k: Optional[int] = None, generator: Optional[torch.Generator] = None
+                ) -> Dict[str, torch.Tensor]:
+        """``stochastic_k``: HFTS stochastic rendering - return only K Gaussians per view, drawn without replacement
+        with p ~ mean opacity (train_gaussian_decoder.py:1154-1187; same draw as ``subsample_by_opacity``).
+        On a CUDA device the head (and the gather of the kept Gaussians) is the fused kernel; on the CPU it is the
+        PyTorch restatement below (used by the tests and the CPU arm of the benchmark)."""
         B, C, H, W = features.shape
         K = self.gaussians_per_patch
-        out = self.mlp(features.permute(0, 2, 3, 1).reshape(B * H * W, C)).reshape(B, H, W, K, 16)
-        ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device=features.device),
-                                torch.linspace(-1, 1, W, device=features.device), indexing="ij")
+        raw = self.mlp(features.permute(0, 2, 3, 1).reshape(B * H * W, C))
+        if features.is_cuda and self.fused_head:
+            raw = raw.reshape(B, H * W * K, 16)
+            grid = None
+            if depth is not None:
+                grid = F.interpolate(depth, (H, W), mode="bilinear", align_corners=False).reshape(B, H, W).contiguous()
+            idx = None
+            if stochastic_k is not None and stochastic_k < H * W * K:
+                with torch.no_grad():
+                    w = torch.sigmoid(raw[..., 15]).mean(dim=0) + 1e-6
+                    idx = torch.multinomial(w / w.sum(), stochastic_k, replacement=False, generator=generator)
+            pos, scl, rot, col, opa = _DecodeHeadFn.apply(raw.contiguous(), grid, self.depth_offset, idx, (B, H, W, K))
+            return {"positions": pos, "scales": scl, "rotations": rot, "colors": col, "opacities": opa}
+        out = self._torch_head(raw.reshape(B, H, W, K, 16), depth)
+        return subsample_by_opacity(out, stochastic_k, generator)
+
+    def _torch_head(self, out: torch.Tensor, depth: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        B, H, W, K, _ = out.shape
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device=out.device),
+                                torch.linspace(-1, 1, W, device=out.device), indexing="ij")
         base_x = xs[None, :, :, None].expand(B, -1, -1, K)
         base_y = ys[None, :, :, None].expand(B, -1, -1, K)
         if depth is not None:
@@ -203,8 +273,7 @@ class DecoderTrainer:
     # ---- the step, in the two halves that are captured separately --------------------------------
     def _forward_backward(self, features, depth, images) -> torch.Tensor:
         R = self.render_size
-        g = self.model(features, depth)
-        g = subsample_by_opacity(g, self.stochastic_k, self.generator)
+        g = self.model(features, depth, stochastic_k=self.stochastic_k, generator=self.generator)
         rendered, rendered_depth, _ = self.renderer.render_batch(g["positions"], g["scales"], g["rotations"],
                                                                  g["colors"], g["opacities"], self.camera)
         if images.shape[-1] != R:

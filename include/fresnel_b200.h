@@ -265,6 +265,24 @@ int frb_unpack_gaussians(int n, int ply, const float* rows, float* positions, fl
 int frb_pack_gaussians(int n, int ply, const float* positions, const float* scales, const float* rotations,
                        const float* colors, const float* opacities, float* rows, void* stream);
 
+/* ---- decoder output head -----------------------------------------------------
+ * DirectPatchDecoder.forward tail, scripts/models/gaussian_decoder_models.py:807-948 (default flags + the
+ * edge-aware modulation :881-895), fused with the stochastic subsampling gather of
+ * scripts/training/train_gaussian_decoder.py:1154-1187.
+ * raw: [B, H*W*K, 16] MLP outputs; depth_grid: [B, H, W] (nullable: z = depth_offset); depth_offset: device
+ * scalar; edge: [B, H, W] edge strength (nullable = edge-aware off); idx: n_sel int64 Gaussian indices kept for
+ * every view (nullable = all H*W*K).  Outputs are [B, n_out, .] with n_out = n_sel or H*W*K.
+ * Backward: g_raw [B, H*W*K, 16] is fully written (zero rows for unselected Gaussians); g_depth_offset[1].
+ * Any of the five incoming gradients may be NULL (= zero). */
+int frb_decode_head_fwd(int B, int H, int W, int K, const float* raw, const float* depth_grid,
+                        const float* depth_offset, const float* edge, float edge_scale_factor,
+                        float edge_opacity_boost, const long long* idx, int n_sel, float* positions, float* scales,
+                        float* rotations, float* colors, float* opacities, void* stream);
+int frb_decode_head_bwd(int B, int H, int W, int K, const float* raw, const float* edge, float edge_scale_factor,
+                        float edge_opacity_boost, const long long* idx, int n_sel, const float* g_positions,
+                        const float* g_scales, const float* g_rotations, const float* g_colors,
+                        const float* g_opacities, float* g_raw, float* g_depth_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -601,6 +601,39 @@ def render_fourier(positions, scales, rotations, colors, opacities, camera, widt
 
 
 # --------------------------------------------------------------------------
+# On-disk formats: GaussianCloud::save_ply / load_ply (src/core/renderer/renderer.cpp:649-793)
+# PARITY UNPINNED for the .ply transforms: the C++ reference needs GLM / Kompute (absent here) and has no
+# test vectors; this is a restatement of the published 3DGS parameterisation as the reference writes it.
+# The .bin format IS pinned: tests/golden/cloud_97.bin is written by the reference's own
+# save_gaussians_to_binary (DR:1485-1497) and read back by its load_gaussians_from_binary (DR:1461-1482).
+# --------------------------------------------------------------------------
+SH_C0 = np.float32(0.28209479177387814)
+
+
+def ply_decode_rows(rows: np.ndarray) -> Dict[str, np.ndarray]:
+    """14-float .ply rows -> activated parameters.  renderer.cpp:754-785."""
+    r = np.asarray(rows, np.float32)
+    return dict(positions=r[:, 0:3].copy(),
+                scales=np.exp(r[:, 3:6]).astype(np.float32),                                    # :766-768
+                rotations=r[:, 6:10].copy(),
+                colors=np.clip(r[:, 10:13] * SH_C0 + np.float32(0.5), 0.0, 1.0).astype(np.float32),   # :777-779
+                opacities=(1.0 / (1.0 + np.exp(-r[:, 13]))).astype(np.float32))                 # :782
+
+
+def ply_encode_rows(g: Dict[str, np.ndarray]) -> np.ndarray:
+    """Activated parameters -> 14-float .ply rows.  renderer.cpp:679-717."""
+    n = g["positions"].shape[0]
+    r = np.zeros((n, 14), np.float32)
+    r[:, 0:3] = g["positions"]
+    r[:, 3:6] = np.log(np.maximum(g["scales"], np.float32(1e-7)))                               # :687-689
+    r[:, 6:10] = g["rotations"]
+    r[:, 10:13] = (g["colors"] - np.float32(0.5)) / SH_C0                                       # :708-710
+    op = g["opacities"].astype(np.float32)
+    r[:, 13] = np.log(op / np.maximum(np.float32(1.0) - op, np.float32(1e-7)))                  # :716
+    return r
+
+
+# --------------------------------------------------------------------------
 def synthetic_cloud(n: int, seed: int = 0, s_lo: float = 0.005, s_hi: float = 0.03,
                     phase_hi: float = 1.0) -> Dict[str, torch.Tensor]:
     """The seeded synthetic Gaussian cloud every config uses (fp32, CPU)."""

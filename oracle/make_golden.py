@@ -432,7 +432,19 @@ def fx_fourier():
     run_fourier("fourier_1500_96x80", inp, cam, W, H, (0.2, 0.1, 0.05), note="FourierGaussianRenderer")
 
 
-FIXTURES = dict(dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
+def fx_bin():
+    """.bin fixture written and read back by the reference's own functions (DR:1461-1497)."""
+    inp = fo.synthetic_cloud(97, seed=23)
+    path = os.path.join(GOLD, "cloud_97.bin")
+    dr.save_gaussians_to_binary(path, {k: inp[k] for k in GRAD_NAMES})
+    back = dr.load_gaussians_from_binary(path)
+    np.savez_compressed(os.path.join(GOLD, "cloud_97_loaded.npz"), **{k: v.numpy() for k, v in back.items()})
+    for k in GRAD_NAMES:
+        assert np.array_equal(back[k].numpy(), inp[k].numpy()), k
+    print(f"cloud_97.bin: {os.path.getsize(path)} bytes, reference save -> load round trip exact")
+
+
+FIXTURES = dict(bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
                 asm=fx_asm, c1=fx_c1)
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../fresnel_b200/csrc/frb_math.h"
+#include "../fresnel_b200/csrc/frb_head.h"
 
 static FrbCamera cam_from(const float* c) {
     FrbCamera cam;
@@ -69,6 +70,31 @@ void shim_project_bwd_mode(int n, const float* p, const float* s, const float* q
         const float* g = g2d + 6 * i;
         frb_project_bwd_one(p + 3 * i, s + 3 * i, q + 4 * i, cam, g[0], g[1], g[2], g[3], g[4], g[5],
                             gp + 3 * i, gs + 3 * i, gq + 4 * i, mode);
+    }
+}
+
+// decoder output head (frb_head.h): out = [pos 3 | scl 3 | rot 4 | col 3 | opa 1] per Gaussian
+void shim_head_fwd(int n, const float* raw, const float* base_xyz, const float* edge, float esf, float eob,
+                   float* out) {
+    for (int i = 0; i < n; ++i) {
+        FrbHeadOut o;
+        frb_head_fwd_one(raw + 16 * i, base_xyz[3 * i], base_xyz[3 * i + 1], base_xyz[3 * i + 2], edge[i], esf, eob, o);
+        float* f = out + 14 * i;
+        for (int k = 0; k < 3; ++k) { f[k] = o.pos[k]; f[3 + k] = o.scl[k]; f[10 + k] = o.col[k]; }
+        for (int k = 0; k < 4; ++k) f[6 + k] = o.rot[k];
+        f[13] = o.opa;
+    }
+}
+
+void shim_head_bwd(int n, const float* raw, const float* edge, float esf, float eob, const float* g_out,
+                   float* g_raw, float* g_z) {
+    for (int i = 0; i < n; ++i) {
+        FrbHeadOut g;
+        const float* f = g_out + 14 * i;
+        for (int k = 0; k < 3; ++k) { g.pos[k] = f[k]; g.scl[k] = f[3 + k]; g.col[k] = f[10 + k]; }
+        for (int k = 0; k < 4; ++k) g.rot[k] = f[6 + k];
+        g.opa = f[13];
+        frb_head_bwd_one(raw + 16 * i, edge[i], esf, eob, g, g_raw + 16 * i, g_z[i]);
     }
 }
 }

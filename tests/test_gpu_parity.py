@@ -469,3 +469,35 @@ def test_dense_and_fourier_fresh_scenes_vs_live_oracle():
     assert rel(img.detach().cpu(), io.detach()) < IMG_TOL
     for k in GRAD_NAMES:
         assert rel(L[k].grad.cpu(), Lo[k].grad) < GRAD_TOL, ("fourier", k)
+
+
+def test_fused_decoder_head_matches_torch_ops():
+    """csrc/head.cu against the PyTorch restatement of the reference head on the same weights: all five outputs,
+    the MLP / depth_offset gradients, with and without the stochastic subset (same multinomial draw)."""
+    from fresnel_b200.training import PatchGaussianDecoder
+    torch.manual_seed(0)
+    model = PatchGaussianDecoder(384, 4).to(dev()).eval()        # eval: dropout off, both paths deterministic
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(3, 384, 37, 37, generator=g).to(dev())
+    depth = torch.rand(3, 1, 64, 64, generator=g).to(dev())
+    weights = {k: torch.randn(s, generator=g).to(dev()) for k, s in
+               (("positions", 3), ("scales", 3), ("rotations", 4), ("colors", 3), ("opacities", 1))}
+    for k_sel in (None, 300):
+        res = {}
+        for fused in (True, False):
+            model.fused_head = fused
+            model.zero_grad(set_to_none=True)
+            gen = torch.Generator(device=dev()).manual_seed(5)
+            out = model(feats, depth, stochastic_k=k_sel, generator=gen)
+            loss = sum((out[k] * (weights[k] if k != "opacities" else weights[k][0])).sum() for k in weights)
+            loss.backward()
+            res[fused] = ({k: v.detach().clone() for k, v in out.items()},
+                          {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+        n_expect = 300 if k_sel else 37 * 37 * 4
+        for k in weights:
+            a, b = res[True][0][k], res[False][0][k]
+            assert a.shape == b.shape and a.shape[1] == n_expect
+            assert rel(a.cpu(), b.cpu()) < 1e-5, (k_sel, k)
+        for n in res[True][1]:
+            assert rel(res[True][1][n].cpu(), res[False][1][n].cpu()) < 1e-4, (k_sel, n)
+    model.fused_head = True
