@@ -345,6 +345,153 @@ def run_train(args, rank, world, local, full):
 
 
 # --------------------------------------------------------------------------------------
+# Third workload (BASELINE.json configs[4]): multi-pose optimisation of ONE cloud, ASM renderer, one view per rank
+#   python bench.py --workload multiview [--gpus N via torchrun] [--mv-gaussians 1000000 --mv-res 1024]
+# --------------------------------------------------------------------------------------
+MV_METRIC = "multi-pose novel-view training views/sec (1M Gaussians, 1024x1024, ASMWaveFieldRenderer)"
+MV_WAVELENGTHS = (0.0635, 0.05, 0.041)
+
+
+def mv_cloud(n, seed=0):
+    import math
+    g = torch.Generator().manual_seed(seed)
+    return dict(positions=torch.randn(n, 3, generator=g) * 0.5,             # centred: the cameras orbit the origin
+                scales=torch.rand(n, 3, generator=g) * (0.012 - 0.002) + 0.002,
+                rotations=torch.randn(n, 4, generator=g), colors=torch.rand(n, 3, generator=g),
+                opacities=torch.rand(n, generator=g) * 0.8 + 0.1,
+                phases=torch.rand(n, generator=g) * 2 * math.pi)
+
+
+def mv_workload_name(n, res):
+    return (f"multi-pose novel-view optimisation of one cloud: {n} Gaussians at {res}x{res}, ASMWaveFieldRenderer "
+            "(16 planes, depth_range (0.1, 4.0), RGB wavelengths), look-at poses az = 45 deg * rank, one view per "
+            "GPU per step, per-Gaussian gradients summed over ranks (BASELINE configs[4])")
+
+
+def run_multiview(args, rank, world, local):
+    import math
+    import torch.distributed as dist
+    import fresnel_b200
+    from fresnel_b200 import _lib
+    from fresnel_b200.training import MultiViewTrainer
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    n, res = args.mv_gaussians, args.mv_res
+    ren = fresnel_b200.ASMWaveFieldRenderer(res, res, depth_range=(0.1, 4.0)).to(dev)
+    wl = torch.tensor(MV_WAVELENGTHS)
+    trainer = MultiViewTrainer(ren, mv_cloud(n), dev, lr=1e-4, with_phases=True, render_kwargs=dict(wavelengths_rgb=wl))
+    cam = fresnel_b200.create_camera_from_pose(0.0, math.radians(45.0 * rank), res)
+    g = torch.Generator().manual_seed(100 + rank)
+    target_host = torch.rand(3, res, res, generator=g).pin_memory()
+    target = target_host.to(dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_resident():
+        trainer.step(cam, target)
+
+    def step_e2e():
+        loss_host.copy_(trainer.step(cam, target_host.to(dev, non_blocking=True)), non_blocking=True)
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.frb_launch_count()
+    barrier()
+    ms = timed(step_resident, args.steps)
+    barrier()
+    launches = L.frb_launch_count() - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, tot_e2e = tot.tolist()
+    if rank == 0:
+        print(json.dumps({
+            "metric": MV_METRIC, "value": world * args.steps / (tot_ms * 1e-3), "unit": "views/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": mv_workload_name(n, res), "gradient_floats_exchanged": trainer.params.flat.numel(),
+                       "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
+                       "parallelism": f"dp{world}: one view per rank, cloud replicated, one flat NCCL all-reduce "
+                                      "(SUM) of the per-Gaussian gradients per step, replicated fused Adam"},
+            "e2e": {"value": world * args.steps / (tot_e2e * 1e-3), "unit": "views/s",
+                    "h2d_bytes_per_step": target_host.numel() * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": tot_e2e / args.steps},
+            "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms)},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_multiview_reference(args, rank):
+    """CPU arm: the oracle ASM renderer, forward + backward of one view, at two bounded sample sizes; the cost is
+    fitted as a + b * n (the FFT part does not depend on n) and extrapolated to the full cloud."""
+    if rank != 0:
+        return
+    import math
+    from oracle import fresnel_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, res = args.mv_gaussians, args.mv_res
+    cloud = mv_cloud(n)
+    cam = fo.camera_from_pose(0.0, 0.0, res)
+    wl = torch.tensor(MV_WAVELENGTHS)
+    target = torch.rand(3, res, res, generator=torch.Generator().manual_seed(100))
+
+    def one(n_s):
+        Lc = {k: cloud[k][:n_s].clone().requires_grad_(True) for k in cloud}
+        t0 = time.perf_counter()
+        img, _ = fo.render_asm(Lc["positions"], Lc["scales"], Lc["rotations"], Lc["colors"], Lc["opacities"], cam,
+                               res, res, Lc["phases"], wl, depth_range=(0.1, 4.0))
+        torch.nn.functional.l1_loss(img, target).backward()
+        return time.perf_counter() - t0
+
+    one(50)
+    n1, n2 = 200, 800
+    t1, t2 = one(n1), one(n2)
+    b = max((t2 - t1) / (n2 - n1), 0.0)
+    a = max(t1 - b * n1, 0.0)
+    est = a + b * n
+    value = 1.0 / est
+    sample = (f"oracle port of ASMWaveFieldRenderer, one view at {res}x{res}: {n1} Gaussians {t1:.2f} s, {n2} Gaussians "
+              f"{t2:.2f} s, fitted {a:.2f} s + {b * 1e3:.3f} ms per Gaussian, extrapolated to {n}")
+    print(json.dumps({
+        "impl": "reference", "metric": MV_METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": 1,
+        "warmup": 1, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": mv_workload_name(n, res)},
+        "cpu_baseline": {"value": value, "unit": "views/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 def main():
@@ -355,7 +502,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--t-eps", type=float, default=None)
-    ap.add_argument("--workload", default="render", choices=["render", "train", "train_full"])
+    ap.add_argument("--workload", default="render", choices=["render", "train", "train_full", "multiview"])
+    ap.add_argument("--mv-gaussians", type=int, default=1_000_000)
+    ap.add_argument("--mv-res", type=int, default=1024)
     ap.add_argument("--no-cuda-graph", action="store_true", help="train workloads: run the step eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -363,6 +512,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "multiview":
+        if args.impl == "reference":
+            run_multiview_reference(args, rank)
+        else:
+            run_multiview(args, rank, world, local)
+        return
     if args.workload != "render":
         full = args.workload == "train_full"
         if args.impl == "reference":

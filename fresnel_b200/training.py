@@ -328,3 +328,88 @@ class DecoderTrainer:
         allreduce_gradients(self.model.parameters())
         self._update()
         return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-pose novel-view optimisation of ONE Gaussian cloud (BASELINE.json configs[4]):
+# the cloud is replicated on every rank, rank r renders view r of the step's pose set, the per-Gaussian
+# gradients (14 or 15 floats per Gaussian: 56-60 MB at one million) are summed over the ranks, and every rank
+# applies the same Adam update.  The pose loop this shards is train_gaussian_decoder.py:1084-1095 / 1209-1223.
+# ------------------------------------------------------------------------------------------------
+PARAM_NAMES = ("positions", "scales", "rotations", "colors", "opacities")
+
+
+class FlatGaussianParams:
+    """The optimised cloud as ONE flat fp32 buffer with per-tensor views (and the same for its gradient), so that
+    the gradient exchange is a single collective over contiguous memory and Adam is a single fused update."""
+
+    WIDTHS = {"positions": 3, "scales": 3, "rotations": 4, "colors": 3, "opacities": 1, "phases": 1}
+
+    def __init__(self, cloud: Dict[str, torch.Tensor], device, with_phases: bool = False):
+        names = PARAM_NAMES + (("phases",) if with_phases else ())
+        n = cloud["positions"].shape[0]
+        self.n, self.names = n, names
+        # rotations first: they are read and written as float4 and must stay 16-byte aligned for every n
+        order = ("rotations",) + tuple(k for k in names if k != "rotations")
+        total = sum(self.WIDTHS[k] for k in names) * n
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device, requires_grad=True)
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.slices, off = {}, 0
+        for k in order:
+            w = self.WIDTHS[k]
+            self.slices[k] = (off, off + w * n, (n, w) if w > 1 else (n,))
+            off += w * n
+        with torch.no_grad():
+            for k in names:
+                a, b, shape = self.slices[k]
+                self.flat[a:b].view(shape).copy_(cloud[k].to(device=device, dtype=torch.float32))
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        """Differentiable views into the flat parameter (autograd writes their gradients into ``flat.grad``)."""
+        return {k: self.flat[a:b].view(shape) for k, (a, b, shape) in self.slices.items()}
+
+
+def allreduce_flat(grad: torch.Tensor, group=None, average: bool = False) -> int:
+    """SUM (or mean) of one contiguous gradient buffer over the ranks: one NCCL all-reduce.  No-op outside a
+    process group.  Returns the number of elements reduced."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        grad.div_(world)
+    return grad.numel()
+
+
+class MultiViewTrainer:
+    """One optimisation step of a replicated Gaussian cloud against this rank's target view.
+
+    ``renderer``: any fresnel_b200 renderer module; ``phases`` are optimised too when the renderer needs them
+    (WaveFieldRenderer / ASMWaveFieldRenderer).  The loss is the mean L1 between the rendered and the target
+    image; gradients are SUMMED over ranks (the loss of the step is the sum over its views)."""
+
+    def __init__(self, renderer: nn.Module, cloud: Dict[str, torch.Tensor], device, lr: float = 1e-3,
+                 with_phases: bool = False, render_kwargs: Optional[dict] = None):
+        self.renderer = renderer
+        self.params = FlatGaussianParams(cloud, device, with_phases=with_phases)
+        self.with_phases = with_phases
+        self.render_kwargs = render_kwargs or {}
+        self.optimizer = torch.optim.Adam([self.params.flat], lr=lr, fused=self.params.flat.is_cuda)
+
+    def step(self, camera, target: torch.Tensor) -> torch.Tensor:
+        p = self.params
+        p.flat.grad.zero_()
+        v = p.views()
+        kw = dict(self.render_kwargs)
+        if self.with_phases:
+            kw["phases"] = v["phases"]
+        image = self.renderer(v["positions"], v["scales"], v["rotations"], v["colors"], v["opacities"], camera, **kw)
+        if isinstance(image, tuple):
+            image = image[0]
+        loss = F.l1_loss(image, target)
+        loss.backward()
+        allreduce_flat(p.flat.grad)
+        self.optimizer.step()
+        return loss.detach()

@@ -100,3 +100,72 @@ def test_gradient_allreduce_world_size_2_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == 6 * 5 + 5 + 5 * 2 + 2
+
+
+class _ToyRenderer(torch.nn.Module):
+    """CPU stand-in with the renderer call signature (the CUDA renderers have no CPU path): a smooth function
+    of all five parameter tensors and the camera's fx."""
+    width = height = 8
+
+    def forward(self, positions, scales, rotations, colors, opacities, camera, phases=None):
+        s = (positions.sum() + scales.pow(2).sum() + rotations.sum() * 0.5 + (colors * opacities[:, None]).sum())
+        if phases is not None:
+            s = s + phases.sin().sum()
+        return (s * camera.fx).expand(3, 8, 8) * torch.linspace(0.1, 1.0, 8)
+
+
+def _mv_worker(rank, world, port, q):
+    from fresnel_b200.training import MultiViewTrainer
+    from fresnel_b200.camera import Camera
+    from oracle import fresnel_oracle as fo
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cloud = fo.synthetic_cloud(33, seed=3)
+        cams = [Camera(1.0 + r, 1.0, 4, 4, 8, 8) for r in range(world)]
+        target = torch.zeros(3, 8, 8)
+        tr = MultiViewTrainer(_ToyRenderer(), cloud, "cpu", lr=1e-2, with_phases=True)
+        before = tr.params.flat.detach().clone()
+        tr.step(cams[rank], target)
+        g_sum = tr.params.flat.grad.clone()
+        # single-process reference: the sum of every view's gradient
+        ref = MultiViewTrainer(_ToyRenderer(), cloud, "cpu", lr=1e-2, with_phases=True)
+        want = torch.zeros_like(g_sum)
+        for r in range(world):
+            ref.params.flat.grad.zero_()
+            v = ref.params.views()
+            img = ref.renderer(v["positions"], v["scales"], v["rotations"], v["colors"], v["opacities"], cams[r],
+                               phases=v["phases"])
+            torch.nn.functional.l1_loss(img, target).backward()
+            want += ref.params.flat.grad
+        ok = torch.allclose(g_sum, want, atol=1e-6) and not torch.equal(before, tr.params.flat.detach())
+        q.put((rank, bool(ok), tr.params.flat.detach().sum().item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multiview_flat_gradient_allreduce_world_size_2_gloo():
+    """C5 exchange step: every rank ends with the SUM of all views' per-Gaussian gradients and the same update."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_mv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert abs(res[0][2] - res[1][2]) < 1e-4          # replicas stay identical after the step
+
+
+def test_flat_params_layout_and_alignment():
+    from fresnel_b200.training import FlatGaussianParams
+    from oracle import fresnel_oracle as fo
+    cloud = fo.synthetic_cloud(37, seed=1)            # odd n
+    fp = FlatGaussianParams(cloud, "cpu", with_phases=True)
+    v = fp.views()
+    for k in ("positions", "scales", "rotations", "colors", "opacities", "phases"):
+        assert torch.equal(v[k].detach(), cloud[k])
+    assert fp.slices["rotations"][0] == 0             # float4-typed tensor first: 16-byte aligned for every n
+    assert fp.flat.numel() == 15 * 37
