@@ -69,7 +69,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t_mark = index, None, [], None
 
     def start(self):
         try:
@@ -83,7 +83,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout_s=8.0):
+        """nvidia-smi needs up to seconds to start on an 8-GPU box: block until it has delivered one sample, so
+        that short timed regions are still covered by the samples taken around them under the same load."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout_s:
+            time.sleep(0.02)
+        self.t_mark = time.time()            # samples from here on are "during the timed region"
 
     def stop(self):
         if self.proc is None:
@@ -96,7 +104,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if self.t_mark is not None and t >= self.t_mark]
+        for ln in (inside or [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -304,13 +313,15 @@ def run_train(args, rank, world, local, full):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     step_e2e()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
     l0 = L.frb_launch_count()
     barrier()
     ms = timed(step_resident, args.steps)
@@ -414,13 +425,15 @@ def run_multiview(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     step_e2e()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
     l0 = L.frb_launch_count()
     barrier()
     ms = timed(step_resident, args.steps)
@@ -593,20 +606,53 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # started before the warm-up: see ClockSampler.wait_first
     for _ in range(args.warmup):
         step_resident()
     for _ in range(max(2, args.warmup // 2)):
         step_e2e()
     barrier()
 
-    sampler = ClockSampler(local)
+    # The resident step is replayed from a CUDA graph (one launch per frame instead of ~20 kernel launches and
+    # ~0.4 ms of Python): the forward is sync-free and allocation-static, so module call + autograd backward
+    # capture as they are.  --no-cuda-graph times the eager calls.
+    kernels_per_step = None
+    step_timed = step_resident
+    if not args.no_cuda_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_resident()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        k0 = L.frb_launch_count()
+        with torch.cuda.graph(graph):
+            step_resident()
+        kernels_per_step = int(L.frb_launch_count() - k0)
+
+        def step_graph():
+            graph.replay()
+        step_timed = step_graph
+        for _ in range(3):
+            step_timed()
+        torch.cuda.synchronize()
+
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
     launches0 = L.frb_launch_count()
     barrier()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_timed, args.steps)
     barrier()
     launches = L.frb_launch_count() - launches0
+    if kernels_per_step is not None:         # replayed kernels do not pass through the library's launch counter
+        launches = kernels_per_step * args.steps
+    for _ in range(3):                       # the caching allocator re-settles after the graph took its pool
+        step_e2e()
+    barrier()
     ms_e2e = timed(step_e2e, args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -661,7 +707,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"single-view render fwd+bwd, {N} Gaussians, {RES}x{RES} (BASELINE configs[1]); "
                                    "one view per rank",
-                       "tile_instances": M, "t_eps": t_eps,
+                       "tile_instances": M, "t_eps": t_eps, "cuda_graph": not args.no_cuda_graph,
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
                        "e2e": "HostRenderSession: pinned host buffers, copy streams overlap the kernels inside a step, "
                               "no cross-step prefetch",
@@ -670,7 +716,7 @@ def main():
                     "ms_per_step": tot_e2e_ms / args.steps},
             "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms),
                         "e2e_min": min(ms_e2e), "e2e_median": statistics.median(ms_e2e), "e2e_max": max(ms_e2e),
-                        "host_enqueue": enqueue.get("step_resident")},
+                        "host_enqueue": enqueue.get(step_timed.__name__)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
