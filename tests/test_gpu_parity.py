@@ -501,3 +501,84 @@ def test_fused_decoder_head_matches_torch_ops():
         for n in res[True][1]:
             assert rel(res[True][1][n].cpu(), res[False][1][n].cpu()) < 1e-4, (k_sel, n)
     model.fused_head = True
+
+
+def test_full_size_properties_config4_phase_blending():
+    """BASELINE.json configs[3] (200k Gaussians, 512x512, phase blending): size-independent properties.
+    (a) input permutation leaves the image bit-identical when depths are tie-free (the running phase makes the
+    result order dependent, so this pins the sort); (b) phase_amplitude = 0 reduces to the plain compositor;
+    (c) the backward pass is linear in the upstream gradients; (d) outputs in range."""
+    W = H = 512
+    N = 200_000
+    inp = fo.synthetic_cloud(N, seed=0)
+    cam = fo.default_camera(W)
+    g = torch.Generator().manual_seed(1)
+    gi, gd = (torch.rand(3, H, W, generator=g) * 2 - 1), (torch.rand(H, W, generator=g) * 2 - 1)
+    img0, dep0, a0, gr0 = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.25)
+    assert np.isfinite(img0).all() and np.isfinite(dep0).all() and a0.min() >= 0 and a0.max() <= 1 + 1e-6
+    for k in GRAD_NAMES + ("phases",):
+        assert np.isfinite(gr0[k]).all(), k
+    perm = torch.randperm(N, generator=g)
+    pin = {k: v[perm] for k, v in inp.items()}
+    img1, dep1, _, gr1 = render_gpu(pin, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.25)
+    db = fo.depth_bits(fo.project(inp["positions"], inp["scales"], inp["rotations"], cam)["depth"])
+    if len(np.unique(db)) == N:
+        assert np.array_equal(img0, img1) and np.array_equal(dep0, dep1)
+    else:
+        assert rel(img1, img0) < 1e-4 and rel(dep1, dep0) < 1e-4
+    for k in GRAD_NAMES + ("phases",):
+        assert rel(gr1[k], gr0[k][perm.numpy()]) < 1e-4, k
+    # amplitude 0: interference factor is exactly 1 -> the plain tile compositor (sum form vs product form of T)
+    imgz, depz, _, grz = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.0)
+    imgp, depp, _, grp = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd)
+    assert rel(imgz, imgp) < IMG_TOL and rel(depz, depp) < IMG_TOL
+    for k in GRAD_NAMES:
+        assert rel(grz[k], grp[k]) < GRAD_TOL, k
+    _, _, _, gr3 = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi * 2.0, gd * -0.5, phases=True, amp=0.25)
+    _, _, _, gra = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd * 0.0, phases=True, amp=0.25)
+    _, _, _, grb = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi * 0.0, gd, phases=True, amp=0.25)
+    for k in GRAD_NAMES + ("phases",):
+        assert rel(gr3[k], 2.0 * gra[k] - 0.5 * grb[k]) < 5e-5, k
+
+
+def test_full_size_properties_config5_asm():
+    """BASELINE.json configs[4] per-view shape (1M Gaussians, 1024x1024, ASM, look-at pose): (a) the image is
+    finite, in range and NOT the background; (b) input permutation changes the image only by summation order;
+    (c) directional derivative: the gradient predicts the change of a random linear functional of the image
+    under a small colour perturbation (colours enter the field linearly before the normalisation)."""
+    W = H = 1024
+    N = 1_000_000
+    d = dev()
+    inp = fo.synthetic_cloud(N, seed=0, s_lo=0.002, s_hi=0.012, phase_hi=2 * math.pi)
+    inp["positions"][:, 2] += 2.0
+    cam = fresnel_b200.create_camera_from_pose(0.0, math.radians(45.0), W)
+    ren = fresnel_b200.ASMWaveFieldRenderer(W, H, depth_range=(0.1, 4.0)).to(d)
+    wl = torch.tensor([0.0635, 0.05, 0.041])
+    g = torch.Generator().manual_seed(2)
+    gi = (torch.rand(3, H, W, generator=g) * 2 - 1).to(d)
+
+    def run(cloud, grad=False):
+        L = {k: v.to(d).requires_grad_(grad) for k, v in cloud.items()}
+        img = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, phases=L["phases"],
+                  wavelengths_rgb=wl)
+        if grad:
+            (img * gi).sum().backward()
+        return img.detach(), L
+
+    img0, L0 = run(inp, grad=True)
+    assert bool(torch.isfinite(img0).all()) and float(img0.min()) >= 0 and float(img0.max()) <= 1
+    assert float(img0.max()) > 0.05
+    for k in GRAD_NAMES + ("phases",):
+        assert bool(torch.isfinite(L0[k].grad).all()), k
+    perm = torch.randperm(N, generator=g)
+    img1, _ = run({k: v[perm] for k, v in inp.items()})
+    assert rel(img1.cpu(), img0.cpu()) < 1e-4
+    dcol = (torch.rand(N, 3, generator=g) - 0.5)
+    eps = 1e-3
+    plus = dict(inp); plus["colors"] = inp["colors"] + eps * dcol
+    minus = dict(inp); minus["colors"] = inp["colors"] - eps * dcol
+    fp = float((run(plus)[0] * gi).sum())
+    fm = float((run(minus)[0] * gi).sum())
+    fd = (fp - fm) / (2 * eps)
+    an = float((L0["colors"].grad.cpu() * dcol).sum())
+    assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd), 1.0), (fd, an)
