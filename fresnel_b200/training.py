@@ -202,6 +202,49 @@ def reconstruction_losses(rendered, target, rendered_depth=None, target_depth=No
     return loss
 
 
+class _ReconLossFn(torch.autograd.Function):
+    """``reconstruction_losses`` as four CUDA kernels (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight):
+        L = _lib.lib()
+        dev = rendered.device
+        rendered, target = rendered.contiguous().float(), target.contiguous().float()
+        has_depth = rendered_depth is not None and target_depth is not None
+        rd = rendered_depth.contiguous().float() if has_depth else None
+        td = target_depth.contiguous().float() if has_depth else None
+        stats = torch.empty(L.frb_recon_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(L.frb_recon_loss_fwd(rendered.numel(), rd.numel() if has_depth else 0, _ptr(rendered), _ptr(target),
+                                        _ptr(rd), _ptr(td), float(rgb_weight), float(depth_weight), _ptr(stats),
+                                        _ptr(loss), _stream()), "frb_recon_loss_fwd")
+        ctx.weights = (float(rgb_weight), float(depth_weight))
+        ctx.has_depth = has_depth
+        ctx.save_for_backward(rendered, target, rd if has_depth else rendered.new_empty(0),
+                              td if has_depth else rendered.new_empty(0), stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        rendered, target, rd, td, stats = ctx.saved_tensors
+        L = _lib.lib()
+        has_depth = ctx.has_depth
+        g_loss = g_loss.contiguous().float()
+        g_rendered = torch.empty_like(rendered)
+        g_rd = torch.empty_like(rd) if has_depth else None
+        _lib.check(L.frb_recon_loss_bwd(rendered.numel(), rd.numel() if has_depth else 0, _ptr(rendered), _ptr(target),
+                                        _ptr(rd) if has_depth else None, _ptr(td) if has_depth else None,
+                                        ctx.weights[0], ctx.weights[1], _ptr(stats), _ptr(g_loss), _ptr(g_rendered),
+                                        _ptr(g_rd), _stream()), "frb_recon_loss_bwd")
+        return g_rendered, None, g_rd, None, None, None
+
+
+def reconstruction_losses_fused(rendered, target, rendered_depth=None, target_depth=None, rgb_weight: float = 1.0,
+                                depth_weight: float = 0.1) -> torch.Tensor:
+    """Same value and gradients as ``reconstruction_losses`` for CUDA tensors, in four kernel launches."""
+    return _ReconLossFn.apply(rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight)
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: Optional[int] = None,
                         group=None) -> int:
     """Average gradients over ranks with ONE flat all-reduce (the decoder is 2.5 MB: a single bucket;
@@ -252,6 +295,7 @@ class DecoderTrainer:
         self.camera = Camera(0.8 * render_size, 0.8 * render_size, render_size / 2, render_size / 2, render_size,
                              render_size)                       # train_gaussian_decoder.py:1910-1917
         self.cuda_graph = cuda_graph
+        self.fused_loss = True          # CUDA: csrc/loss.cu; False keeps the PyTorch ops (A/B checks)
         self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay,
                                            capturable=cuda_graph)
         self.stochastic_k = stochastic_k
@@ -279,7 +323,8 @@ class DecoderTrainer:
         if images.shape[-1] != R:
             images = F.interpolate(images, size=(R, R), mode="bilinear", align_corners=False)
         target_depth = F.interpolate(depth, size=(R, R), mode="bilinear", align_corners=False).squeeze(1)
-        loss = reconstruction_losses(rendered, images, rendered_depth, target_depth)
+        loss_fn = reconstruction_losses_fused if (rendered.is_cuda and self.fused_loss) else reconstruction_losses
+        loss = loss_fn(rendered, images, rendered_depth, target_depth)
         loss.backward()
         return loss.detach()
 

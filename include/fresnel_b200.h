@@ -283,6 +283,21 @@ int frb_decode_head_bwd(int B, int H, int W, int K, const float* raw, const floa
                         const float* g_scales, const float* g_rotations, const float* g_colors,
                         const float* g_opacities, float* g_raw, float* g_depth_offset, void* stream);
 
+/* ---- reconstruction loss front-end -------------------------------------------
+ * compute_losses, scripts/training/train_gaussian_decoder.py:838-930 (L1 RGB + normalised-depth L1; the SSIM /
+ * LPIPS terms need packages that are absent and are dropped by the reference too).
+ * rendered, target: n_rgb floats; rendered_depth, target_depth: n_pix floats (both NULL = no depth term);
+ * stats: frb_recon_loss_workspace_bytes() of device scratch shared by forward and backward; loss, g_loss:
+ * device scalars. */
+size_t frb_recon_loss_workspace_bytes(void);
+int frb_recon_loss_fwd(long long n_rgb, long long n_pix, const float* rendered, const float* target,
+                       const float* rendered_depth, const float* target_depth, float rgb_weight,
+                       float depth_weight, void* stats, float* loss, void* stream);
+int frb_recon_loss_bwd(long long n_rgb, long long n_pix, const float* rendered, const float* target,
+                       const float* rendered_depth, const float* target_depth, float rgb_weight,
+                       float depth_weight, const void* stats, const float* g_loss, float* g_rendered,
+                       float* g_rendered_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

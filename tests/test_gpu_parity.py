@@ -582,3 +582,33 @@ def test_full_size_properties_config5_asm():
     fd = (fp - fm) / (2 * eps)
     an = float((L0["colors"].grad.cpu() * dcol).sum())
     assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd), 1.0), (fd, an)
+
+
+def test_fused_reconstruction_loss_matches_torch_ops():
+    """csrc/loss.cu against the PyTorch restatement of compute_losses (value and both gradients), with and
+    without the depth term, including a constant depth map (std below the 1e-4 clamp: gated gradient)."""
+    from fresnel_b200.training import reconstruction_losses, reconstruction_losses_fused
+    g = torch.Generator().manual_seed(4)
+    B, R = 5, 72
+    target = torch.rand(B, 3, R, R, generator=g).to(dev())
+    tdep = torch.rand(B, R, R, generator=g).to(dev())
+    for case in ("both", "rgb_only", "flat_depth"):
+        r0 = torch.rand(B, 3, R, R, generator=g)
+        d0 = torch.rand(B, R, R, generator=g) * 3 if case != "flat_depth" else torch.full((B, R, R), 0.7)
+        res = []
+        for fn in (reconstruction_losses_fused, reconstruction_losses):
+            r = r0.clone().to(dev()).requires_grad_(True)
+            d = d0.clone().to(dev()).requires_grad_(True)
+            loss = fn(r, target, None if case == "rgb_only" else d, None if case == "rgb_only" else tdep) * 3.0
+            loss.backward()
+            res.append((float(loss), r.grad.cpu(), None if d.grad is None else d.grad.cpu()))
+        assert abs(res[0][0] - res[1][0]) <= 2e-6 * max(abs(res[1][0]), 1.0), case
+        assert rel(res[0][1], res[1][1]) < 1e-5, case
+        if case == "both":
+            assert rel(res[0][2], res[1][2]) < 1e-4, (case, rel(res[0][2], res[1][2]))
+        elif case == "flat_depth":
+            # constant depth: (rd - mean) is pure rounding noise divided by the 1e-4 clamp, so sign(a - b) may flip
+            # where |b| < 1e-3 and one flip changes that element by its full magnitude: compare element-wise
+            a, b = res[0][2].numpy(), res[1][2].numpy()
+            bad = np.abs(a - b) > 1e-4 * np.abs(b).max()
+            assert bad.mean() < 5e-3, (case, float(bad.mean()))
