@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .camera import camera_vector
-from .renderer import RECORD_FLOATS, _call, _check_inputs, _ptr, _stream
+from .renderer import RECORD_FLOATS, _call, _check_inputs, _ptr, _stream, empty_cloud_result
 from .wave import WC_FLOATS, _prepare_wave_bins, _project_backward
 
 MODE_FOURIER = 2
@@ -122,6 +122,9 @@ class FourierGaussianRenderer(nn.Module):
         t = _check_inputs(positions=positions.reshape(B * N, 3), scales=scales.reshape(B * N, 3),
                           rotations=rotations.reshape(B * N, 4), colors=colors.reshape(B * N, 3),
                           opacities=opacities.reshape(B * N))
+        if N == 0:                                                                     # DR:1651-1657
+            return empty_cloud_result(B, self.height, self.width, self._background_host, t["positions"], t["colors"],
+                                      t["opacities"])[0]
         cam_vecs = np.ascontiguousarray(np.stack([camera_vector(c, self.width, self.height) for c in cams]),
                                         np.float32)
         cfg = (cam_vecs, B, int(self.width), int(self.height), 32000.0, self._background_host)

@@ -209,6 +209,17 @@ def worst_case_instances(n: int, n_views: int, width: int, height: int, max_radi
     return n * min(tiles_x * tiles_y, span * span)
 
 
+def empty_cloud_result(n_views: int, height: int, width: int, background, positions, colors, opacities):
+    """N = 0: the reference's "no visible Gaussians" branch (DR:545-552) - the background image and zero depth /
+    alpha, tied to the inputs by the same zero-valued anchor so that ``backward()`` runs."""
+    dev = positions.device
+    anchor = (colors.sum() + opacities.sum() + positions.sum()) * 0.0
+    bg = torch.as_tensor(np.asarray(background, np.float32), device=dev)
+    image = bg.view(1, 3, 1, 1).expand(n_views, 3, height, width) + anchor
+    zeros = torch.zeros(n_views, height, width, dtype=torch.float32, device=dev)
+    return image, zeros + anchor, zeros.clone()
+
+
 FUSED_CALLS = True      # one C call per pass (frb_tile_render_fwd / _bwd); False = stage by stage
 
 
@@ -382,6 +393,8 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
                       rotations=rotations.reshape(B * N, 4), colors=colors.reshape(B * N, 3),
                       opacities=opacities.reshape(B * N),
                       phases=None if phases is None else phases.reshape(B * N))
+    if N == 0:
+        return empty_cloud_result(B, int(height), int(width), background, t["positions"], t["colors"], t["opacities"])
     cam_vecs = np.ascontiguousarray(np.stack([camera_vector(c, width, height) for c in cameras]), np.float32)
     cfg = (cam_vecs, B, int(width), int(height), np.asarray(background, np.float32), float(max_radius),
            float(t_eps), float(phase_amplitude), int(mode))

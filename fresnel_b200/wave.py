@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import _lib
 from .camera import camera_vector
-from .renderer import RECORD_FLOATS, TILE, _call, _check_inputs, _ptr, _stream, build_bins
+from .renderer import RECORD_FLOATS, TILE, _call, _check_inputs, _ptr, _stream, build_bins, empty_cloud_result
 
 WC_FLOATS = 8
 
@@ -214,6 +214,10 @@ class WaveFieldRenderer(nn.Module):
         B = positions.shape[0]
         cams = list(cameras) if isinstance(cameras, (list, tuple)) else [cameras] * B
         t = _flatten_views(positions, scales, rotations, colors, opacities, phases)
+        if positions.shape[1] == 0:                                                    # DR:801-808
+            img, dep, _ = empty_cloud_result(B, self.height, self.width, self.background.tolist(), t["positions"],
+                                             t["colors"], t["opacities"])
+            return img, dep
         cam_vecs = np.stack([camera_vector(c, self.width, self.height) for c in cams])
         cfg = (cam_vecs, B, int(self.width), int(self.height), float(self.max_radius),
                tuple(float(x) for x in self.background.tolist()))
@@ -269,6 +273,9 @@ class ASMWaveFieldRenderer(nn.Module):
         B = positions.shape[0]
         cams = list(cameras) if isinstance(cameras, (list, tuple)) else [cameras] * B
         t = _flatten_views(positions, scales, rotations, colors, opacities, phases)
+        if positions.shape[1] == 0:                                                    # DR:1208-1212
+            return empty_cloud_result(B, self.height, self.width, self._background_host, t["positions"], t["colors"],
+                                      t["opacities"])[0]
         cam_vecs = np.stack([camera_vector(c, self.width, self.height) for c in cams])
         if wavelengths_rgb is None:
             wl = np.full(3, self.wavelength, np.float32)
