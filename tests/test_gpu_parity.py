@@ -607,8 +607,10 @@ def test_fused_reconstruction_loss_matches_torch_ops():
         if case == "both":
             assert rel(res[0][2], res[1][2]) < 1e-4, (case, rel(res[0][2], res[1][2]))
         elif case == "flat_depth":
-            # constant depth: (rd - mean) is pure rounding noise divided by the 1e-4 clamp, so sign(a - b) may flip
-            # where |b| < 1e-3 and one flip changes that element by its full magnitude: compare element-wise
+            # constant depth: torch's fp32 mean of 0.7 is off by one ulp, and that rounding noise divided by the 1e-4
+            # clamp shifts every normalised value by 1e-3: sign(a - b) flips where |b| < 1e-3 (that element changes
+            # by its full magnitude) and the sum of signs S1 moves by ~1e-3 of n (every element moves by that
+            # fraction).  The kernel takes the mean in fp64 (exactly 0.7): compare with that noise floor.
             a, b = res[0][2].numpy(), res[1][2].numpy()
-            bad = np.abs(a - b) > 1e-4 * np.abs(b).max()
+            bad = np.abs(a - b) > 5e-3 * np.abs(b).max()
             assert bad.mean() < 5e-3, (case, float(bad.mean()))
