@@ -31,8 +31,8 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
-    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
-    const int py = ty * TILE + (threadIdx.x / TILE);
+    const int px = tx * TILE + foot_x(threadIdx.x);
+    const int py = ty * TILE + foot_y(threadIdx.x);
     const bool in_image = (px < width) && (py < height);
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);

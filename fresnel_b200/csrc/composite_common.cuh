@@ -16,6 +16,12 @@ constexpr uint32_t NULL_RECT_HI = 0x80008000u;  // x1 = y1 = 0
 constexpr int STATE_GATE_SHIFT = 28;            // state_n = entries consumed | clamp gates << 28
 constexpr int STATE_N_MASK = (1 << STATE_GATE_SHIFT) - 1;
 
+// Pixel owned by a thread: a warp covers an 8x4 block of the 16x16 tile, not a 16x2 strip - fewer list entries have
+// a rectangle that touches the squarer block, so fewer warps execute the per-pixel body for an entry.
+constexpr int FOOT_W = 8, FOOT_H = 4;
+__device__ __forceinline__ int foot_x(int tid) { return ((tid >> 5) % (TILE / FOOT_W)) * FOOT_W + ((tid & 31) % FOOT_W); }
+__device__ __forceinline__ int foot_y(int tid) { return ((tid >> 5) / (TILE / FOOT_W)) * FOOT_H + ((tid & 31) / FOOT_W); }
+
 struct __align__(16) StageBuf {
     float4 rec[BATCH * 3];
 };

@@ -63,8 +63,8 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
-    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
-    const int py = ty * TILE + (threadIdx.x / TILE);
+    const int px = tx * TILE + foot_x(threadIdx.x);
+    const int py = ty * TILE + foot_y(threadIdx.x);
     const bool in_image = (px < width) && (py < height);
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
@@ -195,15 +195,16 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
-    const int px = tx * TILE + (threadIdx.x & (TILE - 1));
-    const int py = ty * TILE + (threadIdx.x / TILE);
+    const int px = tx * TILE + foot_x(threadIdx.x);
+    const int py = ty * TILE + foot_y(threadIdx.x);
     const bool in_image = (px < width) && (py < height);
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
     const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float wbx = (float)(tx * TILE), wby = (float)(ty * TILE + 2 * warp);   // warp's pixel block origin
-    const int wx0 = tx * TILE, wx1 = wx0 + TILE, wy0 = ty * TILE + 2 * warp, wy1 = wy0 + 2;
+    const int wx0 = tx * TILE + (warp % (TILE / FOOT_W)) * FOOT_W, wy0 = ty * TILE + (warp / (TILE / FOOT_W)) * FOOT_H;
+    const int wx1 = wx0 + FOOT_W, wy1 = wy0 + FOOT_H;
+    const float wbx = (float)wx0, wby = (float)wy0;                              // warp's pixel block origin
     const int2 range = ranges[tile];
 
     float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
@@ -264,7 +265,7 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         frb_mbar_wait(&sm.full_bar[s], (visit / PH_STAGES) & 1);
         const float4* rec = sm.rec[s];
 
-        // ---- candidates: lane l tests record l against this warp's 16x2 pixels ----
+        // ---- candidates: lane l tests record l against this warp's pixel block ----
         uint32_t cand;
         {
             bool ok = false;
@@ -367,8 +368,8 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 for (int p = 0; p < 32; ++p) {
                     const float2 cd = row[p];
                     const float4 gpix = pc[p];
-                    const float dx = ux + (float)(p & 15);
-                    const float dy = uy + (float)(p >> 4);
+                    const float dx = ux + (float)(p % FOOT_W);
+                    const float dy = uy + (float)(p / FOOT_W);
                     const float gda = cd.y;
                     d_r = fmaf(cd.x, gpix.x, d_r);
                     d_g = fmaf(cd.x, gpix.y, d_g);
