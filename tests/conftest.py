@@ -25,12 +25,12 @@ def golden():
 
 @pytest.fixture(scope="session")
 def host_shim():
-    """g++ build of tests/host_shim.cpp: frb_math.h (the kernels' arithmetic) on the CPU."""
+    """g++ build of tests/host_shim.cpp: frb_math.h / frb_head.h (the kernels' arithmetic) on the CPU."""
     import ctypes
     so = os.path.join(ROOT, "tests", "_host_shim.so")
     src = os.path.join(ROOT, "tests", "host_shim.cpp")
-    hdr = os.path.join(ROOT, "fresnel_b200", "csrc", "frb_math.h")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "fresnel_b200", "csrc", h) for h in ("frb_math.h", "frb_head.h")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so])
     return ctypes.CDLL(so)
 
