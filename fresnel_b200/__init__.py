@@ -11,10 +11,11 @@ from .camera import Camera, camera_vector, create_camera_from_pose
 from .renderer import DEFAULT_T_EPS, DifferentiableGaussianRenderer, TileBasedRenderer, build_bins, render_views
 from .wave import ASMWaveFieldRenderer, WaveFieldRenderer
 from .fourier import FourierGaussianRenderer
+from .simple import SimplifiedRenderer
 from .io import (load_gaussians_from_binary, load_gaussians_from_ply, save_gaussians_to_binary,
                  save_gaussians_to_ply)
 
 __all__ = ["Camera", "camera_vector", "create_camera_from_pose", "TileBasedRenderer", "WaveFieldRenderer",
-           "ASMWaveFieldRenderer", "DifferentiableGaussianRenderer", "FourierGaussianRenderer", "render_views",
+           "ASMWaveFieldRenderer", "DifferentiableGaussianRenderer", "FourierGaussianRenderer", "SimplifiedRenderer", "render_views",
            "build_bins", "DEFAULT_T_EPS", "load_gaussians_from_binary", "save_gaussians_to_binary",
            "load_gaussians_from_ply", "save_gaussians_to_ply"]

@@ -63,6 +63,13 @@ _SIGNATURES = {
     "frb_recon_loss_workspace_bytes": (c_size_t, []),
     "frb_recon_loss_fwd": (c_int, [ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float, c_float, P, P, P]),
     "frb_recon_loss_bwd": (c_int, [ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float, c_float, P, P, P, P, P]),
+    "frb_composite_fwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, c_float, c_float, P, P, P, P, P, P, P]),
+    "frb_composite_bwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P, P,
+                                      P]),
+    "frb_simple_project_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P]),
+    "frb_simple_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_simple_depth_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "frb_simple_depth_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "frb_asm_assign_planes": (c_int, [c_int, P, c_int, P, P, P]),
     "frb_asm_splat_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "frb_asm_propagate_fwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P]),

@@ -21,7 +21,8 @@ namespace {
 
 __global__ void __launch_bounds__(CTA_THREADS)
 composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
-                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records, float3 bg, float t_eps, float* __restrict__ image,
+                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records, float3 bg, float t_eps,
+                     float alpha_max, float* __restrict__ image,
                      float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
                      int* __restrict__ state_n) {
     __shared__ StageBuf stage[STAGES];
@@ -88,7 +89,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                         float dx = fpx - r0.x, dy = fpy - r0.y;
                         float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                         float a = frb_ex2(power) * r1.y;
-                        a = fminf(fmaxf(a, 0.0f), FRB_ALPHA_MAX);
+                        a = fminf(fmaxf(a, 0.0f), alpha_max);
                         float c = a * T;
                         cr = fmaf(c, r2.x, cr);
                         cg = fmaf(c, r2.y, cg);
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2)
 composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
                      const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
                      const uint32_t* __restrict__ sorted_gids,
-                     float3 bg, const float* __restrict__ state_T,
+                     float3 bg, float alpha_max, const float* __restrict__ state_T,
                      const int* __restrict__ state_n, const float* __restrict__ g_image,
                      const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
                      float* __restrict__ grad2d) {
@@ -296,7 +297,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                 const float g = frb_ex2(power);
                 const float araw = g * r1.y;
-                p.a = fminf(fmaxf(araw, 0.0f), FRB_ALPHA_MAX);
+                p.a = fminf(fmaxf(araw, 0.0f), alpha_max);
                 p.gpass = (p.a == araw) ? g : 0.0f;           // g, or 0 behind the clamp gate 0 <= g*o <= 0.99
                 p.inv_om = frb_rcp(1.0f - p.a);
                 p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
@@ -472,6 +473,18 @@ extern "C" int frb_composite_fwd_sched(int n_views, int width, int height, const
                                  float phase_amplitude, const float* background_host, float t_eps,
                                  float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
                                  float* ckpt, void* stream) {
+    return frb_composite_fwd_cap(n_views, width, height, tile_order, ranges, sorted_records, sorted_phases,
+                                 phase_amplitude, background_host, t_eps, FRB_ALPHA_MAX, image, depth, alpha, state_T,
+                                 state_n, ckpt, stream);
+}
+
+extern "C" int frb_composite_fwd_cap(int n_views, int width, int height, const int32_t* tile_order,
+                                 const int32_t* ranges, const float* sorted_records, const float* sorted_phases,
+                                 float phase_amplitude, const float* background_host, float t_eps, float alpha_max,
+                                 float* image, float* depth, float* alpha, float* state_T, int32_t* state_n,
+                                 float* ckpt, void* stream) {
+    if (!(alpha_max > 0.0f && alpha_max < 1.0f)) return FRB_E_INVALID;   // the backward divides by 1 - alpha
+    if (sorted_phases && alpha_max != FRB_ALPHA_MAX) return FRB_E_INVALID;
     int rc = check_image_args(n_views, width, height);
     if (rc) return rc;
     if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n) return FRB_E_INVALID;
@@ -484,7 +497,7 @@ extern "C" int frb_composite_fwd_sched(int n_views, int width, int height, const
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     composite_fwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps,
-        image, depth, alpha, state_T, state_n);
+        alpha_max, image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -509,6 +522,20 @@ extern "C" int frb_composite_bwd_sched(int n_views, int width, int height, const
                                  const int32_t* state_n, const float* ckpt, const float* g_image,
                                  const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
                                  void* stream) {
+    return frb_composite_bwd_cap(n_views, width, height, tile_order, ranges, sorted_records, sorted_gids,
+                                 sorted_phases, phase_amplitude, background_host, FRB_ALPHA_MAX, state_T, state_n, ckpt,
+                                 g_image, g_depth, g_alpha, grad2d, g_phases, stream);
+}
+
+extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const int32_t* tile_order,
+                                 const int32_t* ranges, const float* sorted_records, const uint32_t* sorted_gids,
+                                 const float* sorted_phases, float phase_amplitude,
+                                 const float* background_host, float alpha_max, const float* state_T,
+                                 const int32_t* state_n, const float* ckpt, const float* g_image,
+                                 const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
+                                 void* stream) {
+    if (!(alpha_max > 0.0f && alpha_max < 1.0f)) return FRB_E_INVALID;
+    if (sorted_phases && alpha_max != FRB_ALPHA_MAX) return FRB_E_INVALID;
     int rc = check_image_args(n_views, width, height);
     if (rc) return rc;
     if (!ranges || !background_host || !state_T || !state_n || !g_image || !grad2d) return FRB_E_INVALID;
@@ -528,7 +555,7 @@ extern "C" int frb_composite_bwd_sched(int n_views, int width, int height, const
     }
     composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
-        bg, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+        bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

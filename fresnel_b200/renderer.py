@@ -110,7 +110,7 @@ class TileBins:
 def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
                width: int, height: int, max_radius: float, phases=None, keep_debug: bool = False,
                sort: bool = True, low_word_fn=None, presort: bool = True, sync: Optional[bool] = None,
-               mode: int = 0) -> TileBins:
+               mode: int = 0, project_fn=None) -> TileBins:
     """Projection + binning: everything up to the per-tile sorted record lists.
 
     Sequences frb_project_fwd -> frb_depth_order -> frb_tile_offsets -> frb_bin_emit ->
@@ -126,7 +126,8 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     replaces the depth bits as the low key word (ASM: the depth-plane index).  ``presort=False`` skips
     the depth order altogether (order-free renderers): lists come out in ascending Gaussian index.
     ``mode``: projection mode of frb_project_fwd_mode (0 tile, 1 dense, 2 Fourier); modes 1 and 2 have
-    image-sized rectangles, so they always take the exact-size (sync) path.
+    image-sized rectangles, so they always take the exact-size (sync) path.  ``project_fn(bins, cam)`` replaces the
+    projection kernel (it must fill ``bins.records``, ``bins.depth_bits`` and ``bins.touched``).
     """
     L = _lib.lib()
     dev = positions.device
@@ -142,9 +143,12 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     b.depth_bits = torch.empty(n, **i32)
     b.touched = torch.empty(n, **i32)
     b.rects = torch.empty(n, 4, **i32) if keep_debug else None
-    _call("frb_project_fwd", L.frb_project_fwd_mode, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations),
-          _ptr(colors), _ptr(opacities), cam.ctypes.data, float(max_radius), int(mode), _ptr(b.records),
-          _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
+    if project_fn is not None:
+        project_fn(b, cam)
+    else:
+        _call("frb_project_fwd", L.frb_project_fwd_mode, n, n_views, _ptr(positions), _ptr(scales), _ptr(rotations),
+              _ptr(colors), _ptr(opacities), cam.ctypes.data, float(max_radius), int(mode), _ptr(b.records),
+              _ptr(b.rects), _ptr(b.depth_bits), _ptr(b.touched), None, st)
 
     if low_word_fn is not None:
         b.depth_bits = low_word_fn(b)
@@ -161,7 +165,7 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     worst = n * min(tiles_x * tiles_y, span * span)
     if sync is None:
         sync = (keep_debug or not sort or phases is not None or low_word_fn is not None or not presort
-                or mode != 0 or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES)
+                or mode != 0 or project_fn is not None or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES)
     if sync:
         m = int(offsets[n].item())      # the one host sync of the forward pass
         m_dev = None

@@ -246,6 +246,37 @@ int frb_asm_propagate_bwd(int n_views, int width, int height, int n_planes,
                           const float* total, const uint32_t* rmax_bits, const float* g_image, float* red,
                           float* g_total, float* d_fields, void* stream);
 
+/* The plain compositor with the alpha clamp as an argument (0 < alpha_max < 1; the tile renderer's is 0.99,
+ * differentiable_renderer.py:647).  Used by SimplifiedRenderer, whose clamp(alpha, 0, 1) (:1430) becomes
+ * alpha_max = 1 - 2^-24.  sorted_phases must be NULL unless alpha_max is the default. */
+int frb_composite_fwd_cap(int n_views, int width, int height, const int32_t* tile_order, const int32_t* ranges,
+                          const float* sorted_records, const float* sorted_phases, float phase_amplitude,
+                          const float* background_host, float t_eps, float alpha_max, float* image, float* depth,
+                          float* alpha, float* state_T, int32_t* state_n, float* ckpt, void* stream);
+int frb_composite_bwd_cap(int n_views, int width, int height, const int32_t* tile_order, const int32_t* ranges,
+                          const float* sorted_records, const uint32_t* sorted_gids, const float* sorted_phases,
+                          float phase_amplitude, const float* background_host, float alpha_max, const float* state_T,
+                          const int32_t* state_n, const float* ckpt, const float* g_image, const float* g_depth,
+                          const float* g_alpha, float* grad2d, float* g_phases, void* stream);
+
+/* ---- SimplifiedRenderer (differentiable_renderer.py:1347-1458): point splats with an integer radius -------
+ * frb_simple_project_fwd: Camera.project (:54-85), radius = min(int(max(mean(scale) fx / depth, 1)), 20),
+ * rectangle [int(u) - r, int(u) + r + 1) x [int(v) - r, int(v) + r + 1) clipped to the image, isotropic conic
+ * exp(-d^2 / (2 max(r/2, 1)^2)); same record layout as frb_project_fwd.
+ * frb_simple_depth_fwd / bwd: depth map = depth of the front-most list entry with alpha > 0.1 (:1438-1442);
+ * hit: [views, H, W] Gaussian ids (-1 = none).  frb_simple_project_bwd: chain (u, v, depth) -> positions;
+ * scales and rotations receive no gradient in the reference (radius goes through .item()). */
+int frb_simple_project_fwd(int n, int n_views, const float* positions, const float* scales, const float* colors,
+                           const float* opacities, const float* camera_host, float* records, uint32_t* depth_bits,
+                           uint32_t* tiles_touched, void* stream);
+int frb_simple_project_bwd(int n, int n_views, const float* positions, const float* camera_host,
+                           const float* grad2d, float* g_positions, float* g_colors, float* g_opacities,
+                           void* stream);
+int frb_simple_depth_fwd(int n_views, int width, int height, const int32_t* ranges, const float* sorted_records,
+                         const uint32_t* sorted_gids, float* depth, int32_t* hit, void* stream);
+int frb_simple_depth_bwd(int n_views, int width, int height, const int32_t* hit, const float* g_depth,
+                         float* grad2d, void* stream);
+
 /* ---- FourierGaussianRenderer epilogue (differentiable_renderer.py:1740-1753) and its backward ----
  * accum: [view][8][H][W] as written by frb_wave_splat_fwd on FRB_MODE_FOURIER records with zero phases
  * (planes 0..2 = channel sums); mx_key: n_views words (global maximum, order-preserving key);

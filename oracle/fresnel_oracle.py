@@ -601,6 +601,65 @@ def render_fourier(positions, scales, rotations, colors, opacities, camera, widt
 
 
 # --------------------------------------------------------------------------
+# SimplifiedRenderer.forward (DR:1347-1458) and Camera.project (DR:54-85)
+# --------------------------------------------------------------------------
+def camera_project(positions, camera) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Pixel coordinates and depth of N points, fixed elementwise fp32 order.  DR:54-85."""
+    V = camera.view_matrix.to(torch.float32)
+    x, y, z = positions[:, 0], positions[:, 1], positions[:, 2]
+
+    def row(i):
+        return ((V[i, 0] * x + V[i, 1] * y) + V[i, 2] * z) + V[i, 3]
+
+    pcx, pcy, pcz = row(0), row(1), row(2)
+    zs = torch.clamp(pcz.abs(), min=camera.near) * torch.sign(pcz + 1e-8)     # DR:78
+    u = (_f32(camera.fx) * pcx) / (-zs) + _f32(camera.cx)                      # DR:81
+    v = (_f32(camera.fy) * (-pcy)) / (-zs) + _f32(camera.cy)                   # DR:82
+    return u, v, -zs                                                           # DR:85
+
+
+def simplified_radius(scales_i: torch.Tensor, fx: float, d: torch.Tensor) -> int:
+    """DR:1402-1403, the reference's own expression (Python float product, fp32 tensor division)."""
+    return min(int(max(scales_i.mean().item() * fx / d, 1)), 20)
+
+
+def render_simplified(positions, scales, colors, opacities, camera, width, height,
+                      background=(0.0, 0.0, 0.0)) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Point splats with an integer radius, blended back to front with "over".  DR:1369-1458.
+    Returns (image (3,H,W), depth (H,W) with inf replaced by 0 as DR:1453 does)."""
+    H, W = height, width
+    bg = torch.tensor(background, dtype=torch.float32)
+    u, v, depth = camera_project(positions, camera)
+    order = torch.argsort(depth, descending=True, stable=True)                # DR:1381 (stable)
+    image = bg.view(3, 1, 1).expand(3, H, W).clone()
+    depth_map = torch.full((H, W), float("inf"))
+    for i in order.tolist():                                                  # DR:1394
+        d = depth[i]
+        if d <= 0:                                                            # DR:1398
+            continue
+        radius = simplified_radius(scales[i], camera.fx, d.detach())
+        x_int, y_int = int(u[i].item()), int(v[i].item())                     # DR:1406
+        x0, x1 = max(0, x_int - radius), min(W, x_int + radius + 1)
+        y0, y1 = max(0, y_int - radius), min(H, y_int + radius + 1)
+        if x0 >= x1 or y0 >= y1:                                              # DR:1412
+            continue
+        yy, xx = torch.meshgrid(torch.arange(y0, y1, dtype=torch.float32),
+                                torch.arange(x0, x1, dtype=torch.float32), indexing="ij")
+        dist_sq = (xx - u[i]) ** 2 + (yy - v[i]) ** 2                         # DR:1423
+        weight = torch.exp(-dist_sq / (2 * max(radius / 2, 1) ** 2))          # DR:1424
+        alpha = torch.clamp(weight * opacities[i], 0, 1)                      # DR:1427-1428
+        new = alpha.unsqueeze(0) * colors[i].view(3, 1, 1) + (1 - alpha).unsqueeze(0) * image[:, y0:y1, x0:x1]
+        image = torch.cat([image[:, :y0], torch.cat([image[:, y0:y1, :x0], new, image[:, y0:y1, x1:]], 2),
+                           image[:, y1:]], 1)                                 # DR:1431-1436 without in-place writes
+        dm = depth_map[y0:y1, x0:x1]
+        dnew = torch.where(alpha > 0.1, torch.minimum(dm, d.expand(y1 - y0, x1 - x0)), dm)   # DR:1438-1442
+        depth_map = torch.cat([depth_map[:y0], torch.cat([depth_map[y0:y1, :x0], dnew, depth_map[y0:y1, x1:]], 1),
+                               depth_map[y1:]], 0)
+    depth_map = torch.where(depth_map == float("inf"), torch.zeros_like(depth_map), depth_map)   # DR:1453
+    return image, depth_map
+
+
+# --------------------------------------------------------------------------
 # On-disk formats: GaussianCloud::save_ply / load_ply (src/core/renderer/renderer.cpp:649-793)
 # PARITY UNPINNED for the .ply transforms: the C++ reference needs GLM / Kompute (absent here) and has no
 # test vectors; this is a restatement of the published 3DGS parameterisation as the reference writes it.

@@ -307,6 +307,36 @@ def run_fourier(name, inp, cam, W, H, bg, note=""):
     print(f"{name}: fourier ok, oracle-vs-ref img {e_img:.2e} grads {worst:.2e}, img max {float(img_r.max()):.3f}")
 
 
+def run_simplified(name, inp, cam, W, H, bg, note=""):
+    """SimplifiedRenderer (DR:1347-1458): reference forward + backward, oracle cross-check."""
+    gi, gd = upstream(H, W)
+    rc = ref_camera(cam)
+    ren = dr.SimplifiedRenderer(W, H, background=bg)
+    names = ("positions", "colors", "opacities")
+    # the reference cannot backpropagate through this renderer (in-place slice writes on tensors saved for the
+    # backward: "modified by an inplace operation", as on the phase-blending path): forward from the reference,
+    # gradients from the oracle's functional restatement of the same expressions
+    with torch.no_grad():
+        img_r, dep_r = ren(inp["positions"], inp["scales"], inp["rotations"], inp["colors"], inp["opacities"], rc,
+                           return_depth=True)
+    Lo = leafs(inp, names)
+    img_o, dep_o = fo.render_simplified(Lo["positions"], Lo["scales"], Lo["colors"], Lo["opacities"], cam, W, H,
+                                        background=bg)
+    ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
+    e_img, e_dep = rel(img_o.detach(), img_r.detach()), rel(dep_o.detach(), dep_r.detach())
+    assert e_img < 1e-5 and e_dep < 1e-6, (name, e_img, e_dep)
+    out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), image=img_r.detach().numpy(),
+               depth=dep_r.detach().numpy(), gimage=gi.numpy(), gdepth=gd.numpy(), grad_source="oracle_functional",
+               note=note)
+    for k in GRAD_NAMES + ("phases",):
+        out["in_" + k] = inp[k].numpy()
+    for k in names:
+        out["grad_" + k] = Lo[k].grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: simplified ok, oracle-vs-ref img {e_img:.2e} depth {e_dep:.2e} [gradients: oracle], "
+          f"depth pixels hit {int((dep_r > 0).sum())}")
+
+
 # ---------------------------------------------------------------- fixtures
 def redraw_std(inp, idx, g):
     n = idx.numel()
@@ -444,7 +474,35 @@ def fx_bin():
     print(f"cloud_97.bin: {os.path.getsize(path)} bytes, reference save -> load round trip exact")
 
 
-FIXTURES = dict(bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
+def fx_simplified():
+    """SimplifiedRenderer: rotated look-at camera; Gaussians whose integer radius or integer pixel centre could
+    flip under a one-ulp change are re-drawn (the fixture pins the arithmetic, not one rounding)."""
+    W, H = 96, 80
+    cam = fo.camera_from_pose(math.radians(15.0), math.radians(-30.0), W)
+    cam.cx, cam.cy, cam.width, cam.height = W / 2, H / 2, W, H
+    inp = fo.synthetic_cloud(900, seed=29, s_lo=0.02, s_hi=0.25)
+    inp["positions"][:, 2] += 2.0
+    inp["positions"][:40] *= 3.0                       # some behind the camera / outside the image
+    g = torch.Generator().manual_seed(30)
+    for _ in range(20):
+        u, v, d = fo.camera_project(inp["positions"], cam)
+        q = inp["scales"].mean(dim=1) * cam.fx / d
+        def near_int(t, tol):
+            return (t - t.round()).abs() < tol
+        fragile = (d > 0) & (near_int(q, 2e-3) | near_int(u, 2e-3) | near_int(v, 2e-3) | (d.abs() < 0.02))
+        idx = torch.nonzero(fragile).squeeze(1)
+        if idx.numel() == 0:
+            break
+        p = torch.randn(idx.numel(), 3, generator=g) * 0.5
+        inp["positions"][idx] = p
+        inp["scales"][idx] = torch.rand(idx.numel(), 3, generator=g) * 0.23 + 0.02
+    else:
+        raise RuntimeError("could not settle the simplified fixture")
+    run_simplified("simplified_900_96x80", inp, cam, W, H, (0.1, 0.15, 0.2),
+                   note="SimplifiedRenderer, look-at camera el 15 az -30; gradients for positions, colours, opacities")
+
+
+FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
                 asm=fx_asm, c1=fx_c1)
 
 if __name__ == "__main__":

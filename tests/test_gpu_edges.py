@@ -28,6 +28,7 @@ def renderers(W, H, bg):
         "asm": (fresnel_b200.ASMWaveFieldRenderer(W, H, background=bg).to(dev()), True),
         "dense": (fresnel_b200.DifferentiableGaussianRenderer(W, H, background=bg), False),
         "fourier": (fresnel_b200.FourierGaussianRenderer(W, H, background=bg).to(dev()), False),
+        "simple": (fresnel_b200.SimplifiedRenderer(W, H, background=bg), False),
     }
 
 
@@ -40,7 +41,7 @@ def call(ren, needs_phase, L, cam):
     return ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, **kw)
 
 
-@pytest.mark.parametrize("kind", ["tile", "phase", "wave", "asm", "dense", "fourier"])
+@pytest.mark.parametrize("kind", ["tile", "phase", "wave", "asm", "dense", "fourier", "simple"])
 def test_empty_cloud_renders_the_background(kind):
     """N = 0 (the reference's 'no visible Gaussians' branch, DR:545-552): background image, backward runs."""
     W, H, bg = 40, 24, (0.25, 0.5, 0.75)

@@ -614,3 +614,24 @@ def test_fused_reconstruction_loss_matches_torch_ops():
             a, b = res[0][2].numpy(), res[1][2].numpy()
             bad = np.abs(a - b) > 5e-3 * np.abs(b).max()
             assert bad.mean() < 5e-3, (case, float(bad.mean()))
+
+
+def test_simplified_renderer_matches_reference_golden(golden):
+    """SimplifiedRenderer: image and depth map against the reference's own output, gradients
+    (positions, colours, opacities) against the oracle's functional restatement; scales / rotations get none."""
+    z = golden("simplified_900_96x80")
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = {k: v.to(dev()).requires_grad_(True) for k, v in golden_inputs(z).items()}
+    ren = fresnel_b200.SimplifiedRenderer(W, H, background=tuple(float(x) for x in z["bg"]))
+    img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, return_depth=True)
+    assert img.shape == (3, H, W) and dep.shape == (H, W)
+    assert rel(img.detach().cpu(), z["image"]) < IMG_TOL
+    assert np.array_equal(dep.detach().cpu().numpy() > 0, z["depth"] > 0)          # same pixels hit
+    assert rel(dep.detach().cpu(), z["depth"]) < 1e-6
+    torch.autograd.backward((img, dep), (torch.from_numpy(z["gimage"]).to(dev()), torch.from_numpy(z["gdepth"]).to(dev())))
+    for k in ("positions", "colors", "opacities"):
+        assert rel(L[k].grad.cpu(), z["grad_" + k]) < GRAD_TOL, (k, rel(L[k].grad.cpu(), z["grad_" + k]))
+    assert L["scales"].grad is None and L["rotations"].grad is None
+    img2 = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam)
+    assert torch.equal(img2, img)

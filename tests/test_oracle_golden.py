@@ -116,3 +116,17 @@ def test_oracle_fourier_matches_reference(golden):
     for k in GRAD_NAMES:
         g = L[k].grad if L[k].grad is not None else torch.zeros_like(L[k])
         assert rel(g, z["grad_" + k]) < 1e-4, k
+
+
+def test_oracle_simplified_matches_reference(golden):
+    """SimplifiedRenderer restatement against the reference's own forward output (the reference cannot
+    backpropagate through this renderer: in-place writes on saved tensors)."""
+    z = golden("simplified_900_96x80")
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = golden_inputs(z)
+    with torch.no_grad():
+        img, dep = fo.render_simplified(L["positions"], L["scales"], L["colors"], L["opacities"], cam, W, H,
+                                        background=tuple(z["bg"]))
+    assert rel(img, z["image"]) < 1e-5
+    assert rel(dep, z["depth"]) < 1e-6
