@@ -396,7 +396,8 @@ def run_multiview(args, rank, world, local):
     n, res = args.mv_gaussians, args.mv_res
     ren = fresnel_b200.ASMWaveFieldRenderer(res, res, depth_range=(0.1, 4.0)).to(dev)
     wl = torch.tensor(MV_WAVELENGTHS)
-    trainer = MultiViewTrainer(ren, mv_cloud(n), dev, lr=1e-4, with_phases=True, render_kwargs=dict(wavelengths_rgb=wl))
+    trainer = MultiViewTrainer(ren, mv_cloud(n), dev, lr=1e-4, with_phases=True, render_kwargs=dict(wavelengths_rgb=wl),
+                               exchange=args.exchange)
     cam = fresnel_b200.create_camera_from_pose(0.0, math.radians(45.0 * rank), res)
     g = torch.Generator().manual_seed(100 + rank)
     target_host = torch.rand(3, res, res, generator=g).pin_memory()
@@ -453,8 +454,13 @@ def run_multiview(args, rank, world, local):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": mv_workload_name(n, res), "gradient_floats_exchanged": trainer.params.flat.numel(),
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
-                       "parallelism": f"dp{world}: one view per rank, cloud replicated, one flat NCCL all-reduce "
-                                      "(SUM) of the per-Gaussian gradients per step, replicated fused Adam"},
+                       "exchange": args.exchange,
+                       "parallelism": (f"dp{world}: one view per rank, cloud replicated, per-Gaussian gradients "
+                                       "summed and Adam applied by ONE kernel per rank over NVLink peer memory "
+                                       "(reduce-scatter by peer loads, sharded Adam, all-gather by peer stores; "
+                                       "csrc/exchange.cu)" if args.exchange == "peer" else
+                                       f"dp{world}: one view per rank, cloud replicated, one flat NCCL all-reduce "
+                                       "(SUM) of the per-Gaussian gradients per step, replicated fused Adam")},
             "e2e": {"value": world * args.steps / (tot_e2e * 1e-3), "unit": "views/s",
                     "h2d_bytes_per_step": target_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": tot_e2e / args.steps},
@@ -518,6 +524,8 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_full", "multiview"])
     ap.add_argument("--mv-gaussians", type=int, default=1_000_000)
     ap.add_argument("--mv-res", type=int, default=1024)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multiview: fused peer-memory exchange + Adam kernel, or NCCL all-reduce + torch Adam")
     ap.add_argument("--no-cuda-graph", action="store_true", help="train workloads: run the step eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -583,6 +591,35 @@ def main():
         session.step(cam)
 
     h2d, d2h = session.h2d_bytes, session.d2h_bytes
+
+    # Throughput form of the same call: two HostRenderSession steps in flight, each replayed from one CUDA graph
+    # (fresnel_b200/host.py HostRenderPipeline).  Every step still copies its inputs up and its results down inside
+    # the bracket; step i+1's H2D and step i's D2H overlap the other step's kernels.
+    from fresnel_b200.host import HostRenderPipeline
+    pipe = HostRenderPipeline(ren, N_GAUSS, dev, depth=2)
+    for s_ in pipe.slots:
+        s_.load(host, gi_h, gd_h)
+
+    def timed_pipeline(steps, with_flush=True):
+        """ONE bracket around ``steps`` pipelined steps (they overlap, so per-step brackets would double count).
+        The 256 MiB L2 flush is enqueued on the slot's stream before every step and is INSIDE the bracket."""
+        main = torch.cuda.current_stream()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        for st_ in pipe.streams:
+            st_.wait_event(a)
+        for _ in range(steps):
+            slot = pipe.acquire()
+            if with_flush:
+                with torch.cuda.stream(pipe.streams[slot]):
+                    flush.fill_(1.0)
+            pipe.submit(cam, slot)
+        for st_ in pipe.streams:
+            main.wait_stream(st_)
+        b.record(main)
+        torch.cuda.synchronize()
+        pipe.drain()
+        return a.elapsed_time(b)
 
     enqueue = {}
 
@@ -655,6 +692,12 @@ def main():
     barrier()
     ms_e2e = timed(step_e2e, args.steps)
     barrier()
+    timed_pipeline(4)                        # captures the two slot graphs
+    barrier()
+    pipe_ms = timed_pipeline(args.steps)
+    barrier()
+    pipe_noflush_ms = timed_pipeline(args.steps, with_flush=False)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # per-stage timing for the roofline line (same workload, instrumented pass)
@@ -662,10 +705,10 @@ def main():
         timed(step_resident, args.steps)
     stages = {k: sum(v) / len(v) for k, v in st.summary().items()}
 
-    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sum(ms), sum(ms_e2e), pipe_ms, pipe_noflush_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    tot_ms, tot_e2e_ms = tot.tolist()
+    tot_ms, tot_e2e_ms, tot_pipe_ms, tot_pipe_nf_ms = tot.tolist()
 
     if rank == 0:
         # workload counts for the algorithmic bytes: M = tile instances
@@ -700,7 +743,8 @@ def main():
         achieved = alg[top] / (stages[top] * 1e-3) / 1e9
         frame_bytes = 168 * N + 36 * HW + 96 * M
         value = world * args.steps / (tot_ms * 1e-3)
-        e2e = world * args.steps / (tot_e2e_ms * 1e-3)
+        e2e_serial = world * args.steps / (tot_e2e_ms * 1e-3)
+        e2e = world * args.steps / (tot_pipe_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
@@ -709,11 +753,17 @@ def main():
                                    "one view per rank",
                        "tile_instances": M, "t_eps": t_eps, "cuda_graph": not args.no_cuda_graph,
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
-                       "e2e": "HostRenderSession: pinned host buffers, copy streams overlap the kernels inside a step, "
-                              "no cross-step prefetch",
+                       "e2e": "HostRenderPipeline: HostRenderSession steps (pinned host buffers both ways, H2D of the "
+                              "parameters and upstream gradients, D2H of image, depth and all gradients) replayed from "
+                              "CUDA graphs, two steps in flight on two streams; one bracket over all steps with the "
+                              "256 MiB L2 flush of every step INSIDE it; e2e.serial = one step at a time, eager calls, "
+                              "per-step brackets, flush outside",
                        "parallelism": f"views sharded over {world} rank(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": tot_e2e_ms / args.steps},
+                    "ms_per_step": tot_pipe_ms / args.steps, "pipeline_depth": pipe.depth,
+                    "kernels_per_step": pipe.kernels_per_step,
+                    "value_no_flush": world * args.steps / (tot_pipe_nf_ms * 1e-3),
+                    "serial": {"value": e2e_serial, "ms_per_step": tot_e2e_ms / args.steps}},
             "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms),
                         "e2e_min": min(ms_e2e), "e2e_median": statistics.median(ms_e2e), "e2e_max": max(ms_e2e),
                         "host_enqueue": enqueue.get(step_timed.__name__)},

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "frb_simple_project_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "frb_simple_depth_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
     "frb_simple_depth_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P]),
+    "frb_peer_shard_floats": (ctypes.c_longlong, [c_int, c_int, ctypes.c_longlong]),
+    "frb_peer_adam_step": (c_int, [c_int, c_int, ctypes.c_longlong, P, P, P, P, P, P, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, c_float, c_float, P]),
     "frb_asm_assign_planes": (c_int, [c_int, P, c_int, P, P, P]),
     "frb_asm_splat_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "frb_asm_propagate_fwd": (c_int, [c_int, c_int, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P, P]),

@@ -390,15 +390,28 @@ class FlatGaussianParams:
 
     WIDTHS = {"positions": 3, "scales": 3, "rotations": 4, "colors": 3, "opacities": 1, "phases": 1}
 
-    def __init__(self, cloud: Dict[str, torch.Tensor], device, with_phases: bool = False):
+    @classmethod
+    def total_floats(cls, n: int, with_phases: bool = False) -> int:
+        return (sum(cls.WIDTHS[k] for k in PARAM_NAMES) + (1 if with_phases else 0)) * n
+
+    def __init__(self, cloud: Dict[str, torch.Tensor], device, with_phases: bool = False, storage=None):
+        """``storage``: optional (parameter, gradient) fp32 buffers of ``total_floats`` elements to live in
+        (PeerShardedAdam's peer-mapped buffers); by default two fresh tensors."""
         names = PARAM_NAMES + (("phases",) if with_phases else ())
         n = cloud["positions"].shape[0]
         self.n, self.names = n, names
         # rotations first: they are read and written as float4 and must stay 16-byte aligned for every n
         order = ("rotations",) + tuple(k for k in names if k != "rotations")
         total = sum(self.WIDTHS[k] for k in names) * n
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device, requires_grad=True)
-        self.flat.grad = torch.zeros_like(self.flat)
+        if storage is None:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=device, requires_grad=True)
+            self.flat.grad = torch.zeros_like(self.flat)
+        else:
+            flat, grad = storage
+            if flat.numel() != total or grad.numel() != total or flat.dtype != torch.float32:
+                raise ValueError(f"storage must be two fp32 buffers of {total} elements")
+            self.flat = flat.detach().zero_().requires_grad_(True)
+            self.flat.grad = grad.detach().zero_()
         self.slices, off = {}, 0
         for k in order:
             w = self.WIDTHS[k]
@@ -428,6 +441,70 @@ def allreduce_flat(grad: torch.Tensor, group=None, average: bool = False) -> int
     return grad.numel()
 
 
+class PeerShardedAdam:
+    """Gradient exchange + Adam as ONE kernel per rank over NVLink peer memory (csrc/exchange.cu,
+    ``frb_peer_adam_step``): reduce-scatter by peer loads, Adam on the owned shard (moments sharded: 1/world of
+    the optimiser state per rank), all-gather by peer stores, with the two barriers inside the kernel.
+    Replaces ``allreduce_flat(grad)`` + ``torch.optim.Adam.step()``; same update rule (no weight decay, no
+    amsgrad), gradients SUMMED over ranks (``average=True``: mean).
+
+    ``param`` and ``grad`` are the buffers the parameters and their gradient must live in (hand them to
+    FlatGaussianParams as ``storage``): with a process group they are symmetric-memory allocations mapped into
+    every rank of the node, without one (or world 1) plain tensors.  There is no NCCL call on this path and no
+    fallback: a world > 1 without peer access raises."""
+
+    def __init__(self, n_floats: int, device, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 average: bool = False, group=None):
+        from . import _lib
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise TypeError("PeerShardedAdam needs a CUDA device (fresnel_b200 has no CPU path)")
+        self.n = int(n_floats)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        in_group = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if in_group else 1
+        self.rank = dist.get_rank(group) if in_group else 0
+        self.grad_scale = 1.0 / self.world if average else 1.0
+        f32 = dict(dtype=torch.float32, device=dev)
+        pad = 2 * max(self.world, 1)
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            gname = (group or dist.group.WORLD).group_name
+            self.param = symm_mem.empty(self.n, **f32)
+            self.grad = symm_mem.empty(self.n, **f32)
+            self.signal = symm_mem.empty(pad, dtype=torch.int32, device=dev)
+            self.param.zero_(); self.grad.zero_(); self.signal.zero_()
+            self._handles = [symm_mem.rendezvous(t, gname) for t in (self.grad, self.param, self.signal)]
+            table = [[int(p) for p in h.buffer_ptrs] for h in self._handles]
+            torch.cuda.synchronize(dev)
+            self._handles[2].barrier()               # every pad is zero before anybody signals
+            torch.cuda.synchronize(dev)
+        else:
+            self.param = torch.zeros(self.n, **f32)
+            self.grad = torch.zeros(self.n, **f32)
+            self.signal = torch.zeros(pad, dtype=torch.int32, device=dev)
+            self._handles = []
+            table = [[t.data_ptr()] for t in (self.grad, self.param, self.signal)]
+        self._ptrs = torch.tensor(table, dtype=torch.int64, device=dev)          # (3, world) device addresses
+        shard = int(_lib.lib().frb_peer_shard_floats(self.world, self.rank, self.n))
+        self.shard_floats = shard
+        self.exp_avg = torch.zeros(max(shard, 4), **f32)
+        self.exp_avg_sq = torch.zeros(max(shard, 4), **f32)
+        self.state = torch.zeros(2, dtype=torch.int32, device=dev)               # [ticket, steps taken]
+        self.device = dev
+
+    def step(self) -> None:
+        """Enqueue the fused exchange + update on the current stream.  Every rank must call it once per step."""
+        from . import _lib
+        L = _lib.lib()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        p = self._ptrs
+        _lib.check(L.frb_peer_adam_step(self.world, self.rank, self.n, p[0].data_ptr(), p[1].data_ptr(),
+                                        p[2].data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                        self.state.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                        self.grad_scale, st), "frb_peer_adam_step")
+
+
 class MultiViewTrainer:
     """One optimisation step of a replicated Gaussian cloud against this rank's target view.
 
@@ -436,12 +513,24 @@ class MultiViewTrainer:
     image; gradients are SUMMED over ranks (the loss of the step is the sum over its views)."""
 
     def __init__(self, renderer: nn.Module, cloud: Dict[str, torch.Tensor], device, lr: float = 1e-3,
-                 with_phases: bool = False, render_kwargs: Optional[dict] = None):
+                 with_phases: bool = False, render_kwargs: Optional[dict] = None, exchange: str = "nccl"):
+        """``exchange``: "nccl" = one flat all-reduce + replicated fused Adam (the library form; also the CPU /
+        gloo path of the tests); "peer" = PeerShardedAdam, the fused exchange + update kernel over NVLink peer
+        memory (CUDA only)."""
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
         self.renderer = renderer
-        self.params = FlatGaussianParams(cloud, device, with_phases=with_phases)
+        self.exchange = exchange
         self.with_phases = with_phases
         self.render_kwargs = render_kwargs or {}
-        self.optimizer = torch.optim.Adam([self.params.flat], lr=lr, fused=self.params.flat.is_cuda)
+        if exchange == "peer":
+            n = cloud["positions"].shape[0]
+            self.optimizer = PeerShardedAdam(FlatGaussianParams.total_floats(n, with_phases), device, lr=lr)
+            self.params = FlatGaussianParams(cloud, device, with_phases=with_phases,
+                                             storage=(self.optimizer.param, self.optimizer.grad))
+        else:
+            self.params = FlatGaussianParams(cloud, device, with_phases=with_phases)
+            self.optimizer = torch.optim.Adam([self.params.flat], lr=lr, fused=self.params.flat.is_cuda)
 
     def step(self, camera, target: torch.Tensor) -> torch.Tensor:
         p = self.params
@@ -455,6 +544,9 @@ class MultiViewTrainer:
             image = image[0]
         loss = F.l1_loss(image, target)
         loss.backward()
-        allreduce_flat(p.flat.grad)
-        self.optimizer.step()
+        if self.exchange == "peer":
+            self.optimizer.step()                    # exchange and update in one kernel
+        else:
+            allreduce_flat(p.flat.grad)
+            self.optimizer.step()
         return loss.detach()

@@ -329,6 +329,25 @@ int frb_recon_loss_bwd(long long n_rgb, long long n_pix, const float* rendered, 
                        float depth_weight, const void* stats, const float* g_loss, float* g_rendered,
                        float* g_rendered_depth, void* stream);
 
+/* ---- gradient exchange fused with the optimiser step over NVLink peer memory ---
+ * Multi-view optimisation of one replicated cloud (BASELINE configs[4]): replaces the pair
+ * dist.all_reduce(grad) + torch.optim.Adam.step() that follows loss.backward() in the reference's loop
+ * (scripts/training/train_gaussian_decoder.py:1261-1266) by ONE kernel per rank: entry barrier, reduce-scatter
+ * by peer loads (fixed rank order), Adam on the owned shard (torch.optim.Adam semantics: no weight decay, no
+ * amsgrad; moments sharded), all-gather by peer stores, exit barrier.
+ * grad_ptrs / param_ptrs / signal_ptrs: DEVICE arrays of `world` 64-bit addresses, entry k = rank k's buffer
+ * as mapped into this process (peer-mapped symmetric memory; world = 1: plain local pointers).  Gradient and
+ * parameter buffers hold n_floats fp32 and are 16-byte aligned; a signal pad is 2 * world uint32, zero before
+ * the first step.  exp_avg / exp_avg_sq: frb_peer_shard_floats(world, rank, n_floats) floats each, zero before
+ * the first step.  state: 2 uint32 on this device, zero before the first step ([1] counts the steps taken, so
+ * the arguments never change and the launch replays from a CUDA graph).  The summed gradient is multiplied by
+ * grad_scale (1 = SUM, 1/world = mean).  Every rank must call it once per step; the call returns when enqueued. */
+long long frb_peer_shard_floats(int world, int rank, long long n_floats);
+int frb_peer_adam_step(int world, int rank, long long n_floats, const unsigned long long* grad_ptrs,
+                       const unsigned long long* param_ptrs, const unsigned long long* signal_ptrs,
+                       float* exp_avg, float* exp_avg_sq, uint32_t* state, double lr, double beta1, double beta2,
+                       float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
