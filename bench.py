@@ -524,6 +524,7 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_full", "multiview"])
     ap.add_argument("--mv-gaussians", type=int, default=1_000_000)
     ap.add_argument("--mv-res", type=int, default=1024)
+    ap.add_argument("--pipeline-depth", type=int, default=6, help="render e2e: host-to-host steps in flight")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multiview: fused peer-memory exchange + Adam kernel, or NCCL all-reduce + torch Adam")
     ap.add_argument("--no-cuda-graph", action="store_true", help="train workloads: run the step eagerly")
@@ -596,7 +597,7 @@ def main():
     # (fresnel_b200/host.py HostRenderPipeline).  Every step still copies its inputs up and its results down inside
     # the bracket; step i+1's H2D and step i's D2H overlap the other step's kernels.
     from fresnel_b200.host import HostRenderPipeline
-    pipe = HostRenderPipeline(ren, N_GAUSS, dev, depth=2)
+    pipe = HostRenderPipeline(ren, N_GAUSS, dev, depth=args.pipeline_depth)
     for s_ in pipe.slots:
         s_.load(host, gi_h, gd_h)
 
@@ -692,7 +693,7 @@ def main():
     barrier()
     ms_e2e = timed(step_e2e, args.steps)
     barrier()
-    timed_pipeline(4)                        # captures the two slot graphs
+    timed_pipeline(2 * pipe.depth)           # captures the slot graphs
     barrier()
     pipe_ms = timed_pipeline(args.steps)
     barrier()
@@ -755,7 +756,7 @@ def main():
                        "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed",
                        "e2e": "HostRenderPipeline: HostRenderSession steps (pinned host buffers both ways, H2D of the "
                               "parameters and upstream gradients, D2H of image, depth and all gradients) replayed from "
-                              "CUDA graphs, two steps in flight on two streams; one bracket over all steps with the "
+                              "CUDA graphs, pipeline_depth steps in flight on as many streams; one bracket over all steps with the "
                               "256 MiB L2 flush of every step INSIDE it; e2e.serial = one step at a time, eager calls, "
                               "per-step brackets, flush outside",
                        "parallelism": f"views sharded over {world} rank(s), no data-path collective"},

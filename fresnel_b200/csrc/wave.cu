@@ -64,7 +64,7 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                       const uint64_t* __restrict__ keys, int n_planes, float* __restrict__ accum,
                       uint32_t* __restrict__ rmax_bits, float2* __restrict__ fields) {
     __shared__ __align__(16) WaveStage stage[STAGES];
-    __shared__ uint32_t plane_s[STAGES][BATCH];
+    __shared__ int group_end[64];          // ASM: list position (relative to the tile's range) where plane p ends
     __shared__ __align__(8) uint64_t full_bar[STAGES];
 
     const int tile = blockIdx.x;
@@ -88,6 +88,17 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
         for (int s = 0; s < STAGES; ++s) frb_mbar_init(&full_bar[s], 1);
         frb_mbar_fence_init();
     }
+    if (ASM && threadIdx.x < n_planes) {
+        // the tile list is sorted by plane (low word of the key): upper bound of plane p by binary search, so that
+        // the inner loop below runs over whole plane groups without a per-record plane test
+        int lo = range.x, hi = range.y;
+        const uint32_t p = threadIdx.x;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if ((uint32_t)keys[mid] <= p) lo = mid + 1; else hi = mid;
+        }
+        group_end[threadIdx.x] = (threadIdx.x == n_planes - 1) ? count : lo - range.x;
+    }
     __syncthreads();
     auto issue = [&](int b) {
         int s = b % STAGES;
@@ -101,52 +112,49 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
         for (int b = 0; b < STAGES && b < n_batches; ++b) issue(b);
 
     float re0 = 0.f, re1 = 0.f, re2 = 0.f, im0 = 0.f, im1 = 0.f, im2 = 0.f, ad = 0.f, aw = 0.f;
-    int cur_plane = -1;
-    bool dirty = false;
+    int grp = 0;                           // ASM: plane whose group is being accumulated
 
-    auto flush = [&]() {
-        if (ASM && dirty && in_image) {
-            float2* f = fields + ((size_t)view * n_planes + cur_plane) * 3 * hw + pix_in_view;
+    // ASM: every (pixel, plane) of the tile is written exactly once, zeros included: no memset of the fields
+    auto flush = [&](int plane) {
+        if (ASM && in_image) {
+            float2* f = fields + ((size_t)view * n_planes + plane) * 3 * hw + pix_in_view;
             f[0] = make_float2(re0, im0);
             f[hw] = make_float2(re1, im1);
             f[2 * hw] = make_float2(re2, im2);
         }
         re0 = re1 = re2 = im0 = im1 = im2 = 0.f;
-        dirty = false;
     };
 
     for (int b = 0; b < n_batches; ++b) {
         const int s = b % STAGES;
         const int cnt = min(BATCH, count - b * BATCH);
-        if (ASM) {
-            if (threadIdx.x < cnt) plane_s[s][threadIdx.x] = (uint32_t)keys[range.x + b * BATCH + threadIdx.x];
-        }
         frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
-        if (ASM) __syncthreads();
         const float4* rec = stage[s].rec;
         const float4* wcs = stage[s].wc;
-        for (int j = 0; j < cnt; ++j) {
+        int j = 0;
+        while (j < cnt) {
+            int run_end = cnt;
             if (ASM) {
-                const int p = (int)plane_s[s][j];
-                if (p != cur_plane) {       // uniform: the tile list is sorted by plane
-                    flush();
-                    cur_plane = p;
-                }
+                const int pos = b * BATCH + j;
+                while (pos >= group_end[grp]) flush(grp++);      // uniform; group_end[n_planes - 1] = count > pos
+                run_end = min(cnt, group_end[grp] - b * BATCH);
             }
-            float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-            if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
-                float4 r0 = rec[3 * j + 0];
-                float4 wa = wcs[2 * j + 0], wb = wcs[2 * j + 1];
-                float dx = fpx - r0.x, dy = fpy - r0.y;
-                float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                float amp = frb_ex2(power) * r1.y;
-                re0 = fmaf(amp, wa.x, re0); re1 = fmaf(amp, wa.y, re1); re2 = fmaf(amp, wa.z, re2);
-                im0 = fmaf(amp, wa.w, im0); im1 = fmaf(amp, wb.x, im1); im2 = fmaf(amp, wb.y, im2);
-                if (!ASM) {
-                    ad = fmaf(amp, r1.z, ad);
-                    aw += amp;
+#pragma unroll 4
+            for (; j < run_end; ++j) {
+                float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                    float4 r0 = rec[3 * j + 0];
+                    float4 wa = wcs[2 * j + 0], wb = wcs[2 * j + 1];
+                    float dx = fpx - r0.x, dy = fpy - r0.y;
+                    float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                    float amp = frb_ex2(power) * r1.y;
+                    re0 = fmaf(amp, wa.x, re0); re1 = fmaf(amp, wa.y, re1); re2 = fmaf(amp, wa.z, re2);
+                    im0 = fmaf(amp, wa.w, im0); im1 = fmaf(amp, wb.x, im1); im2 = fmaf(amp, wb.y, im2);
+                    if (!ASM) {
+                        ad = fmaf(amp, r1.z, ad);
+                        aw += amp;
+                    }
                 }
-                dirty = true;
             }
         }
         __syncthreads();
@@ -154,7 +162,7 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
     }
 
     if (ASM) {
-        flush();
+        for (; grp < n_planes; ++grp) flush(grp);
         return;
     }
     float rm = 0.0f;
@@ -176,7 +184,7 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
 // Thirteen sums per list entry over the pixels of its rectangle inside this tile.
 // gpix: ASM = false: [view][8][H][W] (dRe rgb, dIm rgb, dD, dW); ASM = true: [view][plane][3][H][W] float2.
 template <bool ASM>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 4)
 wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
                       const float4* __restrict__ sorted_records, const float4* __restrict__ sorted_wc,
                       const uint32_t* __restrict__ sorted_gids, const uint64_t* __restrict__ keys, int n_planes,
@@ -249,10 +257,21 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
             // at least half of the lanes are on pixels of the rectangle and neighbouring lanes read neighbouring
             // shared-memory words.  The thirteen partial sums are reduced over the warp with the halving butterfly.
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            // the entry's 80 bytes come straight from global memory (L2): the next entry of this warp is loaded
+            // before the current one is processed, so the load latency hides behind the pixel loop
+            float4 n0, n1, n2, na, nb;
+            uint32_t ngid = 0;
+            auto load_entry = [&](int e) {
+                n0 = sorted_records[3 * (size_t)e + 0]; n1 = sorted_records[3 * (size_t)e + 1];
+                n2 = sorted_records[3 * (size_t)e + 2];
+                na = sorted_wc[2 * (size_t)e + 0]; nb = sorted_wc[2 * (size_t)e + 1];
+                ngid = sorted_gids[e];
+            };
+            if (g0 + warp < g1) load_entry(g0 + warp);
             for (int e = g0 + warp; e < g1; e += CTA_THREADS / 32) {
-                const float4 r0 = sorted_records[3 * (size_t)e + 0], r1 = sorted_records[3 * (size_t)e + 1],
-                             r2 = sorted_records[3 * (size_t)e + 2];
-                const float4 wa = sorted_wc[2 * (size_t)e + 0], wb = sorted_wc[2 * (size_t)e + 1];
+                const float4 r0 = n0, r1 = n1, r2 = n2, wa = na, wb = nb;
+                const uint32_t gid = ngid;
+                if (e + CTA_THREADS / 32 < g1) load_entry(e + CTA_THREADS / 32);
                 const uint32_t lo = __float_as_uint(r1.w), hi = __float_as_uint(r2.w) & 0x7fff7fffu;
                 // rectangle clipped to this tile, in tile-local pixel coordinates
                 const int x0 = max((int)(lo & 0xffff) - tx0, 0), x1 = min((int)(hi & 0xffff) - tx0, TILE);
@@ -292,7 +311,6 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 const float sx = __shfl_sync(0xffffffffu, tot, 0), sy = __shfl_sync(0xffffffffu, tot, 2);   // slots 0, 1
                 if ((lane & 1) == 0 && slot < 13) {
                     const float oln2 = r1.y * FRB_LN2;                // dL/d(power) = g * damp * o * ln2
-                    const uint32_t gid = sorted_gids[e];
                     float* g2 = grad2d + (size_t)gid * FRB_GRAD_FLOATS;
                     float* gw = gwc + (size_t)gid * WC_FLOATS;
                     float v = tot;
@@ -552,7 +570,7 @@ extern "C" int frb_asm_splat_fwd(int n_views, int width, int height, int n_plane
     if (!ranges || !fields || n_planes < 1 || n_planes > 64) return FRB_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     int tiles_x, tpv = tiles_of(width, height, &tiles_x);
-    FRB_CUDA_OK(cudaMemsetAsync(fields, 0, sizeof(float2) * (size_t)n_views * n_planes * 3 * width * height, st));
+    // no memset: the kernel writes every (view, plane, channel, pixel) of the fields, zeros included
     wave_splat_fwd_kernel<true><<<n_views * tpv, CTA_THREADS, 0, st>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, (const float4*)sorted_wc,
         keys, n_planes, nullptr, nullptr, (float2*)fields);
