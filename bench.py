@@ -464,7 +464,8 @@ def run_multiview(args, rank, world, local):
             "e2e": {"value": world * args.steps / (tot_e2e * 1e-3), "unit": "views/s",
                     "h2d_bytes_per_step": target_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": tot_e2e / args.steps},
-            "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms)},
+            "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms),
+                        **({"all": [round(x, 3) for x in ms]} if os.environ.get("FRB_BENCH_ALL_STEPS") else {})},
             "gpu_launches": int(launches), "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()

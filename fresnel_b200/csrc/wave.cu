@@ -301,11 +301,16 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                         if (!ASM) part[6] = fmaf(amp, gb.z, part[6]);
                         float gd = g * damp;                          // dL/dopacity contribution
                         part[5] += gd;
-                        float tx_ = dx * gd, ty_ = dy * gd;
-                        part[0] += tx_; part[1] += ty_;               // sx, sy
-                        part[2] = fmaf(dx, tx_, part[2]); part[3] = fmaf(dx, ty_, part[3]); part[4] = fmaf(dy, ty_, part[4]);
+                        float ty_ = dy * gd;
+                        part[1] += ty_;                               // sy
+                        part[4] = fmaf(dy, ty_, part[4]);
                     }
                 }
+                // dx is fixed per lane (a lane stays in its column of the patch): the moments in x follow from
+                // the lane's sums of gd and dy * gd
+                part[0] = dx * part[5];                               // sx
+                part[2] = dx * part[0];                               // sum dx^2 gd
+                part[3] = dx * part[1];                               // sum dx dy gd
                 const float tot = warp_reduce_multi<13>(part, lane);
                 const int slot = warp_reduce_multi_index(lane);
                 const float sx = __shfl_sync(0xffffffffu, tot, 0), sy = __shfl_sync(0xffffffffu, tot, 2);   // slots 0, 1

@@ -74,3 +74,23 @@ def test_camera_mirror_matches_oracle_pose():
     assert (a.fx, a.fy, a.cx, a.cy) == (b.fx, b.fy, b.cx, b.cy)
     v = fresnel_b200.camera_vector(a, 128, 128)
     assert v.shape == (20,) and v.dtype == np.float32 and v[16] == 128
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 16])
+def test_peer_shard_partition_covers_the_buffer(cuda_lib, world):
+    """frb_peer_shard_floats (host function of csrc/exchange.cu): the shards of the fused exchange + Adam kernel
+    are float4-aligned, disjoint, in rank order, and cover every float (the < 4 float tail goes to the last rank);
+    invalid arguments are refused, as is a launch with null pointers (no GPU needed for either)."""
+    for n in (0, 1, 3, 4, 5, 1003, 4096, 15_000_000, 15_000_003):
+        shards = [cuda_lib.frb_peer_shard_floats(world, r, n) for r in range(world)]
+        assert sum(shards) == n, (world, n, shards)
+        assert all(s >= 0 for s in shards)
+        assert all(s % 4 == 0 for s in shards[:-1])
+        per = ((n // 4) + world - 1) // world * 4
+        assert all(s <= per + 3 for s in shards)
+    assert cuda_lib.frb_peer_shard_floats(0, 0, 8) == -1
+    assert cuda_lib.frb_peer_shard_floats(2, 2, 8) == -1
+    assert cuda_lib.frb_peer_adam_step(2, 0, 16, None, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0,
+                                       None) == -1
+    assert cuda_lib.frb_peer_adam_step(17, 0, 16, None, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0,
+                                       None) == -1
