@@ -341,29 +341,27 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const float ux = wbx - r0.x, uy = wby - r0.y;
                 const float2* row = my_pair + lane * PAIR_STRIDE;
                 const float4* pc = sm.pixc[warp];
-                float sx = 0.f, sy = 0.f;                 // sum dx*dpow, sum dy*dpow
+                // sums as fp32 pairs (FFMA2: two fmas per issue slot, same bits as fmaf)
+                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg, s_xy = s_rg, s_AB = s_rg;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) {
-                    float2 cd = row[p];
-                    float4 gpix = pc[p];
-                    float dx = ux + (float)(p % BWD_FW);
-                    float dy = uy + (float)(p / BWD_FW);
-                    const float gda = cd.y;                 // g * gated dL/dalpha, formed in phase 1
-                    d_r = fmaf(cd.x, gpix.x, d_r);
-                    d_g = fmaf(cd.x, gpix.y, d_g);
-                    d_b = fmaf(cd.x, gpix.z, d_b);
-                    d_dep = fmaf(cd.x, gpix.w, d_dep);
-                    d_o += gda;
-                    float tx_ = dx * gda, ty_ = dy * gda;
-                    sx += tx_; sy += ty_;
-                    d_A = fmaf(dx, tx_, d_A);
-                    d_B = fmaf(dx, ty_, d_B);
-                    d_C = fmaf(dy, ty_, d_C);
+                    const float2 cd = row[p];               // (c, g * gated dL/dalpha), formed in phase 1
+                    const float4 gpix = pc[p];
+                    const float dx = ux + (float)(p % BWD_FW);
+                    const float dy = uy + (float)(p / BWD_FW);
+                    s_rg = frb_fma2s(cd.x, make_float2(gpix.x, gpix.y), s_rg);
+                    s_bd = frb_fma2s(cd.x, make_float2(gpix.z, gpix.w), s_bd);
+                    d_o += cd.y;
+                    const float2 t = frb_mul2s(cd.y, make_float2(dx, dy));      // (dx, dy) * dpow
+                    s_xy = frb_add2(s_xy, t);                                   // sum dx*dpow, sum dy*dpow
+                    s_AB = frb_fma2s(dx, t, s_AB);                              // sum dx^2 dpow, sum dx dy dpow
+                    d_C = fmaf(dy, t.y, d_C);
                 }
+                d_r = s_rg.x; d_g = s_rg.y; d_b = s_bd.x; d_dep = s_bd.y;
                 // dL/d(power) = gda * o * ln2 (g = 2^power); u, v enter through dx, dy
-                d_A *= oln2; d_B *= oln2; d_C *= oln2;
-                d_u = -(2.0f * r0.z * sx + r0.w * sy) * oln2;
-                d_v = -(r0.w * sx + 2.0f * r1.x * sy) * oln2;
+                d_A = s_AB.x * oln2; d_B = s_AB.y * oln2; d_C *= oln2;
+                d_u = -(2.0f * r0.z * s_xy.x + r0.w * s_xy.y) * oln2;
+                d_v = -(r0.w * s_xy.x + 2.0f * r1.x * s_xy.y) * oln2;
             }
             {
                 // (shared-memory float atomics compile to CAS loops on sm_100a: plain stores, summed below)
@@ -375,16 +373,23 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             __syncwarp();   // pair tile is reused by the next sub-block
         }
         __syncthreads();    // partial sums of all warps (and gid) visible
-        for (int i = threadIdx.x; i < N_GRADS * BATCH; i += CTA_THREADS) {
-            const int v = i / BATCH, jb = i - v * BATCH;
+        // one thread per (Gaussian, float4 of its grad2d row [du dv dA dB | dC do ddepth _ | dr dg db _]):
+        // the eight warps' partial sums are added and leave as ONE 16-byte vector reduction (red.global.add.v4.f32)
+        // instead of up to four scalar atomics
+        if (threadIdx.x < 3 * BATCH) {
+            const int q = threadIdx.x / BATCH, jb = threadIdx.x - q * BATCH;
             if (jb < cnt) {
-                float sum = 0.f;
+                const int v0 = (q == 0) ? 0 : (q == 1 ? 4 : 7);
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int w = 0; w < BWD_WARPS; ++w) sum += sm.part[w][v][jb];
-                if (sum != 0.0f) {
-                    const int slot = v + (v >= 7 ? 1 : 0);      // [du dv dA dB | dC do ddepth _ | dr dg db _]
-                    atomicAdd(grad2d + (size_t)sm.gid[s][jb] * FRB_GRAD_FLOATS + slot, sum);
+                for (int w = 0; w < BWD_WARPS; ++w) {
+                    sum.x += sm.part[w][v0][jb];
+                    sum.y += sm.part[w][v0 + 1][jb];
+                    sum.z += sm.part[w][v0 + 2][jb];
+                    if (q == 0) sum.w += sm.part[w][3][jb];
                 }
+                if (sum.x != 0.0f || sum.y != 0.0f || sum.z != 0.0f || sum.w != 0.0f)
+                    frb_red_add_f4(grad2d + (size_t)sm.gid[s][jb] * FRB_GRAD_FLOATS + 4 * q, sum);
             }
         }
         __syncthreads();    // stage s, gid[s] and part are free

@@ -88,6 +88,47 @@ __device__ __forceinline__ float frb_rcp(float x) {
     return y;
 }
 
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2: one issue slot for two IEEE fp32 operations) --------
+// The compositor and splat kernels are issue-bound with the FMA pipe at ~40 %, so pairing independent FMAs that
+// share a multiplicand (SASS takes the scalar as a broadcast operand, "R4.F32") removes issue slots without
+// changing a single result bit: each half is a correctly rounded fp32 fma, exactly like fmaf.
+__device__ __forceinline__ unsigned long long frb_pack2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 frb_unpack2(unsigned long long r) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+__device__ __forceinline__ float2 frb_fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(frb_pack2(a.x, a.y)), "l"(frb_pack2(b.x, b.y)),
+        "l"(frb_pack2(c.x, c.y)));
+    return frb_unpack2(d);
+}
+// (s * b.x + c.x, s * b.y + c.y)
+__device__ __forceinline__ float2 frb_fma2s(float s, float2 b, float2 c) { return frb_fma2(make_float2(s, s), b, c); }
+__device__ __forceinline__ float2 frb_mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(frb_pack2(a.x, a.y)), "l"(frb_pack2(b.x, b.y)));
+    return frb_unpack2(d);
+}
+__device__ __forceinline__ float2 frb_mul2s(float s, float2 b) { return frb_mul2(make_float2(s, s), b); }
+__device__ __forceinline__ float2 frb_add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(frb_pack2(a.x, a.y)), "l"(frb_pack2(b.x, b.y)));
+    return frb_unpack2(d);
+}
+
+// 16-byte vector reduction into global memory (sm_90+): four fp32 adds in one L2 atomic transaction, no return
+// value.  addr must be 16-byte aligned.
+__device__ __forceinline__ void frb_red_add_f4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 // Orders generic-proxy shared-memory writes before later async-proxy (TMA) accesses.
 __device__ __forceinline__ void frb_fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
