@@ -437,7 +437,9 @@ def run_multiview(args, rank, world, local):
         sampler.wait_first()
     l0 = L.frb_launch_count()
     barrier()
+    mem0 = torch.cuda.memory_stats(dev)
     ms = timed(step_resident, args.steps)
+    mem1 = torch.cuda.memory_stats(dev)
     barrier()
     launches = L.frb_launch_count() - l0
     ms_e2e = timed(step_e2e, args.steps)
@@ -449,6 +451,9 @@ def run_multiview(args, rank, world, local):
     tot_ms, tot_e2e = tot.tolist()
     if rank == 0:
         print(json.dumps({
+            "allocator": {k: [mem0.get(k, 0), mem1.get(k, 0)] for k in
+                          ("segment.all.allocated", "segment.all.freed", "num_alloc_retries", "num_device_alloc",
+                           "num_device_free", "reserved_bytes.all.current")},
             "metric": MV_METRIC, "value": world * args.steps / (tot_ms * 1e-3), "unit": "views/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -362,27 +362,26 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 const float2* row = my_pair + lane * PH_STRIDE;
                 const float* prow = my_phib + lane * PH_STRIDE;
                 const float4* pc = sm.pixc[warp];
-                float d_A = 0.f, d_B = 0.f, d_C = 0.f, d_o = 0.f, d_dep = 0.f, d_r = 0.f, d_g = 0.f, d_b = 0.f,
-                      d_phi = 0.f, sx = 0.f, sy = 0.f;
+                float d_C = 0.f, d_o = 0.f, d_phi = 0.f;
+                // sums as fp32 pairs (FFMA2 / FMUL2 / FADD2: two operations per issue slot, same bits as fmaf)
+                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg, s_xy = s_rg, s_AB = s_rg;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) {
                     const float2 cd = row[p];
                     const float4 gpix = pc[p];
                     const float dx = ux + (float)(p % FOOT_W);
                     const float dy = uy + (float)(p / FOOT_W);
-                    const float gda = cd.y;
-                    d_r = fmaf(cd.x, gpix.x, d_r);
-                    d_g = fmaf(cd.x, gpix.y, d_g);
-                    d_b = fmaf(cd.x, gpix.z, d_b);
-                    d_dep = fmaf(cd.x, gpix.w, d_dep);
-                    d_o += gda;
+                    s_rg = frb_fma2s(cd.x, make_float2(gpix.x, gpix.y), s_rg);
+                    s_bd = frb_fma2s(cd.x, make_float2(gpix.z, gpix.w), s_bd);
+                    d_o += cd.y;
                     d_phi += prow[p];
-                    const float tx_ = dx * gda, ty_ = dy * gda;
-                    sx += tx_; sy += ty_;
-                    d_A = fmaf(dx, tx_, d_A);
-                    d_B = fmaf(dx, ty_, d_B);
-                    d_C = fmaf(dy, ty_, d_C);
+                    const float2 t = frb_mul2s(cd.y, make_float2(dx, dy));
+                    s_xy = frb_add2(s_xy, t);
+                    s_AB = frb_fma2s(dx, t, s_AB);
+                    d_C = fmaf(dy, t.y, d_C);
                 }
+                const float sx = s_xy.x, sy = s_xy.y, d_A = s_AB.x, d_B = s_AB.y;
+                const float d_r = s_rg.x, d_g = s_rg.y, d_b = s_bd.x, d_dep = s_bd.y;
                 float* sp = &sm.sums[visit & 1][0][lane];
                 atomicAdd(sp + 0 * SUB, -(2.0f * r0.z * sx + r0.w * sy) * oln2);
                 atomicAdd(sp + 1 * SUB, -(r0.w * sx + 2.0f * r1.x * sy) * oln2);
@@ -399,15 +398,27 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         }
         __syncthreads();    // every warp's sums of this block are in; stage s is free
         if (threadIdx.x == 0 && visit + PH_STAGES < n_blocks) issue(visit + PH_STAGES);
-        for (int i = threadIdx.x; i < N_PHASE_GRADS * SUB; i += CTA_THREADS) {
-            const int v = i / SUB, jb = i - v * SUB;
-            float* sp = &sm.sums[visit & 1][v][jb];
-            const float sum = *sp;
-            if (sum != 0.0f) {
-                *sp = 0.0f;                      // this buffer is used again two blocks later
-                const uint32_t gid = sorted_gids[range.x + base_n + jb];
-                if (v == 10) atomicAdd(g_phases + gid, sum);
-                else atomicAdd(grad2d + (size_t)gid * FRB_GRAD_FLOATS + v + (v >= 7 ? 1 : 0), sum);
+        // one thread per (Gaussian, float4 of its grad2d row [du dv dA dB | dC do ddepth _ | dr dg db _]) leaves with a
+        // 16-byte vector reduction; a fourth group of threads takes the phase gradients
+        if (threadIdx.x < 4 * SUB) {
+            const int q = threadIdx.x / SUB, jb = threadIdx.x - q * SUB;
+            float* base = &sm.sums[visit & 1][0][jb];
+            if (q < 3) {
+                const int v0 = (q == 0) ? 0 : (q == 1 ? 4 : 7);
+                float4 sum = make_float4(base[v0 * SUB], base[(v0 + 1) * SUB], base[(v0 + 2) * SUB],
+                                         q == 0 ? base[3 * SUB] : 0.0f);
+                if (sum.x != 0.0f || sum.y != 0.0f || sum.z != 0.0f || sum.w != 0.0f) {
+                    base[v0 * SUB] = 0.0f; base[(v0 + 1) * SUB] = 0.0f; base[(v0 + 2) * SUB] = 0.0f;
+                    if (q == 0) base[3 * SUB] = 0.0f;        // this buffer is used again two blocks later
+                    const uint32_t gid = sorted_gids[range.x + base_n + jb];
+                    frb_red_add_f4(grad2d + (size_t)gid * FRB_GRAD_FLOATS + 4 * q, sum);
+                }
+            } else {
+                const float sum = base[10 * SUB];
+                if (sum != 0.0f) {
+                    base[10 * SUB] = 0.0f;
+                    atomicAdd(g_phases + sorted_gids[range.x + base_n + jb], sum);
+                }
             }
         }
     }

@@ -88,7 +88,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // One pass: rank (stable), look back, scatter.  Warp w of a block owns the contiguous items
 // [w*256, (w+1)*256) of the block's tile, visited in 8 rounds of 32 consecutive items, so
 // (tile, warp, round, lane) order is input order.  GEN_VALS: values are the input indices.
-template <typename KeyT, bool GEN_VALS>
+template <typename KeyT, bool GEN_VALS, int IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                       const uint32_t* __restrict__ vals_in,
@@ -109,27 +109,27 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     for (int d = lane; d < RADIX; d += 32) cnt[warp][d] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
-    if ((long long)tile * SORT_TILE >= m) return;           // past the end: nobody looks back at this tile
+    if ((long long)tile * (SORT_THREADS * IPT) >= m) return;           // past the end: nobody looks back at this tile
 
-    long long base = (long long)tile * SORT_TILE + warp * SORT_WARP_ITEMS;
-    KeyT key[SORT_IPT];
-    uint32_t rank[SORT_IPT];
+    long long base = (long long)tile * (SORT_THREADS * IPT) + warp * (32 * IPT);
+    KeyT key[IPT];
+    uint32_t rank[IPT];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
+    for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         key[r] = (i < m) ? keys_in[i] : (KeyT)0;
     }
     // the eight match.any operations are independent: issue them back to back, then update the counters
-    uint32_t peers[SORT_IPT];
+    uint32_t peers[IPT];
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
+    for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         uint32_t d = (i < m) ? digit_of(key[r], shift, mask) : RADIX;   // invalid lanes match each other only
         peers[r] = __match_any_sync(0xffffffffu, d);
     }
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
+    for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         bool valid = i < m;
         uint32_t d = digit_of(key[r], shift, mask);
@@ -204,7 +204,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     __syncthreads();
 
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
+    for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         if (i < m) {
             uint32_t dg = digit_of(key[r], shift, mask);
@@ -216,8 +216,16 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     }   // while: next tile
 }
 
+// Small sorts (the depth order of one view's Gaussians) use 512-key tiles: a 100k-key pass is a chain of L2 round
+// trips, not bandwidth, and four times as many, four times shorter tiles put every SM to work on it.
+constexpr int SORT_IPT_SMALL = 2;
+constexpr int SORT_TILE_SMALL = SORT_THREADS * SORT_IPT_SMALL;
+constexpr int SORT_SMALL_MAX = 1 << 19;                    // below this many keys: small tiles
+
+inline int sort_tile_of(int m) { return m <= SORT_SMALL_MAX ? SORT_TILE_SMALL : SORT_TILE; }
+
 size_t sort_ws_words(int m, int n_passes) {
-    return (size_t)WS_STATUS + (size_t)n_passes * (size_t)frb_div_up(m, SORT_TILE) * RADIX;
+    return (size_t)WS_STATUS + (size_t)n_passes * (size_t)frb_div_up(m, sort_tile_of(m)) * RADIX;
 }
 
 // Sorts on bits [begin_bit, end_bit).  Pass p reads buffer (p even ? A : B) and writes the other;
@@ -236,7 +244,8 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
         plan.mask[plan.n_passes] = (1u << nb) - 1u;
         ++plan.n_passes;
     }
-    const int n_blocks = frb_div_up(m, SORT_TILE);
+    const bool small = sort_tile_of(m) == SORT_TILE_SMALL;
+    const int n_blocks = frb_div_up(m, sort_tile_of(m));
     FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
     radix_hist_all_kernel<KeyT><<<min(n_blocks, 592), SORT_THREADS, 0, st>>>(m, m_dev, first_keys, plan,
                                                                              ws + WS_HIST);
@@ -248,14 +257,17 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
         KeyT* kout = to_b ? keys_b : keys_a;
         uint32_t* vout = to_b ? vals_b : vals_a;
         uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RADIX;
-        if (vin == nullptr)
-            radix_onesweep_kernel<KeyT, true><<<min(n_blocks, SORT_GRID_MAX), SORT_THREADS, 0, st>>>(
-                m, m_dev, kin, nullptr, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
-                ws + WS_TICKET + p, ws + WS_ERROR);
-        else
-            radix_onesweep_kernel<KeyT, false><<<min(n_blocks, SORT_GRID_MAX), SORT_THREADS, 0, st>>>(
-                m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,
-                ws + WS_TICKET + p, ws + WS_ERROR);
+        const int grid = min(n_blocks, SORT_GRID_MAX);
+#define FRB_ONESWEEP(GEN, IPT_)                                                                                     \
+    radix_onesweep_kernel<KeyT, GEN, IPT_><<<grid, SORT_THREADS, 0, st>>>(                                          \
+        m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,              \
+        ws + WS_TICKET + p, ws + WS_ERROR)
+        if (vin == nullptr) {
+            if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL); else FRB_ONESWEEP(true, SORT_IPT);
+        } else {
+            if (small) FRB_ONESWEEP(false, SORT_IPT_SMALL); else FRB_ONESWEEP(false, SORT_IPT);
+        }
+#undef FRB_ONESWEEP
         frb_note_launches(1);
         FRB_LAUNCH_CHECK();
         kin = kout; vin = vout;

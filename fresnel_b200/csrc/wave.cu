@@ -322,6 +322,8 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 const float tot = warp_reduce_multi<13>(part, lane);
                 const int slot = warp_reduce_multi_index(lane);
                 const float sx = __shfl_sync(0xffffffffu, tot, 0), sy = __shfl_sync(0xffffffffu, tot, 2);   // slots 0, 1
+                // lane 2k holds the total of value k: thirteen lanes of ONE atomic instruction on two contiguous rows
+                // (as four 16-byte vector reductions gathered by shuffles this was 25 % slower: 2.32 -> 2.90 ms)
                 if ((lane & 1) == 0 && slot < 13) {
                     const float oln2 = r1.y * FRB_LN2;                // dL/d(power) = g * damp * o * ln2
                     float* g2 = grad2d + (size_t)gid * FRB_GRAD_FLOATS;
@@ -372,16 +374,13 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 const float oln2 = r1.y * FRB_LN2;                    // dL/d(power) = g * damp * o * ln2
                 const uint32_t gid = sorted_gids[e];
                 float* g2 = grad2d + (size_t)gid * FRB_GRAD_FLOATS;
-                atomicAdd(g2 + 0, -(2.0f * r0.z * sx + r0.w * sy) * oln2);
-                atomicAdd(g2 + 1, -(r0.w * sx + 2.0f * r1.x * sy) * oln2);
-                atomicAdd(g2 + 2, sxx * oln2);
-                atomicAdd(g2 + 3, sxy * oln2);
-                atomicAdd(g2 + 4, syy * oln2);
-                atomicAdd(g2 + 5, s_amp);
-                if (!ASM) atomicAdd(g2 + 6, s_dep);
+                // four 16-byte vector reductions instead of thirteen scalar atomics
+                frb_red_add_f4(g2 + 0, make_float4(-(2.0f * r0.z * sx + r0.w * sy) * oln2,
+                                                   -(r0.w * sx + 2.0f * r1.x * sy) * oln2, sxx * oln2, sxy * oln2));
+                frb_red_add_f4(g2 + 4, make_float4(syy * oln2, s_amp, ASM ? 0.0f : s_dep, 0.0f));
                 float* gw = gwc + (size_t)gid * WC_FLOATS;
-                atomicAdd(gw + 0, dcc0); atomicAdd(gw + 1, dcc1); atomicAdd(gw + 2, dcc2);
-                atomicAdd(gw + 3, dcs0); atomicAdd(gw + 4, dcs1); atomicAdd(gw + 5, dcs2);
+                frb_red_add_f4(gw + 0, make_float4(dcc0, dcc1, dcc2, dcs0));
+                frb_red_add_f4(gw + 4, make_float4(dcs1, dcs2, 0.0f, 0.0f));
             }
         }
     }

@@ -103,7 +103,7 @@ def _check_inputs(**tensors):
 class TileBins:
     """Sorted tile instance lists of one batch of views (result of the binning stage)."""
 
-    __slots__ = ("m", "m_dev", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
+    __slots__ = ("m", "m_alloc", "m_dev", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
                  "records", "rects", "depth_bits", "touched")
 
 
@@ -173,18 +173,22 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
         m = worst                       # capacity; the true count stays on the device (offsets[n])
         m_dev = offsets[n:]
     b.m = m
+    # buffers are sized for a rounded-up instance count (views of length m are handed out): in an optimisation
+    # loop m drifts a little every step, and every new size class is a cudaMalloc of tens of milliseconds
+    cap = b.m_alloc = instance_capacity(m) if sync else m
 
     b.ranges = torch.empty(n_tiles, 2, **i32)
-    b.keys = torch.empty(m, dtype=torch.int64, device=dev)
-    b.sorted_gids = torch.empty(m, **i32)
-    b.sorted_records = torch.empty(max(m, 1), RECORD_FLOATS, dtype=torch.float32, device=dev)
+    b.keys = torch.empty(cap, dtype=torch.int64, device=dev)[:m]
+    b.sorted_gids = torch.empty(cap, **i32)[:m]
+    b.sorted_records = torch.empty(max(cap, 1), RECORD_FLOATS, dtype=torch.float32, device=dev)[:max(m, 1)]
     b.sorted_phases = None
     if m > 0:
         _call("frb_bin_emit", L.frb_bin_emit, n, n_views, width, height, _ptr(b.records), _ptr(b.depth_bits),
               _ptr(b.order), _ptr(offsets), _ptr(b.keys), _ptr(b.sorted_gids), st)
-        keys_tmp = torch.empty(m, dtype=torch.int64, device=dev)
-        vals_tmp = torch.empty(m, **i32)
-        ws = torch.empty(L.frb_sort_workspace_bytes(m), dtype=torch.uint8, device=dev)
+        keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
+        vals_tmp = torch.empty(cap, **i32)
+        ws = torch.empty(max(L.frb_sort_workspace_bytes(m), L.frb_sort_workspace_bytes(cap)), dtype=torch.uint8,
+                         device=dev)
         tile_bits = max(1, int(math.ceil(math.log2(max(n_tiles, 2)))))
         begin = 32 if sort else 0
         if sync:
@@ -194,7 +198,7 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
             _call("frb_radix_sort_pairs", L.frb_radix_sort_pairs_dev, m, _ptr(m_dev), _ptr(b.keys),
                   _ptr(b.sorted_gids), _ptr(keys_tmp), _ptr(vals_tmp), begin, 32 + tile_bits, _ptr(ws), st)
     if phases is not None:
-        b.sorted_phases = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        b.sorted_phases = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)[:max(m, 1)]
     if sync:
         _call("frb_ranges_and_gather", L.frb_ranges_and_gather, m, _ptr(b.keys), _ptr(b.sorted_gids), n_tiles,
               _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases), _ptr(b.sorted_phases), st)
@@ -204,6 +208,15 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
               _ptr(b.sorted_phases), st)
     b.m_dev = m_dev
     return b
+
+
+def instance_capacity(m: int) -> int:
+    """Allocation size for m tile instances: m rounded up to 1/16 of the next power of two (at least 65,536), i.e. at
+    most ~12 % more, so that nearby instance counts share one size."""
+    if m <= 0:
+        return 0
+    g = max(1 << 16, 1 << max(0, (m - 1).bit_length() - 4))
+    return -(-m // g) * g
 
 
 def worst_case_instances(n: int, n_views: int, width: int, height: int, max_radius: float) -> int:
@@ -320,7 +333,7 @@ class _TileRenderFn(torch.autograd.Function):
         ckpt = None
         if phases is not None:
             n_tiles = bins.ranges.shape[0]
-            ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m, n_tiles), 1), **f32)
+            ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m_alloc, n_tiles), 1), **f32)
         tile_order = torch.empty(bins.ranges.shape[0], dtype=torch.int32, device=dev)
         _call("frb_tile_schedule", L.frb_tile_schedule, bins.ranges.shape[0], _ptr(bins.ranges), _ptr(tile_order), st)
         _call("frb_composite_fwd", L.frb_composite_fwd_sched, n_views, width, height, _ptr(tile_order),

@@ -39,7 +39,7 @@ def _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, 
                       max_radius, presort=low_word_fn is not None, low_word_fn=low_word_fn, mode=mode)
     wc = torch.empty(n, WC_FLOATS, dtype=torch.float32, device=dev)
     _call("frb_wave_prepare", L.frb_wave_prepare, n, _ptr(colors), _ptr(phases), stride, _ptr(wc), st)
-    sorted_wc = torch.empty(max(bins.m, 1), WC_FLOATS, dtype=torch.float32, device=dev)
+    sorted_wc = torch.empty(max(bins.m_alloc, 1), WC_FLOATS, dtype=torch.float32, device=dev)[:max(bins.m, 1)]
     _call("frb_wave_gather", L.frb_wave_gather, bins.m, _ptr(bins.sorted_gids), _ptr(wc), _ptr(sorted_wc), st)
     return bins, sorted_wc
 
@@ -116,6 +116,25 @@ class _WaveRenderFn(torch.autograd.Function):
         return (*g, g_phases, None)
 
 
+# The per-plane complex fields (forward) and their gradients (backward) are the largest buffers of the ASM renderer
+# (384 H W bytes per view: 403 MB at 1024^2) and live only inside one call.  They are kept between calls, one per
+# (device, stream, size), instead of going through the caching allocator every step: a block of that size that another
+# allocation has split costs a cudaMalloc of tens of milliseconds in the middle of a training loop.
+_PLANE_SCRATCH: dict = {}
+
+
+def _plane_scratch(numel: int, dev: torch.device) -> torch.Tensor:
+    if torch.cuda.is_current_stream_capturing():         # a graph owns its memory: plain allocation
+        return torch.empty(numel, dtype=torch.float32, device=dev)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, numel)
+    buf = _PLANE_SCRATCH.get(key)
+    if buf is None:
+        if len(_PLANE_SCRATCH) >= 4:
+            _PLANE_SCRATCH.clear()
+        buf = _PLANE_SCRATCH[key] = torch.empty(numel, dtype=torch.float32, device=dev)
+    return buf
+
+
 class _AsmRenderFn(torch.autograd.Function):
     """ASMWaveFieldRenderer.forward DR:1150-1344 for n_views views (wavelengths are constants)."""
 
@@ -138,7 +157,7 @@ class _AsmRenderFn(torch.autograd.Function):
         bins, sorted_wc = _prepare_wave_bins(positions, scales, rotations, colors, opacities, phases, stride, cfg,
                                              low_word_fn=plane_words)
         f32 = dict(dtype=torch.float32, device=dev)
-        fields = torch.empty(n_views, n_planes, 3, height, width, 2, **f32)
+        fields = _plane_scratch(n_views * n_planes * 3 * height * width * 2, dev)
         total = torch.empty(n_views, 3, height, width, 2, **f32)
         rmax = torch.empty(n_views, dtype=torch.int32, device=dev)
         image = torch.empty(n_views, 3, height, width, **f32)
@@ -170,7 +189,7 @@ class _AsmRenderFn(torch.autograd.Function):
         bg_host = np.asarray(bg, np.float32)
         red = torch.empty(2 * n_views, **f32)
         g_total = torch.empty(n_views, 3, height, width, 2, **f32)
-        d_fields = torch.empty(n_views, n_planes, 3, height, width, 2, **f32)
+        d_fields = _plane_scratch(n_views * n_planes * 3 * height * width * 2, dev)
         _call("frb_asm_propagate_bwd", L.frb_asm_propagate_bwd, n_views, width, height, n_planes,
               planes.ctypes.data, float(focal), float(pitch), wavelengths.ctypes.data, bg_host.ctypes.data,
               _ptr(total), _ptr(rmax), _ptr(g_image), _ptr(red), _ptr(g_total), _ptr(d_fields), st)
