@@ -408,8 +408,18 @@ def run_multiview(args, rank, world, local):
     def step_resident():
         trainer.step(cam, target)
 
+    from fresnel_b200.host import BatchPrefetcher
+    prefetch = BatchPrefetcher(dev)
+    prefetch.submit((target_host,))
+
     def step_e2e():
-        loss_host.copy_(trainer.step(cam, target_host.to(dev, non_blocking=True)), non_blocking=True)
+        # double-buffered target staging, as in the decoder-training e2e: this step's target was copied while the
+        # previous step computed, the next one is copied while this step computes; the fence puts that copy inside
+        # this step's bracket, so K timed steps contain K target copies and K loss read-backs.
+        (tgt,) = prefetch.take()
+        prefetch.submit((target_host,))
+        loss_host.copy_(trainer.step(cam, tgt), non_blocking=True)
+        prefetch.fence()
 
     def timed(fn, steps):
         evs = []
