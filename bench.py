@@ -754,9 +754,21 @@ def main():
         }
         top = max(stages, key=stages.get)
         traffic = None       # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+        issue = None         # the bound that actually holds: warp instructions issued per second against the SMs' peak
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(top)
+            prof = json.load(open(tp))
+            traffic = prof.get(top)
+            n_inst = prof.get("warp_instructions", {}).get(top)
+            if n_inst:
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_inst = sms * 4 * mhz * 1e6                      # one warp instruction per scheduler per clock
+                ach = n_inst / (stages[top] * 1e-3)
+                issue = {"warp_instructions_per_launch": n_inst, "achieved_ginst_per_s": ach / 1e9,
+                         "peak_ginst_per_s": peak_inst / 1e9, "frac": ach / peak_inst,
+                         "note": "instruction count from the committed ncu capture (profiles/r1_traffic.json), "
+                                 "duration measured live; peak = SMs x 4 schedulers x SM clock under load"}
         achieved = alg[top] / (stages[top] * 1e-3) / 1e9
         frame_bytes = 168 * N + 36 * HW + 96 * M
         value = world * args.steps / (tot_ms * 1e-3)
@@ -789,6 +801,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[top], "kernel_ms": stages[top],
+                         "issue_roofline": issue,
                          "frame_algorithmic_bytes": frame_bytes,
                          "frame_frac": frame_bytes / (tot_ms / args.steps * 1e-3) / 1e9 / peak,
                          "stage_ms": {k: round(v, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},

@@ -328,28 +328,37 @@ offsets_scan_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t*
         total += x;
     }
     unsigned long long* status = ws + 2;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // warp-wide look-back: 32 predecessors per L2 round trip (lane l inspects tile - 1 - l)
         uint32_t excl = 0;
         if (tile == 0) {
-            st_volatile_u64(status, (unsigned long long)total | SFLAG_PREFIX);
+            if (lane == 0) st_volatile_u64(status, (unsigned long long)total | SFLAG_PREFIX);
         } else {
-            st_volatile_u64(status + tile, (unsigned long long)total | SFLAG_AGG);
+            if (lane == 0) st_volatile_u64(status + tile, (unsigned long long)total | SFLAG_AGG);
             long long look = (long long)tile - 1;
             int spins = 0;
             while (true) {
-                unsigned long long x = ld_volatile_u64(status + look);
-                unsigned long long f = x & SFLAG_MASK;
-                if (f == 0) {
-                    if (++spins > SPIN_LIMIT) { ws[1] = 1; break; }
+                const long long idx = look - lane;
+                const unsigned long long x = (idx >= 0) ? ld_volatile_u64(status + idx) : SFLAG_PREFIX;
+                const unsigned long long f = x & SFLAG_MASK;
+                const uint32_t unpublished = __ballot_sync(0xffffffffu, f == 0);
+                const uint32_t prefixes = __ballot_sync(0xffffffffu, f == SFLAG_PREFIX);
+                const int stop = prefixes ? (__ffs(prefixes) - 1) : 31;       // last lane that contributes
+                const uint32_t need = (stop == 31) ? 0xffffffffu : ((2u << stop) - 1u);
+                if (unpublished & need) {                                     // poll the same window again
+                    if (++spins > SPIN_LIMIT) { if (lane == 0) ws[1] = 1; break; }
                     continue;
                 }
-                excl += (uint32_t)(x & ~SFLAG_MASK);
-                if (f == SFLAG_PREFIX) break;
-                --look;
+                uint32_t c = (lane <= stop) ? (uint32_t)(x & ~SFLAG_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (prefixes) break;
+                look -= 32;
             }
-            st_volatile_u64(status + tile, (unsigned long long)(excl + total) | SFLAG_PREFIX);
+            if (lane == 0) st_volatile_u64(status + tile, (unsigned long long)(excl + total) | SFLAG_PREFIX);
         }
-        prefix_s = excl;
+        if (lane == 0) prefix_s = excl;
     }
     __syncthreads();
     uint32_t excl = prefix_s + woff + incl - s;

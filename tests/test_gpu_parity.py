@@ -413,14 +413,17 @@ def test_host_render_pipeline_matches_direct_call():
     DEV = dev()
     n, R = 6001, 128
     ren = fresnel_b200.TileBasedRenderer(R, R, background=(0.1, 0.2, 0.3))
-    cam = fresnel_b200.Camera(0.8 * R, 0.8 * R, R / 2, R / 2, R, R)
+    # two cameras, changing every other step: every slot sees both (one graph per (slot, camera))
+    cams = [fresnel_b200.Camera(0.8 * R, 0.8 * R, R / 2, R / 2, R, R),
+            fresnel_b200.Camera(0.7 * R, 0.75 * R, R / 2 + 3, R / 2 - 2, R, R)]
+    cam_of = lambda i: cams[(i // 2) % 2]
     g = torch.Generator().manual_seed(7)
-    clouds = [fo.synthetic_cloud(n, 11 + i, 0.01, 0.05) for i in range(5)]
-    ups = [(torch.rand(3, R, R, generator=g) * 2 - 1, torch.rand(R, R, generator=g) * 2 - 1) for _ in range(5)]
+    clouds = [fo.synthetic_cloud(n, 11 + i, 0.01, 0.05) for i in range(6)]
+    ups = [(torch.rand(3, R, R, generator=g) * 2 - 1, torch.rand(R, R, generator=g) * 2 - 1) for _ in range(6)]
     want = []
-    for inp, (gi, gd) in zip(clouds, ups):
+    for i, (inp, (gi, gd)) in enumerate(zip(clouds, ups)):
         L = {k: inp[k].to(DEV).requires_grad_(True) for k in GRAD_NAMES}
-        img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
+        img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam_of(i),
                        return_depth=True)
         torch.autograd.backward((img, dep), (gi.to(DEV), gd.to(DEV)))
         want.append((img.detach().cpu(), dep.detach().cpu(), {k: L[k].grad.cpu() for k in GRAD_NAMES}))
@@ -438,7 +441,7 @@ def test_host_render_pipeline_matches_direct_call():
             collect(*pending.pop(0))
         slot = pipe.acquire()
         pipe.slots[slot].load(inp, gi, gd)
-        pipe.submit(cam, slot)
+        pipe.submit(cam_of(i), slot)
         pending.append((i, slot))
     for item in pending:
         collect(*item)
