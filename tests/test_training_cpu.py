@@ -169,3 +169,31 @@ def test_flat_params_layout_and_alignment():
         assert torch.equal(v[k].detach(), cloud[k])
     assert fp.slices["rotations"][0] == 0             # float4-typed tensor first: 16-byte aligned for every n
     assert fp.flat.numel() == 15 * 37
+
+
+def test_flat_params_accept_external_storage_and_peer_exchange_needs_cuda():
+    """FlatGaussianParams can live in caller-provided buffers (the peer-mapped ones of PeerShardedAdam), with the
+    same layout as in its own; the fused peer exchange itself has no CPU path and says so."""
+    from fresnel_b200.training import FlatGaussianParams, MultiViewTrainer, PeerShardedAdam
+    n = 37
+    g = torch.Generator().manual_seed(2)
+    cloud = dict(positions=torch.randn(n, 3, generator=g), scales=torch.rand(n, 3, generator=g),
+                 rotations=torch.randn(n, 4, generator=g), colors=torch.rand(n, 3, generator=g),
+                 opacities=torch.rand(n, generator=g), phases=torch.rand(n, generator=g))
+    total = FlatGaussianParams.total_floats(n, with_phases=True)
+    assert total == 15 * n
+    own = FlatGaussianParams(cloud, "cpu", with_phases=True)
+    flat, grad = torch.full((total,), 7.0), torch.full((total,), 7.0)
+    ext = FlatGaussianParams(cloud, "cpu", with_phases=True, storage=(flat, grad))
+    assert ext.flat.data_ptr() == flat.data_ptr() and ext.flat.grad.data_ptr() == grad.data_ptr()
+    assert torch.equal(ext.flat.detach(), own.flat.detach()) and float(grad.abs().max()) == 0.0
+    for k, v in ext.views().items():
+        assert torch.equal(v.detach(), cloud[k])
+    with pytest.raises(ValueError):
+        FlatGaussianParams(cloud, "cpu", with_phases=True, storage=(flat[:-1], grad[:-1]))
+    with pytest.raises(TypeError, match="CUDA"):
+        PeerShardedAdam(total, "cpu")
+    with pytest.raises(TypeError, match="CUDA"):
+        MultiViewTrainer(torch.nn.Identity(), cloud, "cpu", with_phases=True, exchange="peer")
+    with pytest.raises(ValueError):
+        MultiViewTrainer(torch.nn.Identity(), cloud, "cpu", exchange="mpi")
