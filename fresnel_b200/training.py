@@ -473,7 +473,8 @@ class PeerShardedAdam:
             self.param = symm_mem.empty(self.n, **f32)
             self.grad = symm_mem.empty(self.n, **f32)
             self.signal = symm_mem.empty(pad, dtype=torch.int32, device=dev)
-            self.param.zero_(); self.grad.zero_(); self.signal.zero_()
+            for t in (self.param, self.grad, self.signal):
+                t.zero_()
             self._handles = [symm_mem.rendezvous(t, gname) for t in (self.grad, self.param, self.signal)]
             table = [[int(p) for p in h.buffer_ptrs] for h in self._handles]
             torch.cuda.synchronize(dev)

@@ -493,6 +493,50 @@ def test_peer_adam_two_ranks_matches_nccl_adam():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.gpu
+def test_plain_c_program_through_the_c_abi_matches_the_module(tmp_path):
+    """examples/render_c_abi.c (C99, CUDA runtime + the library, no torch): forward + backward through
+    frb_tile_render_fwd / _bwd from files; image, depth and alpha are bit-identical to the nn.Module path, the
+    gradients agree to the order of the atomic sums."""
+    import subprocess
+    from test_boundary_cpu import build_c_example
+    exe = build_c_example(str(tmp_path / "render_c_abi"))
+    DEV = dev()
+    n, W, H = 3001, 112, 80
+    inp = fo.synthetic_cloud(n, 21, 0.01, 0.05)
+    g = torch.Generator().manual_seed(4)
+    gi, gd = torch.rand(3, H, W, generator=g) * 2 - 1, torch.rand(H, W, generator=g) * 2 - 1
+    bg = (0.1, 0.2, 0.3)
+    cam = fresnel_b200.Camera(0.8 * W, 0.8 * W, W / 2, H / 2, W, H)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.asarray([n, W, H], np.int32).tobytes())
+        f.write(camera_vector(cam, W, H).astype(np.float32).tobytes())
+        f.write(np.asarray(bg, np.float32).tobytes())
+        for k in GRAD_NAMES:
+            f.write(inp[k].contiguous().numpy().astype(np.float32).tobytes())
+        f.write(gi.numpy().tobytes())
+        f.write(gd.numpy().tobytes())
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(tmp_path / "out.bin", np.float32)
+    hw = H * W
+    assert out.size == 5 * hw + 14 * n
+    ren = fresnel_b200.TileBasedRenderer(W, H, background=bg, t_eps=0.0)
+    L = {k: inp[k].to(DEV).requires_grad_(True) for k in GRAD_NAMES}
+    img, dep, alpha = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
+                          return_depth=True, return_alpha=True)
+    torch.autograd.backward((img, dep), (gi.to(DEV), gd.to(DEV)))
+    assert np.array_equal(out[:3 * hw], img.detach().cpu().numpy().ravel())
+    assert np.array_equal(out[3 * hw:4 * hw], dep.detach().cpu().numpy().ravel())
+    assert np.array_equal(out[4 * hw:5 * hw], alpha.detach().cpu().numpy().ravel())
+    off = 5 * hw
+    for k, w in (("positions", 3), ("scales", 3), ("rotations", 4), ("colors", 3), ("opacities", 1)):
+        a = torch.from_numpy(out[off:off + w * n].copy()).view(L[k].shape)
+        off += w * n
+        assert rel(a, L[k].grad.cpu()) < 1e-5, k
+
+
 def test_dense_renderer_matches_reference_golden(golden):
     """DifferentiableGaussianRenderer: image, depth and the five gradients against the
     reference's own output on the same inputs."""
