@@ -25,6 +25,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                      float alpha_max, float* __restrict__ image,
                      float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
                      int* __restrict__ state_n) {
+    frb_pdl_prologue();
     __shared__ StageBuf stage[STAGES];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
 
@@ -182,6 +183,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                      const int* __restrict__ state_n, const float* __restrict__ g_image,
                      const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
                      float* __restrict__ grad2d) {
+    frb_pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
@@ -402,6 +404,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 constexpr int SCHED_BUCKETS = 1024;
 __global__ void __launch_bounds__(1024) tile_schedule_kernel(int n_tiles, const int2* __restrict__ ranges,
                                                              int* __restrict__ order) {
+    frb_pdl_prologue();
     __shared__ int hist[SCHED_BUCKETS];
     __shared__ int warp_tot[32];
     hist[threadIdx.x] = 0;
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(1024) tile_schedule_kernel(int n_tiles, const 
 extern "C" int frb_tile_schedule(int n_tiles, const int32_t* ranges, int32_t* tile_order, void* stream) {
     if (n_tiles < 0 || !ranges || !tile_order) return FRB_E_INVALID;
     if (n_tiles == 0) return 0;
-    tile_schedule_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_tiles, (const int2*)ranges, tile_order);
+    frb_launch(tile_schedule_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, n_tiles, (const int2*)ranges, tile_order);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -500,7 +503,7 @@ extern "C" int frb_composite_fwd_cap(int n_views, int width, int height, const i
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    composite_fwd_kernel<<<n_views * tpv, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+    frb_launch(composite_fwd_kernel, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream, 
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps,
         alpha_max, image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
@@ -558,7 +561,7 @@ extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const i
                                          (int)sizeof(BwdSmem)));
         attr_set = true;
     }
-    composite_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
+    frb_launch(composite_bwd_kernel, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem), (cudaStream_t)stream, 
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
         bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
     frb_note_launches(1);

@@ -34,7 +34,37 @@ void frb_note_launches(int k);
 
 static inline int frb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (sm_90+): kernels of the render chain are launched with the programmatic stream
+// serialization attribute, so that the NEXT kernel's CTAs are scheduled (and run their prologue up to
+// frb_pdl_prologue()) while the previous kernel drains, instead of after it has drained.  Every chain kernel calls
+// frb_pdl_prologue() before its first global-memory access; without the attribute it is a no-op.
+// FRB_PDL=0 in the environment launches the plain way.
+bool frb_pdl_enabled();
+
 #if defined(__CUDACC__)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t frb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = frb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Let the dependent grid be scheduled now; then wait until the grid this one depends on has completed and its
+// writes are visible.  (A dependent grid waits at the same point for THIS grid, so starting it early is safe.)
+__device__ __forceinline__ void frb_pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t frb_smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

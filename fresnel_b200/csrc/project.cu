@@ -11,6 +11,15 @@ static std::atomic<unsigned long long> g_launches{0};
 void frb_note_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
 extern "C" unsigned long long frb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+#include <cstdlib>
+bool frb_pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("FRB_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs) {
     if (n < 0 || n_views < 1 || n_views > FRB_MAX_VIEWS || camera_host == nullptr) return FRB_E_INVALID;
     if (n % n_views != 0) return FRB_E_INVALID;
@@ -36,6 +45,7 @@ frb_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
                        float max_radius, int mode, float4* __restrict__ records, int4* __restrict__ rects,
                        uint32_t* __restrict__ depth_bits, uint32_t* __restrict__ tiles_touched,
                        float4* __restrict__ debug) {
+    frb_pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const FrbCamera& cam = vs.cam[i / vs.n_per_view];
@@ -77,6 +87,7 @@ frb_project_bwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
                        const float4* __restrict__ grad2d, int mode, float* __restrict__ g_positions,
                        float* __restrict__ g_scales, float4* __restrict__ g_rotations,
                        float* __restrict__ g_colors, float* __restrict__ g_opacities) {
+    frb_pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 g0 = grad2d[3 * i + 0], g1 = grad2d[3 * i + 1], g2 = grad2d[3 * i + 2];
@@ -123,7 +134,7 @@ extern "C" int frb_project_fwd_mode(int n, int n_views, const float* positions, 
     if (!positions || !scales || !rotations || !colors || !opacities || !records || !depth_bits ||
         !tiles_touched)
         return FRB_E_INVALID;
-    frb_project_fwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    frb_launch(frb_project_fwd_kernel, dim3(frb_div_up(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         n, vs, positions, scales, rotations, colors, opacities, max_radius, mode, (float4*)records,
         (int4*)rects, depth_bits, tiles_touched, (float4*)debug);
     frb_note_launches(1);
@@ -150,7 +161,7 @@ extern "C" int frb_project_bwd_mode(int n, int n_views, const float* positions, 
     if (n == 0) return 0;
     if (!positions || !scales || !rotations || !grad2d || !g_positions || !g_scales || !g_rotations)
         return FRB_E_INVALID;
-    frb_project_bwd_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    frb_launch(frb_project_bwd_kernel, dim3(frb_div_up(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         n, vs, positions, scales, rotations, (const float4*)grad2d, mode, g_positions, g_scales,
         (float4*)g_rotations, g_colors, g_opacities);
     frb_note_launches(1);

@@ -60,6 +60,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_all_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys,
                       const __grid_constant__ PassPlan plan, uint32_t* __restrict__ hist) {
+    frb_pdl_prologue();
     __shared__ uint32_t cnt[MAX_PASSES][RADIX];
     if (m_dev) m = min(m, (int)*m_dev);
     for (int p = 0; p < plan.n_passes; ++p) cnt[p][threadIdx.x] = 0;
@@ -95,6 +96,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
                       const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag) {
+    frb_pdl_prologue();
     __shared__ uint32_t cnt[SORT_WARPS][RADIX];
     __shared__ uint32_t digit_base[RADIX];
     __shared__ uint32_t scan_ws[SORT_WARPS];
@@ -247,7 +249,7 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
     const bool small = sort_tile_of(m) == SORT_TILE_SMALL;
     const int n_blocks = frb_div_up(m, sort_tile_of(m));
     FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
-    radix_hist_all_kernel<KeyT><<<min(n_blocks, 592), SORT_THREADS, 0, st>>>(m, m_dev, first_keys, plan,
+    frb_launch(radix_hist_all_kernel<KeyT>, dim3(min(n_blocks, 592)), dim3(SORT_THREADS), 0, st, m, m_dev, first_keys, plan,
                                                                              ws + WS_HIST);
     frb_note_launches(1);
     const KeyT* kin = first_keys;
@@ -259,7 +261,7 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
         uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RADIX;
         const int grid = min(n_blocks, SORT_GRID_MAX);
 #define FRB_ONESWEEP(GEN, IPT_)                                                                                     \
-    radix_onesweep_kernel<KeyT, GEN, IPT_><<<grid, SORT_THREADS, 0, st>>>(                                          \
+    frb_launch(radix_onesweep_kernel<KeyT, GEN, IPT_>, dim3(grid), dim3(SORT_THREADS), 0, st,                                           \
         m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,              \
         ws + WS_TICKET + p, ws + WS_ERROR)
         if (vin == nullptr) {
@@ -296,6 +298,7 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 __global__ void __launch_bounds__(SCAN_THREADS)
 offsets_scan_kernel(int n, const uint32_t* __restrict__ touched, const uint32_t* __restrict__ order,
                     uint32_t* __restrict__ offsets, unsigned long long* __restrict__ ws) {
+    frb_pdl_prologue();
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     __shared__ uint32_t tile_s;
     __shared__ uint32_t prefix_s;
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(256)
 bin_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const float4* __restrict__ records,
                 const uint32_t* __restrict__ depth_bits, const uint32_t* __restrict__ order,
                 const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys, uint32_t* __restrict__ gids) {
+    frb_pdl_prologue();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t off = offsets[k], end = offsets[k + 1];
@@ -424,6 +428,7 @@ gather_records_kernel(int m, const uint32_t* __restrict__ m_dev, const uint32_t*
                       float4* __restrict__ sorted_records, const float* __restrict__ phases,
                       float* __restrict__ sorted_phases, const uint64_t* __restrict__ keys,
                       int2* __restrict__ ranges) {
+    frb_pdl_prologue();
     if (m_dev) m = min(m, (int)*m_dev);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 3ll * m;
          t += (long long)gridDim.x * blockDim.x) {
@@ -515,7 +520,7 @@ extern "C" int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint
     if (!tiles_touched || !workspace) return FRB_E_INVALID;
     int nb = frb_div_up(n, SCAN_TILE);
     FRB_CUDA_OK(cudaMemsetAsync(workspace, 0, frb_scan_workspace_bytes(n), st));
-    offsets_scan_kernel<<<nb, SCAN_THREADS, 0, st>>>(n, tiles_touched, order, offsets,
+    frb_launch(offsets_scan_kernel, dim3(nb), dim3(SCAN_THREADS), 0, st, n, tiles_touched, order, offsets,
                                                      (unsigned long long*)workspace);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
@@ -531,7 +536,7 @@ extern "C" int frb_bin_emit(int n, int n_views, int width, int height, const flo
     if (n == 0) return 0;
     if (!records || !depth_bits || !offsets || !keys || !gids) return FRB_E_INVALID;
     int tiles_x = frb_div_up(width, FRB_TILE), tiles_y = frb_div_up(height, FRB_TILE);
-    bin_emit_kernel<<<frb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    frb_launch(bin_emit_kernel, dim3(frb_div_up(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         n, n / n_views, tiles_x, tiles_x * tiles_y, (const float4*)records, depth_bits, order, offsets, keys,
         gids);
     frb_note_launches(1);
@@ -557,7 +562,7 @@ extern "C" int frb_gather_records(int m, const uint32_t* gids, const float* reco
     if (m == 0) return 0;
     if (!gids || !records || !sorted_records) return FRB_E_INVALID;
     if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
-    gather_records_kernel<<<min(frb_div_up(3ll * m, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+    frb_launch(gather_records_kernel, dim3(min(frb_div_up(3ll * m, 256), 148 * 32)), dim3(256), 0, (cudaStream_t)stream, 
         m, nullptr, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, nullptr, nullptr);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
@@ -573,7 +578,7 @@ static int ranges_and_gather(int m, const uint32_t* m_dev, const uint64_t* keys,
     if (m == 0) return 0;
     if (!keys || !gids || !records || !sorted_records) return FRB_E_INVALID;
     if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
-    gather_records_kernel<<<min(frb_div_up(3ll * m, 256), 148 * 32), 256, 0, st>>>(
+    frb_launch(gather_records_kernel, dim3(min(frb_div_up(3ll * m, 256), 148 * 32)), dim3(256), 0, st, 
         m, m_dev, gids, (const float4*)records, (float4*)sorted_records, phases, sorted_phases, keys,
         (int2*)ranges);
     frb_note_launches(1);
