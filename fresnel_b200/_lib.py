@@ -32,6 +32,7 @@ _SIGNATURES = {
     "frb_scan_workspace_bytes": (c_size_t, [c_int]),
     "frb_tile_offsets": (c_int, [c_int, P, P, P, P, P]),
     "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "frb_bin_sort_dev": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P, P, c_int, P, P, P]),
     "frb_tile_ranges": (c_int, [c_int, P, c_int, P, P]),
     "frb_gather_records": (c_int, [c_int, P, P, P, P, P, P]),
     "frb_ranges_and_gather": (c_int, [c_int, P, P, c_int, P, P, P, P, P, P]),

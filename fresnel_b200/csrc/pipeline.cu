@@ -77,13 +77,21 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
     if ((rc = frb_project_fwd(n, n_views, positions, scales, rotations, colors, opacities, camera_host, max_radius,
                               records, nullptr, depth_bits, touched, nullptr, stream))) return rc;
     if ((rc = frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream))) return rc;
-    if ((rc = frb_tile_offsets(n, touched, order, offsets, S + L.scan_ws, stream))) return rc;
     if (n > 0 && m_capacity > 0) {
-        if ((rc = frb_bin_emit(n, n_views, width, height, records, depth_bits, order, offsets, keys, gids, stream)))
-            return rc;
-        if ((rc = frb_radix_sort_pairs_dev(m_capacity, offsets + n, keys, gids, (uint64_t*)(S + L.keys_tmp),
-                                           (uint32_t*)(S + L.vals_tmp), 32, 32 + tile_bits, S + L.sort_ws, stream)))
-            return rc;
+        if (tile_bits <= 16) {
+            // scan of the tile counts, key emission and the sort histograms in one kernel (offsets[n] = M only)
+            if ((rc = frb_bin_sort_dev(n, n_views, width, height, records, depth_bits, touched, order, m_capacity,
+                                       offsets + n, keys, gids, (uint64_t*)(S + L.keys_tmp),
+                                       (uint32_t*)(S + L.vals_tmp), tile_bits, S + L.scan_ws, S + L.sort_ws, stream)))
+                return rc;
+        } else {
+            if ((rc = frb_tile_offsets(n, touched, order, offsets, S + L.scan_ws, stream))) return rc;
+            if ((rc = frb_bin_emit(n, n_views, width, height, records, depth_bits, order, offsets, keys, gids,
+                                   stream))) return rc;
+            if ((rc = frb_radix_sort_pairs_dev(m_capacity, offsets + n, keys, gids, (uint64_t*)(S + L.keys_tmp),
+                                               (uint32_t*)(S + L.vals_tmp), 32, 32 + tile_bits, S + L.sort_ws,
+                                               stream))) return rc;
+        }
         if ((rc = frb_ranges_and_gather_dev(m_capacity, offsets + n, keys, gids, tiles, ranges, records,
                                             sorted_records, nullptr, nullptr, stream))) return rc;
     } else {

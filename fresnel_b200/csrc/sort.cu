@@ -236,7 +236,7 @@ size_t sort_ws_words(int m, int n_passes) {
 template <typename KeyT>
 int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
                     KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
-                    bool* result_in_b) {
+                    bool* result_in_b, bool hist_ready = false) {
     PassPlan plan;
     plan.n_passes = 0;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
@@ -248,10 +248,12 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
     }
     const bool small = sort_tile_of(m) == SORT_TILE_SMALL;
     const int n_blocks = frb_div_up(m, sort_tile_of(m));
-    FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
-    frb_launch(radix_hist_all_kernel<KeyT>, dim3(min(n_blocks, 592)), dim3(SORT_THREADS), 0, st, m, m_dev, first_keys, plan,
-                                                                             ws + WS_HIST);
-    frb_note_launches(1);
+    if (!hist_ready) {      // otherwise the caller zeroed ws and the producer of the keys filled the histograms
+        FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
+        frb_launch(radix_hist_all_kernel<KeyT>, dim3(min(n_blocks, 592)), dim3(SORT_THREADS), 0, st, m, m_dev,
+                   first_keys, plan, ws + WS_HIST);
+        frb_note_launches(1);
+    }
     const KeyT* kin = first_keys;
     const uint32_t* vin = first_vals;
     bool to_b = (first_keys == keys_a);     // in-place start: A -> B; external start: -> A first
@@ -283,6 +285,7 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+constexpr int EMIT_TILE = 256;               // Gaussians per block of scan_emit_kernel (one per thread)
 constexpr unsigned long long SFLAG_AGG = 1ull << 62, SFLAG_PREFIX = 2ull << 62, SFLAG_MASK = 3ull << 62;
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -399,6 +402,107 @@ bin_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const fl
         }
 }
 
+// Scan + emit + histogram in ONE kernel (the whole-pass forward, pipeline.cu): block b takes 256 Gaussians in depth
+// order, scans their tile counts, obtains its offset by warp-wide decoupled look-back over the preceding blocks,
+// emits the (tile | depth) keys, and counts the tile digits of the two sort passes on the way (shared-memory
+// counters, flushed once per block) - the offsets array, the offsets kernel and the histogram pass over the M keys
+// disappear.  ws: [ticket u64][error u64][status u64 x blocks], zeroed by the caller; hist: the sort workspace's
+// histogram words (pass p at hist + 256 p), zeroed by the caller; m_out: total number of instances.
+__global__ void __launch_bounds__(EMIT_TILE)
+scan_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const float4* __restrict__ records,
+                 const uint32_t* __restrict__ depth_bits, const uint32_t* __restrict__ touched,
+                 const uint32_t* __restrict__ order, uint64_t* __restrict__ keys, uint32_t* __restrict__ gids,
+                 unsigned long long* __restrict__ ws, uint32_t* __restrict__ hist, uint32_t mask1,
+                 uint32_t* __restrict__ m_out) {
+    frb_pdl_prologue();
+    __shared__ uint32_t h[2][RADIX];
+    __shared__ uint32_t wsum[EMIT_TILE / 32];
+    __shared__ uint32_t tile_s, prefix_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_s = (uint32_t)atomicAdd(ws, 1ull);     // blocks are numbered in start order
+    h[0][threadIdx.x] = 0;
+    h[1][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t blk = tile_s;
+    const long long k = (long long)blk * EMIT_TILE + threadIdx.x;
+    uint32_t g = 0, cnt = 0;
+    if (k < n) {
+        g = order ? order[k] : (uint32_t)k;
+        cnt = touched[g];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < EMIT_TILE / 32; ++w) {
+        uint32_t x = wsum[w];
+        if (w < warp) woff += x;
+        total += x;
+    }
+    unsigned long long* status = ws + 2;
+    if (warp == 0) {
+        uint32_t excl = 0;
+        if (blk == 0) {
+            if (lane == 0) st_volatile_u64(status, (unsigned long long)total | SFLAG_PREFIX);
+        } else {
+            if (lane == 0) st_volatile_u64(status + blk, (unsigned long long)total | SFLAG_AGG);
+            long long look = (long long)blk - 1;
+            int spins = 0;
+            while (true) {
+                const long long idx = look - lane;
+                const unsigned long long x = (idx >= 0) ? ld_volatile_u64(status + idx) : SFLAG_PREFIX;
+                const unsigned long long f = x & SFLAG_MASK;
+                const uint32_t unpublished = __ballot_sync(0xffffffffu, f == 0);
+                const uint32_t prefixes = __ballot_sync(0xffffffffu, f == SFLAG_PREFIX);
+                const int stop = prefixes ? (__ffs(prefixes) - 1) : 31;
+                const uint32_t need = (stop == 31) ? 0xffffffffu : ((2u << stop) - 1u);
+                if (unpublished & need) {
+                    if (++spins > SPIN_LIMIT) { if (lane == 0) ws[1] = 1; break; }
+                    continue;
+                }
+                uint32_t c = (lane <= stop) ? (uint32_t)(x & ~SFLAG_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (prefixes) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(status + blk, (unsigned long long)(excl + total) | SFLAG_PREFIX);
+        }
+        if (lane == 0) prefix_s = excl;
+    }
+    __syncthreads();
+    uint32_t off = prefix_s + woff + incl - cnt;
+    if (k == n - 1) *m_out = off + cnt;
+    if (cnt) {
+        uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].w);
+        uint32_t hi = __float_as_uint(records[3 * (size_t)g + 2].w) & 0x7fff7fffu;
+        int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
+        int tx0 = x0 / FRB_TILE, tx1 = (x1 - 1) / FRB_TILE, ty0 = y0 / FRB_TILE, ty1 = (y1 - 1) / FRB_TILE;
+        uint32_t view_base = (g / (uint32_t)n_per_view) * (uint32_t)tiles_per_view;
+        uint64_t db = depth_bits[g];
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                uint32_t tile = view_base + (uint32_t)(ty * tiles_x + tx);
+                keys[off] = ((uint64_t)tile << 32) | db;
+                gids[off] = g;
+                ++off;
+                atomicAdd(&h[0][tile & (RADIX - 1)], 1u);
+                atomicAdd(&h[1][(tile >> RADIX_BITS) & mask1], 1u);
+            }
+    }
+    __syncthreads();
+    uint32_t c0 = h[0][threadIdx.x], c1 = h[1][threadIdx.x];
+    if (c0) atomicAdd(&hist[threadIdx.x], c0);
+    if (c1) atomicAdd(&hist[RADIX + threadIdx.x], c1);
+}
+
 __device__ __forceinline__ void range_boundary(int i, int m, const uint64_t* __restrict__ keys,
                                                int2* __restrict__ ranges) {
     uint32_t t = (uint32_t)(keys[i] >> 32);
@@ -506,7 +610,7 @@ extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* orde
 
 extern "C" size_t frb_scan_workspace_bytes(int n) {
     if (n < 0) n = 0;
-    return sizeof(unsigned long long) * (size_t)(frb_div_up(n, SCAN_TILE) + 2);
+    return sizeof(unsigned long long) * (size_t)(frb_div_up(n, EMIT_TILE) + 2);   // covers both scan kernels
 }
 
 extern "C" int frb_tile_offsets(int n, const uint32_t* tiles_touched, const uint32_t* order,
@@ -541,6 +645,42 @@ extern "C" int frb_bin_emit(int n, int n_views, int width, int height, const flo
         gids);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Whole-pass binning (pipeline.cu): scan + emit + sort histograms in one kernel, then the one-sweep passes on the tile
+// bits.  Same result as frb_tile_offsets + frb_bin_emit + frb_radix_sort_pairs_dev; sorted pairs end in keys / gids.
+// m_out: device word that receives the true instance count (also read by the passes); scan_ws:
+// frb_scan_workspace_bytes(n); sort_ws: frb_sort_workspace_bytes(m_capacity).
+extern "C" int frb_bin_sort_dev(int n, int n_views, int width, int height, const float* records,
+                                const uint32_t* depth_bits, const uint32_t* tiles_touched, const uint32_t* order,
+                                int m_capacity, uint32_t* m_out, uint64_t* keys, uint32_t* gids, uint64_t* keys_tmp,
+                                uint32_t* vals_tmp, int tile_bits, void* scan_ws, void* sort_ws, void* stream) {
+    if (n <= 0 || n_views < 1 || n_views > FRB_MAX_VIEWS || n % n_views != 0 || m_capacity <= 0) return FRB_E_INVALID;
+    if (width < 1 || height < 1 || tile_bits < 1 || tile_bits > 2 * RADIX_BITS) return FRB_E_INVALID;
+    if (width > FRB_MAX_IMAGE_SIDE || height > FRB_MAX_IMAGE_SIDE) return FRB_E_TOO_LARGE;
+    if (!records || !depth_bits || !tiles_touched || !m_out || !keys || !gids || !keys_tmp || !vals_tmp ||
+        !scan_ws || !sort_ws)
+        return FRB_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_passes = tile_bits > RADIX_BITS ? 2 : 1;
+    const uint32_t mask1 = tile_bits > RADIX_BITS ? (1u << (tile_bits - RADIX_BITS)) - 1u : 0u;
+    FRB_CUDA_OK(cudaMemsetAsync(scan_ws, 0, frb_scan_workspace_bytes(n), st));
+    FRB_CUDA_OK(cudaMemsetAsync(sort_ws, 0, sizeof(uint32_t) * sort_ws_words(m_capacity, n_passes), st));
+    int tiles_x = frb_div_up(width, FRB_TILE), tiles_y = frb_div_up(height, FRB_TILE);
+    frb_launch(scan_emit_kernel, dim3(frb_div_up(n, EMIT_TILE)), dim3(EMIT_TILE), 0, st, n, n / n_views, tiles_x,
+               tiles_x * tiles_y, (const float4*)records, depth_bits, tiles_touched, order, keys, gids,
+               (unsigned long long*)scan_ws, (uint32_t*)sort_ws + WS_HIST, mask1, m_out);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    bool in_b = false;
+    int rc = radix_sort_impl<uint64_t>(m_capacity, m_out, keys, gids, keys, gids, keys_tmp, vals_tmp, 32, 32 + tile_bits,
+                                       (uint32_t*)sort_ws, st, &in_b, /*hist_ready=*/true);
+    if (rc) return rc;
+    if (in_b) {
+        FRB_CUDA_OK(cudaMemcpyAsync(keys, keys_tmp, sizeof(uint64_t) * (size_t)m_capacity, cudaMemcpyDeviceToDevice, st));
+        FRB_CUDA_OK(cudaMemcpyAsync(gids, vals_tmp, sizeof(uint32_t) * (size_t)m_capacity, cudaMemcpyDeviceToDevice, st));
+    }
     return 0;
 }
 

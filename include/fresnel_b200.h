@@ -181,6 +181,15 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
  * for n_views views; buffers are carved from two arenas laid out by frb_tile_layout: `persist`
  * (kept for the backward pass) and `scratch` (free after the call's work has run).  m_capacity bounds
  * the number of tile instances (n * max tiles a rectangle can cover is always enough). */
+/* frb_tile_offsets + frb_bin_emit + frb_radix_sort_pairs_dev(begin 32, end 32 + tile_bits) with the scan, the key
+ * emission and the sort's digit histograms fused into one kernel (tile_bits <= 16).  m_out: device word receiving the
+ * instance count M; scan_ws: frb_scan_workspace_bytes(n); sort_ws: frb_sort_workspace_bytes(m_capacity).  The sorted
+ * pairs end in keys / gids. */
+int frb_bin_sort_dev(int n, int n_views, int width, int height, const float* records, const uint32_t* depth_bits,
+                     const uint32_t* tiles_touched, const uint32_t* order, int m_capacity, uint32_t* m_out,
+                     uint64_t* keys, uint32_t* gids, uint64_t* keys_tmp, uint32_t* vals_tmp, int tile_bits,
+                     void* scan_ws, void* sort_ws, void* stream);
+
 typedef struct FrbTileLayout {
     size_t ranges, tile_order, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
     size_t records, depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,

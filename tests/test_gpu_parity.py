@@ -126,6 +126,42 @@ def test_depth_order_matches_stable_argsort(n):
     assert np.array_equal(order.cpu().numpy(), np.argsort(bits, kind="stable").astype(np.int32))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_views", [1, 3])
+def test_fused_scan_emit_sort_equals_the_staged_binning(golden, n_views):
+    """frb_bin_sort_dev (scan + emit + sort histograms in one kernel, then the tile-bit passes; the whole-pass
+    forward uses it) gives the same instance count, sorted keys and Gaussian ids as the staged
+    frb_tile_offsets / frb_bin_emit / frb_radix_sort_pairs path, which the oracle pins bit for bit."""
+    import math
+    d = dev()
+    L = _lib.lib()
+    n1, W, H = 4111, 200, 136
+    inp = fo.synthetic_cloud(n1 * n_views, 31, 0.01, 0.06)
+    t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+    cams = [fresnel_b200.Camera(0.8 * W, 0.8 * W, W / 2 + 2 * v, H / 2 - v, W, H) for v in range(n_views)]
+    camv = np.stack([camera_vector(c, W, H) for c in cams])
+    b = build_bins(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"], camv, n_views, W, H,
+                   64.0, keep_debug=True, sort=True)
+    torch.cuda.synchronize()
+    n = n1 * n_views
+    cap = b.m + 1000
+    tiles = n_views * ((W + 15) // 16) * ((H + 15) // 16)
+    tile_bits = max(1, int(math.ceil(math.log2(max(tiles, 2)))))
+    keys = torch.empty(cap, dtype=torch.int64, device=d)
+    gids = torch.empty(cap, dtype=torch.int32, device=d)
+    keys_tmp, vals_tmp = torch.empty_like(keys), torch.empty_like(gids)
+    m_out = torch.zeros(1, dtype=torch.int32, device=d)
+    scan_ws = torch.empty(L.frb_scan_workspace_bytes(n), dtype=torch.uint8, device=d)
+    sort_ws = torch.empty(L.frb_sort_workspace_bytes(cap), dtype=torch.uint8, device=d)
+    _lib.check(L.frb_bin_sort_dev(n, n_views, W, H, _ptr(b.records), _ptr(b.depth_bits), _ptr(b.touched),
+                                  _ptr(b.order), cap, _ptr(m_out), _ptr(keys), _ptr(gids), _ptr(keys_tmp),
+                                  _ptr(vals_tmp), tile_bits, _ptr(scan_ws), _ptr(sort_ws), _stream()),
+               "frb_bin_sort_dev")
+    torch.cuda.synchronize()
+    assert int(m_out) == b.m and b.m > 1000
+    assert torch.equal(keys[:b.m], b.keys) and torch.equal(gids[:b.m], b.sorted_gids)
+
+
 @pytest.mark.parametrize("presort", [True, False])
 def test_tile_keys_bit_exact(golden, presort):
     """Sorted 64-bit (tile | depth) keys, Gaussian ids and tile ranges equal the oracle's, both via
