@@ -208,7 +208,7 @@ def run_wave(name, inp, cam, W, H, bg, per_channel, note=""):
     img_o, dep_o = fo.render_wave(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
                                   Lo["opacities"], cam, W, H, Lo["phases"], background=bg)
     ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
-    assert rel(img_o.detach(), img_r.detach()) < 2e-6 and rel(dep_o.detach(), dep_r.detach()) < 2e-5
+    assert rel(img_o.detach(), img_r.detach()) < 5e-6 and rel(dep_o.detach(), dep_r.detach()) < 2e-5   # summation order
     out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=64,
                image=img_r.detach().numpy(), depth=dep_r.detach().numpy(),
                gimage=gi.numpy(), gdepth=gd.numpy(), grad_source="reference", note=note)
@@ -432,6 +432,25 @@ def fx_wave():
     run_wave("wave_rgb_2k_128", inp3, cam, W, H, (0.1, 0.2, 0.3), True, note="(N,3) phases")
 
 
+def fx_wave_rot():
+    """WaveFieldRenderer on a non-square image (sides not multiples of the tile) seen by a rotated look-at camera,
+    per-channel phases."""
+    W, H = 112, 80
+    cam = fo.camera_from_pose(math.radians(25.0), math.radians(-50.0), 128)
+    cam.width, cam.height, cam.cx, cam.cy = W, H, W / 2, H / 2
+    inp = fo.synthetic_cloud(1500, seed=27, s_lo=0.01, s_hi=0.05, phase_hi=2 * math.pi)
+    inp["positions"][:, 2] += 2.0
+
+    def redraw(inp, idx, g):
+        inp["positions"][idx] = torch.randn(idx.numel(), 3, generator=g) * 0.5
+
+    inp = settle(inp, cam, W, H, 64, 27, redraw, allow_ties=True)
+    g = torch.Generator().manual_seed(28)
+    inp["phases"] = torch.rand(1500, 3, generator=g) * 2 * math.pi
+    run_wave("wave_rot_1500_112x80", inp, cam, W, H, (0.05, 0.2, 0.1), True,
+             note="look-at camera el 25 az -50, W=112 H=80, (N,3) phases")
+
+
 def fx_asm():
     W = H = 64
     cam = fo.default_camera(W)
@@ -440,6 +459,25 @@ def fx_asm():
     wl = torch.tensor([0.0635, 0.05, 0.041])
     run_asm("asm_1k_64", inp, cam, W, H, (0.05, 0.1, 0.15), wl, (0.1, 4.0),
             note="wavelengths_rgb=(0.0635,0.05,0.041), depth_range=(0.1,4.0), 16 planes")
+
+
+def fx_asm_rot():
+    """ASM on a non-square image whose sides are not multiples of the tile, rotated look-at camera: the frequency grids
+    of the propagator (fftfreq per axis, meshgrid 'xy', DR:1001-1008) and the ragged tile edges both differ from the
+    square default-camera fixture."""
+    W, H = 112, 80
+    cam = fo.camera_from_pose(math.radians(-15.0), math.radians(40.0), 128)
+    cam.width, cam.height, cam.cx, cam.cy = W, H, W / 2, H / 2
+    inp = fo.synthetic_cloud(1500, seed=23, s_lo=0.01, s_hi=0.05, phase_hi=2 * math.pi)
+    inp["positions"][:, 2] += 2.0            # cloud around the origin; the camera orbits at distance 2
+
+    def redraw(inp, idx, g):
+        inp["positions"][idx] = torch.randn(idx.numel(), 3, generator=g) * 0.5
+
+    inp = settle(inp, cam, W, H, 64, 23, redraw, allow_ties=True)
+    wl = torch.tensor([0.0635, 0.05, 0.041])
+    run_asm("asm_rot_1500_112x80", inp, cam, W, H, (0.15, 0.05, 0.1), wl, (0.1, 4.0),
+            note="look-at camera el -15 az 40, W=112 H=80, wavelengths_rgb=(0.0635,0.05,0.041), depth_range=(0.1,4.0)")
 
 
 def fx_dense():
@@ -503,7 +541,7 @@ def fx_simplified():
 
 
 FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
-                asm=fx_asm, c1=fx_c1)
+                wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, c1=fx_c1)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

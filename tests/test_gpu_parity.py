@@ -356,7 +356,7 @@ def _wave_inputs(z, d):
     return {k: torch.from_numpy(z["in_" + k]).to(d).requires_grad_(True) for k in names}
 
 
-@pytest.mark.parametrize("name", ["wave_scalar_2k_128", "wave_rgb_2k_128"])
+@pytest.mark.parametrize("name", ["wave_scalar_2k_128", "wave_rgb_2k_128", "wave_rot_1500_112x80"])
 def test_wave_renderer_matches_reference_golden(golden, name):
     """WaveFieldRenderer with (N,) and (N,3) phases: image, depth and all six gradients."""
     z = golden(name)
@@ -376,9 +376,11 @@ def test_wave_renderer_matches_reference_golden(golden, name):
         ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam)
 
 
-def test_asm_renderer_matches_reference_golden(golden):
-    """ASMWaveFieldRenderer (16 planes, cuFFT propagation with the fused transfer function)."""
-    z = golden("asm_1k_64")
+@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80"])
+def test_asm_renderer_matches_reference_golden(golden, fixture):
+    """ASMWaveFieldRenderer (16 planes, cuFFT propagation with the fused transfer function): the square default-camera
+    fixture and a 112x80 image (sides not multiples of the tile, H != W frequency grids) seen by a rotated camera."""
+    z = golden(fixture)
     d = dev()
     W, H = int(z["W"]), int(z["H"])
     cam = oracle_camera(z["cam"], W, H)

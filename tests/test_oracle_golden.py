@@ -63,7 +63,7 @@ def test_oracle_phase_forward_matches_reference(golden):
     assert rel(dep, z["depth"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["wave_scalar_2k_128", "wave_rgb_2k_128"])
+@pytest.mark.parametrize("name", ["wave_scalar_2k_128", "wave_rgb_2k_128", "wave_rot_1500_112x80"])
 def test_oracle_wave_matches_reference(golden, name):
     z = golden(name)
     W, H = int(z["W"]), int(z["H"])
@@ -76,8 +76,9 @@ def test_oracle_wave_matches_reference(golden, name):
     assert rel(dep, z["depth"]) < 5e-5
 
 
-def test_oracle_asm_matches_reference(golden):
-    z = golden("asm_1k_64")
+@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80"])
+def test_oracle_asm_matches_reference(golden, fixture):
+    z = golden(fixture)
     W, H = int(z["W"]), int(z["H"])
     cam = oracle_camera(z["cam"], W, H)
     L = golden_inputs(z, with_phases=True)
