@@ -420,6 +420,24 @@ def fx_phase():
              note="use_phase_blending=True; forward from the reference, gradients from the oracle clone restatement")
 
 
+def fx_phase_rot():
+    """Phase blending on a non-square image (sides not multiples of the tile), rotated look-at camera, coloured
+    background, amplitude 0.4."""
+    W, H = 112, 80
+    cam = fo.camera_from_pose(math.radians(10.0), math.radians(120.0), 128)
+    cam.width, cam.height, cam.cx, cam.cy = W, H, W / 2, H / 2
+    inp = fo.synthetic_cloud(1500, seed=29, s_lo=0.01, s_hi=0.06)
+    inp["positions"][:, 2] += 2.0
+
+    def redraw(inp, idx, g):
+        inp["positions"][idx] = torch.randn(idx.numel(), 3, generator=g) * 0.5
+
+    inp = settle(inp, cam, W, H, 64, 29, redraw)
+    run_tile("tile_phase_rot_1500_112x80", inp, cam, W, H, bg=(0.3, 0.1, 0.2), phase=True, amp=0.4,
+             note="use_phase_blending=True, amplitude 0.4, look-at camera el 10 az 120, W=112 H=80; forward from the "
+                  "reference, gradients from the oracle clone restatement")
+
+
 def fx_wave():
     W = H = 128
     cam = fo.default_camera(W)
@@ -540,7 +558,7 @@ def fx_simplified():
                    note="SimplifiedRenderer, look-at camera el 15 az -30; gradients for positions, colours, opacities")
 
 
-FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, wave=fx_wave,
+FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
                 wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, c1=fx_c1)
 
 if __name__ == "__main__":

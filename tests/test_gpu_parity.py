@@ -312,11 +312,12 @@ def test_full_size_properties_config2():
         assert rel(gr3[k], 2.0 * gra[k] - 0.5 * grb[k]) < 2e-5, k
 
 
+@pytest.mark.parametrize("fixture", ["tile_phase_2k_128", "tile_phase_rot_1500_112x80"])
 @pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
-def test_phase_blending_matches_reference_golden(golden, t_eps):
+def test_phase_blending_matches_reference_golden(golden, t_eps, fixture):
     """use_phase_blending=True: forward against the reference's own output, gradients against the
     oracle's .clone() restatement (the reference raises inside autograd on this path)."""
-    z = golden("tile_phase_2k_128")
+    z = golden(fixture)
     W, H = int(z["W"]), int(z["H"])
     inp = golden_inputs(z, with_phases=True)
     cam = oracle_camera(z["cam"], W, H)

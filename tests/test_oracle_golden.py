@@ -27,7 +27,7 @@ def test_oracle_tile_matches_reference_golden(golden, name):
         assert rel(g, z["grad_" + k]) < 1e-4, k
 
 
-@pytest.mark.parametrize("name", TILE_FIXTURES + ["c1_tile_16k_256", "tile_phase_2k_128"])
+@pytest.mark.parametrize("name", TILE_FIXTURES + ["c1_tile_16k_256", "tile_phase_2k_128", "tile_phase_rot_1500_112x80"])
 def test_oracle_pins_match_reference_pins(golden, name):
     """visible / rect / stable depth order derived from the REFERENCE's intermediates."""
     z = golden(name)
@@ -49,8 +49,9 @@ def test_oracle_pins_match_reference_pins(golden, name):
     assert int(ranges[-1, 1]) == keys.shape[0] or keys.shape[0] == 0 or ranges[:, 1].max() == keys.shape[0]
 
 
-def test_oracle_phase_forward_matches_reference(golden):
-    z = golden("tile_phase_2k_128")
+@pytest.mark.parametrize("fixture", ["tile_phase_2k_128", "tile_phase_rot_1500_112x80"])
+def test_oracle_phase_forward_matches_reference(golden, fixture):
+    z = golden(fixture)
     W, H = int(z["W"]), int(z["H"])
     cam = oracle_camera(z["cam"], W, H)
     L = golden_inputs(z, with_phases=True)
