@@ -411,6 +411,17 @@ def fx_culled():
     run_tile("tile_allculled_64", inp, cam, W, H, bg=(0.25, 0.5, 0.75), note="nothing visible (DR:545-552)")
 
 
+def fx_params():
+    """Non-default renderer / camera parameters: max_radius 24 (the cap is active for most Gaussians), near 1.4 and
+    far 2.6 (both planes cut through the cloud), fx != fy and an off-centre principal point."""
+    W, H = 96, 64
+    cam = fo.Camera(0.9 * W, 0.7 * W, W / 2 + 5.0, H / 2 - 3.0, W, H, 1.4, 2.6)
+    inp = fo.synthetic_cloud(1500, seed=37, s_lo=0.02, s_hi=0.15)
+    inp = settle(inp, cam, W, H, 24, 37, redraw_std)
+    run_tile("tile_params_1500_96x64", inp, cam, W, H, bg=(0.05, 0.1, 0.2), max_radius=24,
+             note="max_radius=24, near=1.4, far=2.6, fx=0.9W, fy=0.7W, principal point (W/2+5, H/2-3)")
+
+
 def fx_phase():
     W = H = 128
     cam = fo.default_camera(W)
@@ -558,7 +569,7 @@ def fx_simplified():
                    note="SimplifiedRenderer, look-at camera el 15 az -30; gradients for positions, colours, opacities")
 
 
-FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
+FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, params=fx_params, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
                 wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, c1=fx_c1)
 
 if __name__ == "__main__":

@@ -34,7 +34,8 @@ def bits_equal(a, b):
 
 def scene_cases(golden):
     out = []
-    for name in ("tile_edge_1k_96x80", "tile_rotcam_2k_144x120", "c1_tile_16k_256", "tile_allculled_64"):
+    for name in ("tile_edge_1k_96x80", "tile_rotcam_2k_144x120", "c1_tile_16k_256", "tile_allculled_64",
+                 "tile_params_1500_96x64"):
         z = golden(name)
         W, H = int(z["W"]), int(z["H"])
         out.append((name, golden_inputs(z), oracle_camera(z["cam"], W, H), W, H))
@@ -206,7 +207,7 @@ def render_gpu(z_or_inp, cam, W, H, bg, t_eps, max_radius=64, gimg=None, gdep=No
 
 @pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
 @pytest.mark.parametrize("name", ["tile_allculled_64", "tile_edge_1k_96x80", "tile_rotcam_2k_144x120",
-                                  "c1_tile_16k_256"])
+                                  "c1_tile_16k_256", "tile_params_1500_96x64"])
 def test_tile_renderer_matches_reference_golden(golden, name, t_eps):
     z = golden(name)
     W, H = int(z["W"]), int(z["H"])

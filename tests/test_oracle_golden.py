@@ -7,7 +7,7 @@ import torch
 from oracle import fresnel_oracle as fo
 from helpers import GRAD_NAMES, golden_inputs, oracle_camera, rel
 
-TILE_FIXTURES = ["tile_allculled_64", "tile_edge_1k_96x80", "tile_rotcam_2k_144x120"]
+TILE_FIXTURES = ["tile_allculled_64", "tile_edge_1k_96x80", "tile_rotcam_2k_144x120", "tile_params_1500_96x64"]
 
 
 @pytest.mark.parametrize("name", TILE_FIXTURES)
