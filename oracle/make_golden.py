@@ -221,11 +221,13 @@ def run_wave(name, inp, cam, W, H, bg, per_channel, note=""):
     print(f"{name}: wave ok, img max {float(img_r.max()):.3f}")
 
 
-def run_asm(name, inp, cam, W, H, bg, wl, depth_range, note=""):
+def run_asm(name, inp, cam, W, H, bg, wl, depth_range, note="", num_depth_planes=16, focal_depth=0.5,
+            pixel_pitch=1.0 / 256):
     gi, _ = upstream(H, W)
     rc = ref_camera(cam)
     names = GRAD_NAMES + ("phases",)
-    ren = dr.ASMWaveFieldRenderer(W, H, background=bg, depth_range=depth_range)
+    ren = dr.ASMWaveFieldRenderer(W, H, background=bg, depth_range=depth_range, num_depth_planes=num_depth_planes,
+                                  focal_depth=focal_depth, pixel_pitch=pixel_pitch)
     L = leafs(inp, names)
     img_r = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], rc,
                 phases=L["phases"], wavelengths_rgb=wl)
@@ -233,11 +235,13 @@ def run_asm(name, inp, cam, W, H, bg, wl, depth_range, note=""):
     Lo = leafs(inp, names)
     img_o, _ = fo.render_asm(Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"],
                              Lo["opacities"], cam, W, H, Lo["phases"], wl, background=bg,
-                             depth_range=depth_range)
+                             depth_range=depth_range, num_depth_planes=num_depth_planes, focal_depth=focal_depth,
+                             pixel_pitch=pixel_pitch)
     (img_o * gi).sum().backward()
     assert rel(img_o.detach(), img_r.detach()) < 5e-6
     out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=64,
-               wavelengths=wl.numpy(), depth_range=np.array(depth_range),
+               wavelengths=wl.numpy(), depth_range=np.array(depth_range), num_depth_planes=num_depth_planes,
+               focal_depth=focal_depth, pixel_pitch=pixel_pitch,
                image=img_r.detach().numpy(), gimage=gi.numpy(), grad_source="reference", note=note)
     for k in names:
         out["in_" + k] = inp[k].numpy()
@@ -509,6 +513,18 @@ def fx_asm_rot():
             note="look-at camera el -15 az 40, W=112 H=80, wavelengths_rgb=(0.0635,0.05,0.041), depth_range=(0.1,4.0)")
 
 
+def fx_asm_params():
+    """Non-default propagator parameters: 8 depth planes, focal depth 1.2, pixel pitch 1/128, other wavelengths."""
+    W, H = 80, 64
+    cam = fo.default_camera(W, H)
+    inp = fo.synthetic_cloud(1200, seed=41, s_lo=0.01, s_hi=0.05, phase_hi=2 * math.pi)
+    inp = settle(inp, cam, W, H, 64, 41, redraw_std, allow_ties=True)
+    wl = torch.tensor([0.07, 0.045, 0.03])
+    run_asm("asm_params_1200_80x64", inp, cam, W, H, (0.0, 0.1, 0.05), wl, (0.5, 3.0),
+            note="num_depth_planes=8, focal_depth=1.2, pixel_pitch=1/128, wavelengths (0.07,0.045,0.03), depth_range (0.5,3.0)",
+            num_depth_planes=8, focal_depth=1.2, pixel_pitch=1.0 / 128)
+
+
 def fx_dense():
     """DifferentiableGaussianRenderer: rotated look-at camera, some centres outside the image (100-px margin)."""
     W, H = 96, 80
@@ -570,7 +586,7 @@ def fx_simplified():
 
 
 FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, params=fx_params, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
-                wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, c1=fx_c1)
+                wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, asm_params=fx_asm_params, c1=fx_c1)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

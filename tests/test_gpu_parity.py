@@ -378,7 +378,7 @@ def test_wave_renderer_matches_reference_golden(golden, name):
         ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam)
 
 
-@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80"])
+@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80", "asm_params_1200_80x64"])
 def test_asm_renderer_matches_reference_golden(golden, fixture):
     """ASMWaveFieldRenderer (16 planes, cuFFT propagation with the fused transfer function): the square default-camera
     fixture and a 112x80 image (sides not multiples of the tile, H != W frequency grids) seen by a rotated camera."""
@@ -387,8 +387,12 @@ def test_asm_renderer_matches_reference_golden(golden, fixture):
     W, H = int(z["W"]), int(z["H"])
     cam = oracle_camera(z["cam"], W, H)
     L = _wave_inputs(z, d)
+    extra = {}                                   # non-default propagator parameters, when the fixture has them
+    if "num_depth_planes" in z:
+        extra = dict(num_depth_planes=int(z["num_depth_planes"]), focal_depth=float(z["focal_depth"]),
+                     pixel_pitch=float(z["pixel_pitch"]))
     ren = fresnel_b200.ASMWaveFieldRenderer(W, H, background=tuple(float(x) for x in z["bg"]),
-                                            depth_range=tuple(float(x) for x in z["depth_range"])).to(d)
+                                            depth_range=tuple(float(x) for x in z["depth_range"]), **extra).to(d)
     img = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
               phases=L["phases"], wavelengths_rgb=torch.from_numpy(z["wavelengths"]))
     assert rel(img.detach().cpu(), z["image"]) < IMG_TOL, rel(img.detach().cpu(), z["image"])

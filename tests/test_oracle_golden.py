@@ -77,16 +77,20 @@ def test_oracle_wave_matches_reference(golden, name):
     assert rel(dep, z["depth"]) < 5e-5
 
 
-@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80"])
+@pytest.mark.parametrize("fixture", ["asm_1k_64", "asm_rot_1500_112x80", "asm_params_1200_80x64"])
 def test_oracle_asm_matches_reference(golden, fixture):
     z = golden(fixture)
     W, H = int(z["W"]), int(z["H"])
     cam = oracle_camera(z["cam"], W, H)
     L = golden_inputs(z, with_phases=True)
+    extra = {}
+    if "num_depth_planes" in z:
+        extra = dict(num_depth_planes=int(z["num_depth_planes"]), focal_depth=float(z["focal_depth"]),
+                     pixel_pitch=float(z["pixel_pitch"]))
     with torch.no_grad():
         img, _ = fo.render_asm(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
                                W, H, L["phases"], torch.from_numpy(z["wavelengths"]),
-                               background=tuple(z["bg"]), depth_range=tuple(z["depth_range"]))
+                               background=tuple(z["bg"]), depth_range=tuple(z["depth_range"]), **extra)
     assert rel(img, z["image"]) < 1e-5
 
 
