@@ -130,3 +130,17 @@ def test_host_sessions_refuse_cpu_devices():
         HostRenderPipeline(r, 16, torch.device("cpu"))
     with pytest.raises(ValueError):
         HostRenderPipeline(r, 16, torch.device("cpu"), depth=0)
+
+
+def test_instance_capacity_rounding():
+    """renderer.instance_capacity: never below m, at most ~12.5 % (or 65,536 entries) above it, monotone, and constant
+    over the small drifts of an optimisation loop."""
+    from fresnel_b200.renderer import instance_capacity
+    assert instance_capacity(0) == 0 and instance_capacity(-5) == 0
+    prev = 0
+    for m in list(range(1, 2000, 37)) + [65535, 65536, 65537, 770_054, 5_820_000, 5_820_321, 10_000_000, 2**27 + 3]:
+        c = instance_capacity(m)
+        assert c >= m and c - m < max(65536, m // 8 + 1), (m, c)
+        assert c >= prev or m < 2000
+        prev = c
+    assert instance_capacity(5_820_000) == instance_capacity(5_820_321) == instance_capacity(5_900_000)
