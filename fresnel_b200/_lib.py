@@ -44,6 +44,9 @@ _SIGNATURES = {
                                     P, P, P, P]),
     "frb_tile_render_bwd": (c_int, [c_int, c_int, P, P, P, P, c_int, c_int, P, c_int, P, P, P, P, P, P, P, P, P, P,
                                     P]),
+    "frb_stage_timing_enable": (c_int, [c_int]),
+    "frb_stage_timing_count": (c_int, []),
+    "frb_stage_timing_get": (c_int, [c_int, P, P]),
     "frb_tile_schedule": (c_int, [c_int, P, P, P]),
     "frb_composite_fwd_sched": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd_sched": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P, P, P, P, P, P]),

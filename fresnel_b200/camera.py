@@ -84,9 +84,24 @@ def create_camera_from_pose(elevation_rad: float, azimuth_rad: float, render_siz
 def camera_vector(camera, width: int, height: int) -> np.ndarray:
     """The 20-float C-ABI camera (include/fresnel_b200.h): view rows 0..2, fx, fy, cx, cy,
     width, height, near, far.  ``width``/``height`` are the renderer's, as in the reference
-    (DR:541-543 cull against self.width / self.height, not the camera's)."""
-    view = camera.view_matrix.detach().to("cpu", torch.float32).numpy()
+    (DR:541-543 cull against self.width / self.height, not the camera's).
+
+    The reference moves ``camera.view_matrix`` to the device (DR:151); reading it back is a blocking
+    device->host copy (and illegal inside a stream capture), so the host copy of the 12 view floats is cached on the
+    camera object and reused while the matrix is the same tensor at the same version (in-place edits bump
+    ``_version``; ``set_view`` installs a new tensor)."""
+    vm = camera.view_matrix
+    key = (id(vm), getattr(vm, "_version", None))
+    hit = getattr(camera, "_frb_view_cache", None)
+    if hit is not None and hit[0] == key:
+        view12 = hit[1]
+    else:
+        view12 = vm.detach().to("cpu", torch.float32).numpy()[:3, :].reshape(-1).copy()
+        try:
+            camera._frb_view_cache = (key, view12, vm)      # vm kept alive: its id cannot be reused
+        except AttributeError:          # objects with __slots__: no cache
+            pass
     out = np.empty(20, np.float32)
-    out[:12] = view[:3, :].reshape(-1)
+    out[:12] = view12
     out[12:] = (camera.fx, camera.fy, camera.cx, camera.cy, width, height, camera.near, camera.far)
     return out

@@ -235,22 +235,58 @@ asm_finish_bwd_kernel(int n_views, int width, int height, const float2* __restri
 }
 
 // ---- cuFFT plan cache ------------------------------------------------------------------------
+// A cuFFT handle owns ONE work area and ONE stream binding, so a handle shared by two streams (two HostRenderPipeline
+// slots, two host threads) would race on both: the cache is keyed by the stream as well, and the stream is bound once,
+// when the plan is made.  The cache is bounded: when it is full the least recently used plan is destroyed (cufftDestroy
+// frees the work area, which synchronises the device - it only happens when a caller cycles through more than
+// MAX_PLANS distinct (stream, size) combinations).
 std::mutex g_plan_mutex;
-std::map<std::tuple<int, int, int, int>, cufftHandle> g_plans;   // (device, H, W, batch)
+struct PlanEntry { cufftHandle handle; unsigned long long last_use; };
+std::map<std::tuple<int, cudaStream_t, int, int, int>, PlanEntry> g_plans;   // (device, stream, H, W, batch)
+unsigned long long g_plan_clock = 0;
+constexpr size_t MAX_PLANS = 64;
 
-int get_plan(int height, int width, int batch, cufftHandle* out) {
+int get_plan(int height, int width, int batch, cudaStream_t st, cufftHandle* out) {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_plan_mutex);
-    auto key = std::make_tuple(dev, height, width, batch);
+    auto key = std::make_tuple(dev, st, height, width, batch);
     auto it = g_plans.find(key);
-    if (it != g_plans.end()) { *out = it->second; return 0; }
+    if (it != g_plans.end()) {
+        it->second.last_use = ++g_plan_clock;
+        *out = it->second.handle;
+        return 0;
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+        // no allocation inside a stream capture: re-bind a plan of the same shape made on another stream (the
+        // warm-up before a capture usually ran on one), as the capture serialises its use anyway
+        for (auto& kv : g_plans)
+            if (std::get<0>(kv.first) == dev && std::get<2>(kv.first) == height && std::get<3>(kv.first) == width &&
+                std::get<4>(kv.first) == batch) {
+                if (cufftSetStream(kv.second.handle, st) != CUFFT_SUCCESS) return FRB_E_INVALID;
+                PlanEntry e{kv.second.handle, ++g_plan_clock};
+                g_plans.erase(kv.first);
+                g_plans[key] = e;
+                *out = e.handle;
+                return 0;
+            }
+    }
+    if (g_plans.size() >= MAX_PLANS && cap == cudaStreamCaptureStatusNone) {
+        auto lru = g_plans.begin();
+        for (auto j = g_plans.begin(); j != g_plans.end(); ++j)
+            if (j->second.last_use < lru->second.last_use) lru = j;
+        cufftDestroy(lru->second.handle);
+        g_plans.erase(lru);
+    }
     cufftHandle h;
     int n[2] = {height, width};
     if (cufftPlanMany(&h, 2, n, nullptr, 1, height * width, nullptr, 1, height * width, CUFFT_C2C, batch) !=
         CUFFT_SUCCESS)
         return FRB_E_INVALID;
-    g_plans[key] = h;
+    if (cufftSetStream(h, st) != CUFFT_SUCCESS) { cufftDestroy(h); return FRB_E_INVALID; }
+    g_plans[key] = PlanEntry{h, ++g_plan_clock};
     *out = h;
     return 0;
 }
@@ -296,15 +332,13 @@ extern "C" int frb_asm_propagate_fwd(int n_views, int width, int height, int n_p
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cufftHandle big, small;
-    if ((rc = get_plan(height, width, n_views * n_planes * 3, &big))) return rc;
-    if ((rc = get_plan(height, width, n_views * 3, &small))) return rc;
-    if (cufftSetStream(big, st) != CUFFT_SUCCESS) return FRB_E_INVALID;
+    if ((rc = get_plan(height, width, n_views * n_planes * 3, st, &big))) return rc;
+    if ((rc = get_plan(height, width, n_views * 3, st, &small))) return rc;
     if (cufftExecC2C(big, (cufftComplex*)fields, (cufftComplex*)fields, CUFFT_FORWARD) != CUFFT_SUCCESS)
         return FRB_E_INVALID;
     const long long hw = (long long)width * height;
     asm_mul_sum_kernel<<<frb_div_up(hw * 3 * n_views, 256), 256, 0, st>>>(n_views, width, height, P,
                                                                            (const float2*)fields, (float2*)total);
-    if (cufftSetStream(small, st) != CUFFT_SUCCESS) return FRB_E_INVALID;
     if (cufftExecC2C(small, (cufftComplex*)total, (cufftComplex*)total, CUFFT_INVERSE) != CUFFT_SUCCESS)
         return FRB_E_INVALID;
     const float inv_n = 1.0f / (float)hw;
@@ -335,8 +369,8 @@ extern "C" int frb_asm_propagate_bwd(int n_views, int width, int height, int n_p
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cufftHandle big, small;
-    if ((rc = get_plan(height, width, n_views * n_planes * 3, &big))) return rc;
-    if ((rc = get_plan(height, width, n_views * 3, &small))) return rc;
+    if ((rc = get_plan(height, width, n_views * n_planes * 3, st, &big))) return rc;
+    if ((rc = get_plan(height, width, n_views * 3, st, &small))) return rc;
     const long long hw = (long long)width * height;
     const float inv_n = 1.0f / (float)hw;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
@@ -346,12 +380,10 @@ extern "C" int frb_asm_propagate_bwd(int n_views, int width, int height, int n_p
                                                        bg, g_image, red);
     asm_finish_bwd_kernel<<<frb_div_up(hw * n_views, 256), 256, 0, st>>>(
         n_views, width, height, (const float2*)total, inv_n, rmax_bits, bg, g_image, red, (float2*)g_total);
-    if (cufftSetStream(small, st) != CUFFT_SUCCESS) return FRB_E_INVALID;
     if (cufftExecC2C(small, (cufftComplex*)g_total, (cufftComplex*)g_total, CUFFT_FORWARD) != CUFFT_SUCCESS)
         return FRB_E_INVALID;
     asm_mul_conj_kernel<<<frb_div_up(hw * 3 * n_views, 256), 256, 0, st>>>(n_views, width, height, P,
                                                                             (const float2*)g_total, (float2*)d_fields);
-    if (cufftSetStream(big, st) != CUFFT_SUCCESS) return FRB_E_INVALID;
     if (cufftExecC2C(big, (cufftComplex*)d_fields, (cufftComplex*)d_fields, CUFFT_INVERSE) != CUFFT_SUCCESS)
         return FRB_E_INVALID;
     frb_note_launches(3);

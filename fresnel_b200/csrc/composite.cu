@@ -555,12 +555,8 @@ extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const i
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FRB_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(BwdSmem)));
-        attr_set = true;
-    }
+    static unsigned long long smem_opted_in = 0;          // per-device bitmask (the attribute is per device)
+    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel, (int)sizeof(BwdSmem), &smem_opted_in));
     frb_launch(composite_bwd_kernel, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem), (cudaStream_t)stream, 
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
         bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);

@@ -457,12 +457,8 @@ int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FRB_CUDA_OK(cudaFuncSetAttribute(composite_phase_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(PhaseBwdSmem)));
-        attr_set = true;
-    }
+    static unsigned long long smem_opted_in = 0;          // per-device bitmask
+    FRB_CUDA_OK(frb_opt_in_smem(composite_phase_bwd_kernel, (int)sizeof(PhaseBwdSmem), &smem_opted_in));
     composite_phase_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(PhaseBwdSmem), st>>>(
         width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, sorted_phases,
         phase_amplitude, bg, state_T, state_n, (const float2*)ckpt, g_image, g_depth, g_alpha, grad2d, g_phases);

@@ -33,6 +33,7 @@ int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs)
 void frb_note_launches(int k);
 
 static inline int frb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline bool frb_misaligned16(const void* p) { return ((uintptr_t)p & 15u) != 0; }   // NULL counts as aligned
 
 // Programmatic dependent launch (sm_90+): kernels of the render chain are launched with the programmatic stream
 // serialization attribute, so that the NEXT kernel's CTAs are scheduled (and run their prologue up to
@@ -42,6 +43,21 @@ static inline int frb_div_up(long long a, long long b) { return (int)((a + b - 1
 bool frb_pdl_enabled();
 
 #if defined(__CUDACC__)
+
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (one process may render
+// on several GPUs), so the "already done" state is a bitmask indexed by the current device, not a process-wide flag;
+// the mask is atomic because callers may launch from several host threads.
+template <typename K>
+static inline cudaError_t frb_opt_in_smem(K kernel, int bytes, unsigned long long* done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev < 64 && (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+    return e;
+}
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t frb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -5,7 +5,46 @@
 // The stage functions it sequences are the ones declared in include/fresnel_b200.h.
 #include "frb_common.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace {
+
+// ---- per-stage CUDA events INSIDE the whole-pass entry points (bench.py's roofline line) -----------------------
+// With timing enabled, frb_tile_render_fwd / _bwd bracket every stage they enqueue with a pair of events on the
+// caller's stream, so the stage times come from the same code path (same kernels, same buffers, same fused binning)
+// as the throughput figure.  Not for use inside a stream capture (events recorded in a capture cannot be timed).
+struct StageRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+std::mutex g_stage_mutex;
+std::vector<StageRec> g_stages;
+bool g_stage_timing = false;
+
+struct StageScope {
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const char* name;
+    bool on;
+    StageScope(const char* n, void* stream) : st((cudaStream_t)stream), name(n), on(g_stage_timing) {
+        if (!on) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    ~StageScope() {
+        if (!on) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lock(g_stage_mutex);
+        g_stages.push_back(StageRec{name, a, b});
+    }
+};
+#define FRB_STAGE(name, stream, expr)             \
+    do {                                          \
+        StageScope _scope(name, stream);          \
+        if ((rc = (expr))) return rc;             \
+    } while (0)
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -19,6 +58,32 @@ struct Carver {
 };
 
 }  // namespace
+
+extern "C" int frb_stage_timing_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    for (auto& r : g_stages) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_stages.clear();
+    g_stage_timing = on != 0;
+    return 0;
+}
+
+extern "C" int frb_stage_timing_count(void) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    return (int)g_stages.size();
+}
+
+// Name and duration of recorded stage i (waits for its closing event).
+extern "C" int frb_stage_timing_get(int i, const char** name, float* ms) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (i < 0 || i >= (int)g_stages.size() || !name || !ms) return FRB_E_INVALID;
+    FRB_CUDA_OK(cudaEventSynchronize(g_stages[i].b));
+    FRB_CUDA_OK(cudaEventElapsedTime(ms, g_stages[i].a, g_stages[i].b));
+    *name = g_stages[i].name;
+    return 0;
+}
 
 // Byte offsets inside the arenas.  persist: needed again by the backward pass.  scratch: forward only.
 extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_capacity, FrbTileLayout* L) {
@@ -74,16 +139,17 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
     int32_t* ranges = (int32_t*)(P + L.ranges);
     float* sorted_records = (float*)(P + L.sorted_records);
 
-    if ((rc = frb_project_fwd(n, n_views, positions, scales, rotations, colors, opacities, camera_host, max_radius,
-                              records, nullptr, depth_bits, touched, nullptr, stream))) return rc;
-    if ((rc = frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream))) return rc;
+    FRB_STAGE("frb_project_fwd", stream,
+              frb_project_fwd(n, n_views, positions, scales, rotations, colors, opacities, camera_host, max_radius,
+                              records, nullptr, depth_bits, touched, nullptr, stream));
+    FRB_STAGE("frb_depth_order", stream, frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream));
     if (n > 0 && m_capacity > 0) {
         if (tile_bits <= 16) {
             // scan of the tile counts, key emission and the sort histograms in one kernel (offsets[n] = M only)
-            if ((rc = frb_bin_sort_dev(n, n_views, width, height, records, depth_bits, touched, order, m_capacity,
+            FRB_STAGE("frb_bin_sort_dev", stream,
+                      frb_bin_sort_dev(n, n_views, width, height, records, depth_bits, touched, order, m_capacity,
                                        offsets + n, keys, gids, (uint64_t*)(S + L.keys_tmp),
-                                       (uint32_t*)(S + L.vals_tmp), tile_bits, S + L.scan_ws, S + L.sort_ws, stream)))
-                return rc;
+                                       (uint32_t*)(S + L.vals_tmp), tile_bits, S + L.scan_ws, S + L.sort_ws, stream));
         } else {
             if ((rc = frb_tile_offsets(n, touched, order, offsets, S + L.scan_ws, stream))) return rc;
             if ((rc = frb_bin_emit(n, n_views, width, height, records, depth_bits, order, offsets, keys, gids,
@@ -92,16 +158,19 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
                                                (uint32_t*)(S + L.vals_tmp), 32, 32 + tile_bits, S + L.sort_ws,
                                                stream))) return rc;
         }
-        if ((rc = frb_ranges_and_gather_dev(m_capacity, offsets + n, keys, gids, tiles, ranges, records,
-                                            sorted_records, nullptr, nullptr, stream))) return rc;
+        FRB_STAGE("frb_ranges_and_gather", stream,
+                  frb_ranges_and_gather_dev(m_capacity, offsets + n, keys, gids, tiles, ranges, records,
+                                            sorted_records, nullptr, nullptr, stream));
     } else {
         FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
     }
     int32_t* tile_order = (int32_t*)(P + L.tile_order);
-    if ((rc = frb_tile_schedule(tiles, ranges, tile_order, stream))) return rc;
-    return frb_composite_fwd_sched(n_views, width, height, tile_order, ranges, sorted_records, nullptr, 0.0f,
-                                   background_host, t_eps, image, depth, alpha, (float*)(P + L.state_T),
-                                   (int32_t*)(P + L.state_n), nullptr, stream);
+    FRB_STAGE("frb_tile_schedule", stream, frb_tile_schedule(tiles, ranges, tile_order, stream));
+    FRB_STAGE("frb_composite_fwd", stream,
+              frb_composite_fwd_sched(n_views, width, height, tile_order, ranges, sorted_records, nullptr, 0.0f,
+                                      background_host, t_eps, image, depth, alpha, (float*)(P + L.state_T),
+                                      (int32_t*)(P + L.state_n), nullptr, stream));
+    return 0;
 }
 
 // grad2d: scratch of n * FRB_GRAD_FLOATS floats (zeroed here).
@@ -117,12 +186,14 @@ extern "C" int frb_tile_render_bwd(int n, int n_views, const float* positions, c
     if (!persist || !grad2d) return FRB_E_INVALID;
     const char* P = (const char*)persist;
     FRB_CUDA_OK(cudaMemsetAsync(grad2d, 0, sizeof(float) * FRB_GRAD_FLOATS * (size_t)n, (cudaStream_t)stream));
-    if ((rc = frb_composite_bwd_sched(n_views, width, height, (const int32_t*)(P + L.tile_order),
-                                (const int32_t*)(P + L.ranges),
-                                (const float*)(P + L.sorted_records), (const uint32_t*)(P + L.sorted_gids), nullptr,
-                                0.0f, background_host, (const float*)(P + L.state_T),
-                                (const int32_t*)(P + L.state_n), nullptr, g_image, g_depth, g_alpha, grad2d, nullptr,
-                                stream))) return rc;
-    return frb_project_bwd(n, n_views, positions, scales, rotations, camera_host, grad2d, g_positions, g_scales,
-                           g_rotations, g_colors, g_opacities, stream);
+    FRB_STAGE("frb_composite_bwd", stream,
+              frb_composite_bwd_sched(n_views, width, height, (const int32_t*)(P + L.tile_order),
+                                      (const int32_t*)(P + L.ranges), (const float*)(P + L.sorted_records),
+                                      (const uint32_t*)(P + L.sorted_gids), nullptr, 0.0f, background_host,
+                                      (const float*)(P + L.state_T), (const int32_t*)(P + L.state_n), nullptr,
+                                      g_image, g_depth, g_alpha, grad2d, nullptr, stream));
+    FRB_STAGE("frb_project_bwd", stream,
+              frb_project_bwd(n, n_views, positions, scales, rotations, camera_host, grad2d, g_positions, g_scales,
+                              g_rotations, g_colors, g_opacities, stream));
+    return 0;
 }

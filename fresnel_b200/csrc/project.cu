@@ -134,6 +134,9 @@ extern "C" int frb_project_fwd_mode(int n, int n_views, const float* positions, 
     if (!positions || !scales || !rotations || !colors || !opacities || !records || !depth_bits ||
         !tiles_touched)
         return FRB_E_INVALID;
+    // read / written as 16-byte vectors: a misaligned pointer would fault on the device (sticky error)
+    if (frb_misaligned16(rotations) || frb_misaligned16(records) || frb_misaligned16(rects) || frb_misaligned16(debug))
+        return FRB_E_INVALID;
     frb_launch(frb_project_fwd_kernel, dim3(frb_div_up(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         n, vs, positions, scales, rotations, colors, opacities, max_radius, mode, (float4*)records,
         (int4*)rects, depth_bits, tiles_touched, (float4*)debug);
@@ -161,6 +164,7 @@ extern "C" int frb_project_bwd_mode(int n, int n_views, const float* positions, 
     if (n == 0) return 0;
     if (!positions || !scales || !rotations || !grad2d || !g_positions || !g_scales || !g_rotations)
         return FRB_E_INVALID;
+    if (frb_misaligned16(rotations) || frb_misaligned16(grad2d) || frb_misaligned16(g_rotations)) return FRB_E_INVALID;
     frb_launch(frb_project_bwd_kernel, dim3(frb_div_up(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         n, vs, positions, scales, rotations, (const float4*)grad2d, mode, g_positions, g_scales,
         (float4*)g_rotations, g_colors, g_opacities);

@@ -67,6 +67,36 @@ class StageTimer:
 _TIMER: Optional[StageTimer] = None
 
 
+class FusedStageTimer:
+    """Per-stage times of the WHOLE-PASS entry points (frb_tile_render_fwd / _bwd), measured by CUDA events the
+    library records between the stages it enqueues (csrc/pipeline.cu): the same code path as the throughput
+    figure, unlike StageTimer, which forces the stage-by-stage path.  Eager calls only (not inside a capture).
+
+        with FusedStageTimer() as t: ...render + backward...
+        t.summary() -> {stage: [ms, ...]}
+    """
+
+    def __enter__(self):
+        _lib.check(_lib.lib().frb_stage_timing_enable(1), "frb_stage_timing_enable")
+        return self
+
+    def __exit__(self, *exc):
+        self._out = self._read()
+        _lib.check(_lib.lib().frb_stage_timing_enable(0), "frb_stage_timing_enable")
+
+    def _read(self):
+        L = _lib.lib()
+        out = {}
+        name, ms = ctypes.c_char_p(), ctypes.c_float()
+        for i in range(L.frb_stage_timing_count()):
+            _lib.check(L.frb_stage_timing_get(i, ctypes.byref(name), ctypes.byref(ms)), "frb_stage_timing_get")
+            out.setdefault(name.value.decode(), []).append(float(ms.value))
+        return out
+
+    def summary(self):
+        return self._out
+
+
 def _call(name, fn, *args):
     if _TIMER is None:
         _lib.check(fn(*args), name)
@@ -96,7 +126,13 @@ def _check_inputs(**tensors):
             raise TypeError(f"{name} is on {t.device}, expected {dev}")
         if t.dtype != torch.float32:
             t = t.float()
-        out[name] = t.contiguous()
+        t = t.contiguous()
+        if t.data_ptr() % 16:
+            # the kernels read rotations (and write their gradient) as 16-byte vectors; a contiguous view into
+            # a flat buffer (torch.split, flat[a:b].view(n, 4)) may start at any float.  The reference accepts
+            # any tensor, so re-home it (a differentiable copy) instead of faulting on the device
+            t = t.clone()
+        out[name] = t
     return out
 
 

@@ -288,7 +288,7 @@ class DecoderTrainer:
     """
 
     def __init__(self, model: nn.Module, render_size: int, lr: float = 1e-4, stochastic_k: Optional[int] = None,
-                 seed: int = 0, weight_decay: float = 0.01, cuda_graph: bool = False):
+                 seed: int = 0, weight_decay: float = 1e-5, cuda_graph: bool = False):
         self.model = model
         self.render_size = render_size
         self.renderer = TileBasedRenderer(render_size, render_size)
@@ -336,6 +336,12 @@ class DecoderTrainer:
         static = [torch.empty_like(t) for t in (features, depth, images)]
         for s, t in zip(static, (features, depth, images)):
             s.copy_(t)
+        # The warm-up runs real steps (the allocator, cuBLAS workspaces and the optimiser state must exist before
+        # the capture), but it must not count as training: model, optimiser state and the RNG are put back
+        # afterwards, so cuda_graph=True and cuda_graph=False follow the same trajectory and Adam step count.
+        import copy
+        model_state = copy.deepcopy(self.model.state_dict())
+        rng_state = torch.cuda.get_rng_state(static[0].device)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                           # warm-up off the capture stream
@@ -345,6 +351,13 @@ class DecoderTrainer:
                 self._update()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            self.model.load_state_dict(model_state)
+            for st in self.optimizer.state.values():            # in place: the capture must see the same tensors
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        torch.cuda.set_rng_state(rng_state, static[0].device)
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
         from . import _lib

@@ -208,6 +208,14 @@ int frb_tile_render_bwd(int n, int n_views, const float* positions, const float*
                         float* g_positions, float* g_scales, float* g_rotations, float* g_colors,
                         float* g_opacities, void* stream);
 
+/* Per-stage timing of the whole-pass entry points (measurement aid, bench.py's roofline line): with timing
+ * enabled frb_tile_render_fwd / _bwd bracket every stage they enqueue with CUDA events on the caller's stream.
+ * frb_stage_timing_enable(on) clears what was recorded; _get(i) waits for stage i and returns its name (static
+ * string) and duration.  Do not enable inside a stream capture. */
+int frb_stage_timing_enable(int on);
+int frb_stage_timing_count(void);
+int frb_stage_timing_get(int i, const char** name, float* ms);
+
 /* ---- complex wave field: WaveFieldRenderer DR:747-926 ------------------------------------ */
 /* wc: 8 floats per Gaussian [colour_c cos(phi_c) x3, colour_c sin(phi_c) x3, 0, 0];
  * phases: n x phase_stride floats, phase_stride = 1 (scalar phase) or 3 (per channel), radians.

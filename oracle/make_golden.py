@@ -123,7 +123,9 @@ def rel(a, b):
 
 
 def run_tile(name, inp, cam, W, H, bg=(0.0, 0.0, 0.0), max_radius=64, phase=False, amp=0.25,
-             note=""):
+             note="", forward_only=False):
+    """forward_only: no gradients in the fixture (full-size phase-blending fixture: the clone restatement's tape
+    would need tens of GB); image / depth from the reference, oracle cross-checked under no_grad."""
     t0 = time.time()
     gi, gd = upstream(H, W)
     rc = ref_camera(cam)
@@ -152,13 +154,16 @@ def run_tile(name, inp, cam, W, H, bg=(0.0, 0.0, 0.0), max_radius=64, phase=Fals
         order = torch.argsort(dep).numpy().astype(np.int32)
     # oracle
     Lo = leafs(inp, GRAD_NAMES + (("phases",) if phase else ()))
-    img_o, dep_o, alpha_o = fo.render_tile_based(
-        Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"], Lo["opacities"], cam, W, H,
-        background=bg, max_radius=max_radius, use_phase_blending=phase, phase_amplitude=amp,
-        phases=Lo["phases"] if phase else None)
-    ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
-    grads_o = {k: (Lo[k].grad if Lo[k].grad is not None else torch.zeros_like(Lo[k])).numpy()
-               for k in GRAD_NAMES + (("phases",) if phase else ())}
+    with torch.set_grad_enabled(not forward_only):
+        img_o, dep_o, alpha_o = fo.render_tile_based(
+            Lo["positions"], Lo["scales"], Lo["rotations"], Lo["colors"], Lo["opacities"], cam, W, H,
+            background=bg, max_radius=max_radius, use_phase_blending=phase, phase_amplitude=amp,
+            phases=Lo["phases"] if phase else None)
+    grads_o = {}
+    if not forward_only:
+        ((img_o * gi).sum() + (dep_o * gd).sum()).backward()
+        grads_o = {k: (Lo[k].grad if Lo[k].grad is not None else torch.zeros_like(Lo[k])).numpy()
+                   for k in GRAD_NAMES + (("phases",) if phase else ())}
     pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, max_radius)
 
     # cross-checks: oracle vs reference
@@ -176,7 +181,7 @@ def run_tile(name, inp, cam, W, H, bg=(0.0, 0.0, 0.0), max_radius=64, phase=Fals
             worst = max(worst, e)
         grads, src = grads_r, "reference"
     else:
-        grads, src = grads_o, "oracle_clone"
+        grads, src = grads_o, ("none" if forward_only else "oracle_clone")
 
     out = dict(cam=cam_vec(cam), W=W, H=H, bg=np.array(bg, np.float32), max_radius=max_radius,
                phase_blending=int(phase), phase_amplitude=amp,
@@ -585,14 +590,93 @@ def fx_simplified():
                    note="SimplifiedRenderer, look-at camera el 15 az -30; gradients for positions, colours, opacities")
 
 
+def fx_overlap():
+    """>= 700 overlapping Gaussians per pixel ("re-check product-form transmittance at ~700 overlaps/px"):
+    20,000 big Gaussians on a 128x128 image.  The reference keeps the SUM form of the accumulated alpha
+    (DR:647-658: contribution = alpha * (1 - accumulated_alpha)); the kernels carry the transmittance as a product.
+    Two opacity regimes: the standard U(0.1, 0.9) (the transmittance dies after a few dozen entries, so the tail
+    probes the sum form's quantisation of 1 - A near 1) and a faint one (x 0.04: hundreds of entries contribute)."""
+    W = H = 128
+    cam = fo.default_camera(W)
+    for name, seed, k in (("tile_overlap_20k_128", 43, 1.0), ("tile_overlap_faint_20k_128", 47, 0.04)):
+        inp = fo.synthetic_cloud(20000, seed=seed, s_lo=0.05, s_hi=0.15)
+        inp["opacities"] = inp["opacities"] * k
+        inp = settle(inp, cam, W, H, 64, seed, redraw_std)
+        run_tile(name, inp, cam, W, H, bg=(0.1, 0.2, 0.3),
+                 note=f"20k Gaussians, scales U(0.05,0.15), opacities U(0.1,0.9)*{k}: ~1000 rectangle overlaps per pixel")
+
+
+def zone_snap_cloud(n, seed, num_zones=8, s_lo=0.005, s_hi=0.03):
+    """BASELINE configs[3] inputs: the synthetic cloud with the decoder-side Fresnel treatment applied -
+    depth snapped to the centre of its zone by the REFERENCE's FresnelZones.get_zone_centers_for_depth
+    (gaussian_decoder_models.py:833-841: base_z = offset + zone_centre * (-2)), i.e. only `num_zones` distinct depths
+    (massive exact ties), and the edge-aware modulation of gaussian_decoder_models.py:881-895 (scales shrunk by up to
+    50 %, opacity boosted by up to 0.2 and clamped) with a seeded per-Gaussian edge strength."""
+    from utils.fresnel_zones import FresnelZones
+    inp = fo.synthetic_cloud(n, seed=seed, s_lo=s_lo, s_hi=s_hi)
+    zones = FresnelZones(num_zones=num_zones, depth_range=(0.0, 1.0))
+    d01 = ((-inp["positions"][:, 2]) - 1.0) / 2.0                    # camera depth 1..3 -> 0..1
+    zc = zones.get_zone_centers_for_depth(d01)
+    inp["positions"][:, 2] = -1.0 + zc * (-2.0)
+    g = torch.Generator().manual_seed(seed + 500)
+    edge = torch.rand(n, generator=g) ** 2
+    inp["scales"] = inp["scales"] * (1.0 - 0.5 * edge).unsqueeze(-1)
+    inp["opacities"] = torch.clamp(inp["opacities"] + 0.2 * edge, 0, 1)
+    return inp
+
+
+def redraw_xy(inp, idx, g):
+    inp["positions"][idx, :2] = torch.randn(idx.numel(), 2, generator=g) * 0.5
+
+
+def fx_c4_small():
+    """configs[3] at a size whose gradients the oracle clone restatement finishes quickly: 20k @ 256^2, 8 zones."""
+    W = H = 256
+    cam = fo.default_camera(W)
+    inp = zone_snap_cloud(20000, 53)
+    inp = settle(inp, cam, W, H, 64, 53, redraw_xy, allow_ties=True)
+    assert np.unique(inp["positions"][:, 2].numpy()).size <= 8
+    run_tile("c4_zones_phase_20k_256", inp, cam, W, H, phase=True, amp=0.25,
+             note="configs[3] inputs (8 Fresnel depth zones => exact depth ties, edge-aware scales / opacities), "
+                  "use_phase_blending=True; forward from the reference, gradients from the oracle clone restatement")
+    run_tile("c4_zones_tile_20k_256", inp, cam, W, H, phase=False,
+             note="same inputs without phase blending: forward and gradients from the reference")
+
+
+def fx_c2():
+    """BASELINE configs[1] at full size: 100,000 Gaussians, 512x512, fwd + bwd of the unmodified reference."""
+    W = H = 512
+    cam = fo.default_camera(W)
+    inp = fo.synthetic_cloud(100000, seed=0)
+    inp = settle(inp, cam, W, H, 64, 0, redraw_std)
+    run_tile("c2_tile_100k_512", inp, cam, W, H, note="config 2 (BASELINE configs[1]) at full size")
+
+
+def fx_c4():
+    """BASELINE configs[3] at full size: 200,000 Gaussians, 512x512, 8 zones, edge-aware inputs, phase blending."""
+    W = H = 512
+    cam = fo.default_camera(W)
+    inp = zone_snap_cloud(200000, 59)
+    inp = settle(inp, cam, W, H, 64, 59, redraw_xy, allow_ties=True)
+    run_tile("c4_zones_phase_200k_512", inp, cam, W, H, phase=True, amp=0.25,
+             note="configs[3] at full size; forward from the reference (no gradients in this fixture: they are "
+                  "pinned by c4_zones_phase_20k_256)", forward_only=True)
+
+
 FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, params=fx_params, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
-                wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, asm_params=fx_asm_params, c1=fx_c1)
+                wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, asm_params=fx_asm_params, c1=fx_c1, overlap=fx_overlap,
+                c4_small=fx_c4_small)
+# full-size fixtures: tens of minutes of CPU each, only with --only
+BIG = dict(c2=fx_c2, c4=fx_c4)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     a = ap.parse_args()
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(a.threads)
+    if a.only in BIG:
+        BIG[a.only]()
     for k, f in FIXTURES.items():
         if a.only in (None, k):
             f()

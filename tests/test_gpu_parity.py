@@ -224,6 +224,57 @@ def test_tile_renderer_matches_reference_golden(golden, name, t_eps):
         assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
 
 
+@pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
+@pytest.mark.parametrize("name", ["c2_tile_100k_512", "tile_overlap_20k_128", "tile_overlap_faint_20k_128",
+                                  "c4_zones_tile_20k_256"])
+def test_tile_renderer_matches_reference_golden_at_named_sizes(golden, name, t_eps):
+    """The unmodified reference's own forward + backward at the sizes BASELINE names and at the depth complexity
+    SURVEY A.4 asks to re-check: configs[1] in full (100,000 Gaussians, 512x512, ~355 overlaps per pixel), two
+    scenes with ~1000 rectangle overlaps per pixel (the reference keeps 1 - sum(c) where the kernels carry a
+    product, DR:647-658) and the configs[3] inputs (8 depth zones: every depth is one of eight values, so the
+    order is decided by the stable tie rule alone).  Same 1e-5 / 1e-4 bars as the small fixtures."""
+    z = golden(name)
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z)
+    cam = oracle_camera(z["cam"], W, H)
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, tuple(float(x) for x in z["bg"]), t_eps,
+                                        int(z["max_radius"]), torch.from_numpy(z["gimage"]),
+                                        torch.from_numpy(z["gdepth"]))
+    assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
+    assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
+    assert rel(alpha, z["alpha"]) < IMG_TOL, rel(alpha, z["alpha"])
+    for k in GRAD_NAMES:
+        assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
+
+
+def test_binning_matches_reference_pins_at_config2_size(golden):
+    """Bit-exact integer work at BASELINE configs[1] size: visibility, rectangles and the stable depth order are the
+    ones derived from the REFERENCE's intermediates (fixture), the sorted (tile | depth) keys / ids / ranges are the
+    oracle's."""
+    d = dev()
+    z = golden("c2_tile_100k_512")
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z)
+    cam = oracle_camera(z["cam"], W, H)
+    t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+    b = build_bins(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"],
+                   camera_vector(cam, W, H)[None], 1, W, H, 64.0, keep_debug=True, sort=True)
+    torch.cuda.synchronize()
+    vis = z["visible"]
+    rects = b.rects.cpu().numpy()
+    vi = np.nonzero(vis)[0]
+    r = z["rect"][vi].copy()
+    r[(r[:, 0] >= r[:, 1]) | (r[:, 2] >= r[:, 3])] = 0
+    assert np.array_equal(rects[vi], r) and np.all(rects[~vis] == 0)
+    o = b.order.cpu().numpy()
+    assert np.array_equal(o[vis[o]], z["order"][vis[z["order"]]])
+    pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, 64)
+    assert b.m == pn["keys"].shape[0]
+    assert np.array_equal(b.keys.cpu().numpy().view(np.uint64), pn["keys"])
+    assert np.array_equal(b.sorted_gids.cpu().numpy(), pn["gids"])
+    assert np.array_equal(b.ranges.cpu().numpy(), pn["ranges"])
+
+
 def test_tile_renderer_matches_oracle_fresh_scene():
     """Seeded scene not in the fixtures, oracle run live on the CPU (a few seconds)."""
     W, H = 120, 88
@@ -326,6 +377,26 @@ def test_phase_blending_matches_reference_golden(golden, t_eps, fixture):
                                         int(z["max_radius"]), torch.from_numpy(z["gimage"]),
                                         torch.from_numpy(z["gdepth"]), phases=True,
                                         amp=float(z["phase_amplitude"]))
+    assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
+    assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
+    assert rel(alpha, z["alpha"]) < IMG_TOL
+    for k in GRAD_NAMES + ("phases",):
+        assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
+
+
+@pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
+def test_phase_blending_config4_zone_inputs(golden, t_eps):
+    """BASELINE configs[3] inputs at 20k / 256x256: depths snapped to 8 Fresnel zones by the reference's FresnelZones
+    (exact depth ties everywhere), edge-aware scales / opacities, use_phase_blending=True.  Forward against the
+    reference's output, gradients against the oracle clone restatement."""
+    z = golden("c4_zones_phase_20k_256")
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z, with_phases=True)
+    assert np.unique(z["in_positions"][:, 2]).size <= 8
+    cam = oracle_camera(z["cam"], W, H)
+    img, dep, alpha, grads = render_gpu(inp, cam, W, H, tuple(float(x) for x in z["bg"]), t_eps,
+                                        int(z["max_radius"]), torch.from_numpy(z["gimage"]),
+                                        torch.from_numpy(z["gdepth"]), phases=True, amp=float(z["phase_amplitude"]))
     assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
     assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
     assert rel(alpha, z["alpha"]) < IMG_TOL

@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""Prints the measured parity margins the GPU tests assert on (run on a B200): how far each output of the CUDA path
+is from the golden vectors, so tolerances are set from measurements and not loosened blindly."""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fresnel_b200  # noqa: E402
+from helpers import GRAD_NAMES, oracle_camera, rel  # noqa: E402
+from oracle import fresnel_oracle as fo  # noqa: E402
+
+d = torch.device("cuda:0")
+out = {}
+
+
+def gold(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+for name in ("wave_scalar_2k_128", "wave_rgb_2k_128", "wave_rot_1500_112x80"):
+    z = gold(name)
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = {k: torch.from_numpy(z["in_" + k]).to(d) for k in GRAD_NAMES + ("phases",)}
+    ren = fresnel_b200.WaveFieldRenderer(W, H, background=tuple(float(x) for x in z["bg"]))
+    img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, return_depth=True,
+                   phases=L["phases"])
+    e = np.abs(dep.cpu().numpy().astype(np.float64) - z["depth"])
+    i = np.unravel_index(e.argmax(), e.shape)
+    row = {"image": rel(img.cpu(), z["image"]), "depth": rel(dep.cpu(), z["depth"]),
+           "worst_px": [int(i[0]), int(i[1])], "gpu": float(dep[i]), "ref": float(z["depth"][i])}
+    if "depth64" in z:
+        row["depth_vs_f64"] = rel(dep.cpu(), z["depth64"])
+        row["ref32_vs_f64"] = rel(z["depth"], z["depth64"])
+    out[name] = row
+
+# config-4 / config-5 sized permutation checks on tie-free clouds
+def unique_depth_cloud(n, **kw):
+    inp = fo.synthetic_cloud(n, **kw)
+    z = inp["positions"][:, 2].clone()
+    for _ in range(20):
+        b = z.numpy().view(np.int32)
+        _, first = np.unique(b, return_index=True)
+        dup = np.ones(n, bool); dup[first] = False
+        if not dup.any():
+            break
+        z[torch.from_numpy(dup)] += (torch.rand(int(dup.sum())) - 0.5) * 1e-3
+    inp["positions"][:, 2] = z
+    return inp
+
+
+def tile(inp, cam, W, H, phases):
+    ren = fresnel_b200.TileBasedRenderer(W, H, background=(0.1, 0.0, 0.2), use_phase_blending=phases, t_eps=0.0)
+    L = {k: v.to(d) for k, v in inp.items()}
+    img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, return_depth=True,
+                   phases=L["phases"] if phases else None)
+    return img.cpu().numpy(), dep.cpu().numpy()
+
+
+g = torch.Generator().manual_seed(1)
+inp = unique_depth_cloud(200_000, seed=0)
+cam = fo.default_camera(512)
+perm = torch.randperm(200_000, generator=g)
+i0, d0 = tile(inp, cam, 512, 512, True)
+i1, d1 = tile({k: v[perm] for k, v in inp.items()}, cam, 512, 512, True)
+out["c4_permutation_tie_free"] = {"image_equal": bool(np.array_equal(i0, i1)), "depth_equal": bool(np.array_equal(d0, d1)),
+                                  "image": rel(i1, i0), "depth": rel(d1, d0)}
+
+W = H = 1024
+N = 1_000_000
+inp = fo.synthetic_cloud(N, seed=0, s_lo=0.002, s_hi=0.012, phase_hi=2 * math.pi)
+inp["positions"][:, 2] += 2.0
+cam = fresnel_b200.create_camera_from_pose(0.0, math.radians(45.0), W)
+ren = fresnel_b200.ASMWaveFieldRenderer(W, H, depth_range=(0.1, 4.0)).to(d)
+wl = torch.tensor([0.0635, 0.05, 0.041])
+
+
+def asm(cloud):
+    L = {k: v.to(d) for k, v in cloud.items()}
+    return ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, phases=L["phases"],
+               wavelengths_rgb=wl).cpu().numpy()
+
+
+a0 = asm(inp)
+a0b = asm(inp)
+perm = torch.randperm(N, generator=g)
+a1 = asm({k: v[perm] for k, v in inp.items()})
+out["c5_asm"] = {"run_to_run_equal": bool(np.array_equal(a0, a0b)), "run_to_run": rel(a0b, a0),
+                 "permutation": rel(a1, a0)}
+print(json.dumps(out, indent=1))
