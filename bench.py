@@ -632,6 +632,78 @@ def run_multiview_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------
+# Fourth workload (BASELINE.json configs[3]): Fresnel-zone + edge-aware + phase-blending render, fwd + bwd
+# --------------------------------------------------------------------------------------
+C4_METRIC = "Fresnel-zone + edge-aware + phase-blending render fwd+bwd frames/sec (8 zones, 200k Gaussians, 512x512)"
+C4_N = 200_000
+
+
+def c4_cloud(n, seed):
+    """configs[3] inputs (same recipe as oracle/make_golden.py zone_snap_cloud): the synthetic cloud with the
+    decoder-side Fresnel treatment applied - depth snapped to the centre of one of 8 zones
+    (gaussian_decoder_models.py:833-841: only eight distinct depths, i.e. massive exact ties for the stable order),
+    scales shrunk / opacities boosted by a seeded edge strength (:881-895) - plus a phase per Gaussian."""
+    from fresnel_b200.zones import FresnelZones
+    c = synthetic_cloud(n, seed)
+    zones = FresnelZones(num_zones=8, depth_range=(0.0, 1.0))
+    d01 = ((-c["positions"][:, 2]) - 1.0) / 2.0
+    c["positions"][:, 2] = -1.0 + zones.get_zone_centers_for_depth(d01) * (-2.0)
+    g = torch.Generator().manual_seed(seed + 500)
+    edge = torch.rand(n, generator=g) ** 2
+    c["scales"] = c["scales"] * (1.0 - 0.5 * edge).unsqueeze(-1)
+    c["opacities"] = torch.clamp(c["opacities"] + 0.2 * edge, 0, 1)
+    c["phases"] = torch.rand(n, generator=g)
+    return c
+
+
+def measure_phase(args, rank, world, dev, steps, flush):
+    """configs[3]: TileBasedRenderer(use_phase_blending=True) on the zone-snapped, edge-modulated cloud; one view per
+    rank, forward + backward with upstream gradients for image and depth (six gradients: the phases too)."""
+    import fresnel_b200
+    from fresnel_b200 import _lib
+    from fresnel_b200.renderer import StageTimer
+    L = _lib.lib()
+    ren = fresnel_b200.TileBasedRenderer(RES, RES, use_phase_blending=True, phase_amplitude=0.25)
+    cam = fresnel_b200.Camera(0.8 * RES, 0.8 * RES, RES / 2, RES / 2, RES, RES)
+    cloud = {k: v.to(dev).requires_grad_(True) for k, v in c4_cloud(C4_N, seed=rank).items()}
+    gi_h, gd_h = upstream(1 + rank)
+    gi, gd = gi_h.to(dev), gd_h.to(dev)
+
+    def step():
+        for v in cloud.values():
+            v.grad = None
+        img, dep = ren(cloud["positions"], cloud["scales"], cloud["rotations"], cloud["colors"], cloud["opacities"],
+                       cam, return_depth=True, phases=cloud["phases"])
+        torch.autograd.backward((img, dep), (gi, gd))
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    _barrier(world)
+    l0 = L.frb_launch_count()
+    ms = _timed_steps(step, steps, flush)
+    launches = L.frb_launch_count() - l0
+    _barrier(world)
+    with StageTimer() as st:
+        _timed_steps(step, max(3, min(steps, 10)), flush)
+    stage_ms = {k: sum(v) / len(v) for k, v in st.summary().items()}
+    (tot_ms,) = _max_over_ranks([sum(ms)], dev, world)
+    with torch.no_grad():
+        depths = torch.unique(cloud["positions"][:, 2]).numel()
+    return {"metric": C4_METRIC, "value": world * steps / (tot_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "weak",
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"phase-blending render fwd+bwd, {C4_N} Gaussians, {RES}x{RES}, 8 Fresnel depth "
+                                   "zones + edge-aware scales / opacities applied to the inputs (BASELINE configs[3]); "
+                                   "one view per rank, eager calls (one 4-byte device->host read per frame sizes the "
+                                   "instance buffers)",
+                       "distinct_depths": int(depths),
+                       "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed"},
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
+            "gpu_launches": int(launches)}
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 def main():
@@ -869,6 +941,8 @@ def main():
         torch.cuda.empty_cache()
         w_steps = max(5, min(args.steps, 20))
         workloads["train"] = measure_train(args, rank, world, dev, False, args.steps, flush)
+        torch.cuda.empty_cache()
+        workloads["phase"] = measure_phase(args, rank, world, dev, w_steps, flush)
         torch.cuda.empty_cache()
         workloads["multiview"] = measure_multiview(args, rank, world, dev, "peer", w_steps, flush, stages=True)
         if world > 1:

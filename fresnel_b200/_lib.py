@@ -29,6 +29,7 @@ _SIGNATURES = {
     "frb_ranges_and_gather_dev": (c_int, [c_int, P, P, P, c_int, P, P, P, P, P, P]),
     "frb_depth_order_workspace_bytes": (c_size_t, [c_int]),
     "frb_depth_order": (c_int, [c_int, P, P, P, P]),
+    "frb_depth_order_rank": (c_int, [c_int, P, P, P, P, P]),
     "frb_scan_workspace_bytes": (c_size_t, [c_int]),
     "frb_tile_offsets": (c_int, [c_int, P, P, P, P, P]),
     "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
@@ -44,6 +45,13 @@ _SIGNATURES = {
                                     P, P, P, P]),
     "frb_tile_render_bwd": (c_int, [c_int, c_int, P, P, P, P, c_int, c_int, P, c_int, P, P, P, P, P, P, P, P, P, P,
                                     P]),
+    "frb_tile_lists_max_gaussians": (c_int, []),
+    "frb_tile_lists_max_tiles": (c_int, []),
+    "frb_tile_lists_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "frb_tile_count": (c_int, [c_int, c_int, c_int, c_int, P, P, P]),
+    "frb_tile_scan": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "frb_tile_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
+    "frb_tile_rank_gather": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
     "frb_stage_timing_enable": (c_int, [c_int]),
     "frb_stage_timing_count": (c_int, []),
     "frb_stage_timing_get": (c_int, [c_int, P, P]),
@@ -64,9 +72,15 @@ _SIGNATURES = {
     "frb_decode_head_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, c_float, P, c_int, P, P, P, P, P, P]),
     "frb_decode_head_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, c_float, c_float, P, c_int, P, P, P, P, P, P,
                                     P, P]),
+    "frb_decode_head_fwd_ex": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P]),
+    "frb_decode_head_bwd_ex": (c_int, [c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P, P, P, P, P, P]),
     "frb_recon_loss_workspace_bytes": (c_size_t, []),
     "frb_recon_loss_fwd": (c_int, [ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float, c_float, P, P, P]),
     "frb_recon_loss_bwd": (c_int, [ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float, c_float, P, P, P, P, P]),
+    "frb_recon_loss_fwd_ex": (c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float,
+                                      c_float, c_float, c_int, P, c_float, c_int, P, P, P]),
+    "frb_recon_loss_bwd_ex": (c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float,
+                                      c_float, c_float, c_int, P, c_float, c_int, P, P, P, P, P]),
     "frb_composite_fwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, c_float, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P, P,
                                       P]),
@@ -91,7 +105,14 @@ class TileLayout(ctypes.Structure):
     _fields_ = [(name, c_size_t) for name in (
         "ranges", "tile_order", "state_T", "state_n", "sorted_gids", "sorted_records", "persist_bytes", "records", "depth_bits",
         "touched", "order", "offsets", "depth_ws", "scan_ws", "keys", "keys_tmp", "vals_tmp", "sort_ws",
-        "scratch_bytes")]
+        "tile_ws", "inst_rank", "rank", "scratch_bytes")]
+
+
+class HeadExtras(ctypes.Structure):
+    """FrbHeadExtras of include/fresnel_b200.h."""
+    _fields_ = [("edge", c_void_p), ("edge_scale_factor", c_float), ("edge_opacity_boost", c_float),
+                ("num_zones", c_int), ("zone_boundaries_host", c_void_p), ("zone_centers_host", c_void_p),
+                ("pose_trig", c_void_p)]
 
 
 class FresnelB200Error(RuntimeError):

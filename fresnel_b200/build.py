@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libfresnel_b200.so")
 OBJ_DIR = os.path.join(CSRC, "build")
 
-SOURCES = ["project.cu", "sort.cu", "composite.cu", "composite_phase.cu", "wave.cu", "asm.cu", "fourier.cu", "io.cu", "head.cu", "loss.cu", "simple.cu", "exchange.cu", "pipeline.cu"]
+SOURCES = ["project.cu", "sort.cu", "tile_lists.cu", "composite.cu", "composite_phase.cu", "wave.cu", "asm.cu", "fourier.cu", "io.cu", "head.cu", "loss.cu", "simple.cu", "exchange.cu", "pipeline.cu"]
 HEADERS = ["frb_math.h", "frb_head.h", "frb_common.cuh", "composite_common.cuh", os.path.join(ROOT, "include", "fresnel_b200.h")]
 
 NVCC_FLAGS = [

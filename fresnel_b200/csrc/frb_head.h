@@ -5,7 +5,9 @@
  * against autograd of the PyTorch restatement (fresnel_b200/training.py), without a GPU.
  *
  * Reference (GM = scripts/models/gaussian_decoder_models.py):
- *   DirectPatchDecoder.forward tail GM:807-948 with default flags plus the edge-aware modulation GM:881-895
+ *   DirectPatchDecoder.forward tail GM:807-948: grid + offset positions, Fresnel zone snap of the depth GM:833-838,
+ *   pose rotation GM:51-104 / GM:860, softplus scales, 6D rotations, sigmoid colour / opacity and the edge-aware
+ *   modulation GM:881-895
  *   rotation_6d_to_quaternion GM:186-276 (the +-1e-8 random sign jitter of GM:208 is a fixed +1e-8)
  * Raw layout (GM:795-800): [0:3] position offset (z unused: depth is locked, GM:844-850), [3:6] scale,
  * [6:12] 6D rotation, [12:15] colour, [15] opacity.
@@ -188,6 +190,34 @@ FRB_HEAD_HD void frb_rot6d_to_quat_bwd(const float r6[6], const float gq[4], flo
     for (int k = 0; k < 3; ++k) { g_r6[k] = g_a1[k]; g_r6[3 + k] = g_a2[k]; }
 }
 
+/* Fresnel zone snap, GM:833-838 with FresnelZones.get_zone_centers_for_depth (utils/fresnel_zones.py:96-139):
+ * clamp to the depth range, zone index = number of INTERIOR boundaries below the value (torch.bucketize, right =
+ * False), result = that zone's centre.  boundaries: num_zones + 1 values, centers: num_zones values. */
+FRB_HEAD_HD float frb_zone_center(float d, const float* boundaries, const float* centers, int num_zones) {
+    const float lo = boundaries[0], hi = boundaries[num_zones];
+    d = d < lo ? lo : (d > hi ? hi : d);
+    int idx = 0;
+    for (int k = 1; k < num_zones; ++k) idx += (boundaries[k] < d) ? 1 : 0;
+    return centers[idx];
+}
+
+/* rotate_positions_for_pose, GM:51-104: Ry(azimuth) then Rx(elevation); trig = (cos az, sin az, cos el, sin el). */
+FRB_HEAD_HD void frb_pose_rotate(const float p[3], const float trig[4], float out[3]) {
+    const float x_rot = p[0] * trig[0] + p[2] * trig[1];
+    const float z_rot = -p[0] * trig[1] + p[2] * trig[0];
+    out[0] = x_rot;
+    out[1] = p[1] * trig[2] - z_rot * trig[3];
+    out[2] = p[1] * trig[3] + z_rot * trig[2];
+}
+
+/* gp = J^T g of frb_pose_rotate (the rotation is orthogonal: its transpose) */
+FRB_HEAD_HD void frb_pose_rotate_bwd(const float g[3], const float trig[4], float gp[3]) {
+    const float g_zrot = -g[1] * trig[3] + g[2] * trig[2];
+    gp[0] = g[0] * trig[0] - g_zrot * trig[1];
+    gp[1] = g[1] * trig[2] + g[2] * trig[3];
+    gp[2] = g[0] * trig[1] + g_zrot * trig[0];
+}
+
 /* base_x, base_y: the patch-grid coordinate in [-1, 1]; z_base = depth_offset - 2 * depth_grid (GM:840);
  * edge: Fresnel edge strength of the patch (0 when edge-aware placement is off, GM:881-895). */
 FRB_HEAD_HD void frb_head_fwd_one(const float raw[FRB_HEAD_RAW], float base_x, float base_y, float z_base, float edge,
@@ -219,7 +249,8 @@ FRB_HEAD_HD void frb_head_fwd_one(const float raw[FRB_HEAD_RAW], float base_x, f
 /* g_raw[16] and the z gradient (the caller sums it into depth_offset's gradient). */
 FRB_HEAD_HD void frb_head_bwd_one(const float raw[FRB_HEAD_RAW], float edge, float edge_scale_factor,
                                   float edge_opacity_boost, const FrbHeadOut& g, float g_raw[FRB_HEAD_RAW],
-                                  float& g_z) {
+                                  float& g_z, float& g_edge) {
+    g_edge = 0.0f;
     g_raw[0] = 0.25f * g.pos[0];
     g_raw[1] = 0.25f * g.pos[1];
     g_raw[2] = 0.0f;
@@ -232,6 +263,10 @@ FRB_HEAD_HD void frb_head_bwd_one(const float raw[FRB_HEAD_RAW], float edge, flo
         const float sp = (x > 20.0f) ? x : log1pf(expf(x));
         const float s = sp * 0.15f;
         float gs = g.scl[k] * smod;
+        {
+            const float sc = s < 1e-6f ? 1e-6f : (s > 2.0f ? 2.0f : s);
+            g_edge -= g.scl[k] * edge_scale_factor * sc;                      /* scale = sc * (1 - f * edge) */
+        }
         if (!(s >= 1e-6f && s <= 2.0f)) gs = 0.0f;                            /* clamp backward, inclusive */
         float gx = gs * 0.15f * ((x > 20.0f) ? 1.0f : frb_sigmoidf(x));
         if (!(r >= -10.0f && r <= 20.0f)) gx = 0.0f;
@@ -245,6 +280,7 @@ FRB_HEAD_HD void frb_head_bwd_one(const float raw[FRB_HEAD_RAW], float edge, flo
     if (edge_opacity_boost != 0.0f || edge != 0.0f) {
         const float pre = y + edge_opacity_boost * edge;
         if (!(pre >= 0.0f && pre <= 1.0f)) go = 0.0f;
+        g_edge += go * edge_opacity_boost;
     }
     g_raw[15] = go * y * (1.0f - y);
 }

@@ -48,6 +48,11 @@ struct StageScope {
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// tile lists by counting + bitmap ranking (tile_lists.cu) when the rank bitmap and the tile counters fit an SM
+bool frb_use_tile_lists(int n, int tiles) {
+    return n > 0 && n <= frb_tile_lists_max_gaussians() && tiles <= frb_tile_lists_max_tiles();
+}
+
 struct Carver {
     size_t off = 0;
     size_t take(size_t bytes) {
@@ -104,13 +109,22 @@ extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_
     L->depth_bits = s.take(4 * (size_t)n);
     L->touched = s.take(4 * (size_t)n);
     L->order = s.take(4 * (size_t)n);
+    L->rank = s.take(4 * (size_t)n);
     L->offsets = s.take(4 * ((size_t)n + 1));
     L->depth_ws = s.take(frb_depth_order_workspace_bytes(n));
     L->scan_ws = s.take(frb_scan_workspace_bytes(n));
-    L->keys = s.take(8 * m);
-    L->keys_tmp = s.take(8 * m);
-    L->vals_tmp = s.take(4 * m);
-    L->sort_ws = s.take(frb_sort_workspace_bytes(m_capacity));
+    if (frb_use_tile_lists(n, (int)tiles)) {
+        // tile lists by counting + bitmap ranking: 4 bytes of scratch per instance, no key buffers
+        L->keys = L->keys_tmp = L->vals_tmp = L->sort_ws = s.off;
+        L->tile_ws = s.take(frb_tile_lists_workspace_bytes(n, (int)tiles));
+        L->inst_rank = s.take(4 * m);
+    } else {
+        L->keys = s.take(8 * m);
+        L->keys_tmp = s.take(8 * m);
+        L->vals_tmp = s.take(4 * m);
+        L->sort_ws = s.take(frb_sort_workspace_bytes(m_capacity));
+        L->tile_ws = L->inst_rank = s.off;
+    }
     L->scratch_bytes = s.off;
     return 0;
 }
@@ -142,8 +156,27 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
     FRB_STAGE("frb_project_fwd", stream,
               frb_project_fwd(n, n_views, positions, scales, rotations, colors, opacities, camera_host, max_radius,
                               records, nullptr, depth_bits, touched, nullptr, stream));
-    FRB_STAGE("frb_depth_order", stream, frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream));
-    if (n > 0 && m_capacity > 0) {
+    int32_t* tile_order = (int32_t*)(P + L.tile_order);
+    if (m_capacity > 0 && frb_use_tile_lists(n, tiles)) {
+        // count per tile -> scan (ranges, launch order) -> depth sort -> emit depth ranks -> per-tile bitmap ranking + gather
+        uint32_t* inst_rank = (uint32_t*)(S + L.inst_rank);
+        uint32_t* rank = (uint32_t*)(S + L.rank);
+        // (counting and scanning need no depth order; running them on a forked stream beside the depth sort was
+        // measured and dropped: 2564-2577 frames/s against 2586-2588 in stream order - inside the replayed graph the
+        // cross-stream edges cost the programmatic-launch overlap they replace, profiles/r2_e_overlap_ab.txt)
+        FRB_STAGE("frb_tile_count", stream, frb_tile_count(n, n_views, width, height, records, S + L.tile_ws, stream));
+        FRB_STAGE("frb_tile_scan", stream,
+                  frb_tile_scan(n, tiles, m_capacity, ranges, tile_order, offsets + n, S + L.tile_ws, stream));
+        FRB_STAGE("frb_depth_order", stream,
+                  frb_depth_order_rank(n, depth_bits, order, rank, S + L.depth_ws, stream));
+        FRB_STAGE("frb_tile_emit", stream,
+                  frb_tile_emit(n, n_views, width, height, records, rank, m_capacity, S + L.tile_ws, inst_rank,
+                                stream));
+        FRB_STAGE("frb_tile_rank_gather", stream,
+                  frb_tile_rank_gather(n, tiles, tile_order, ranges, inst_rank, order, records, nullptr, nullptr, gids,
+                                       sorted_records, nullptr, nullptr, stream));
+    } else if (n > 0 && m_capacity > 0) {
+        FRB_STAGE("frb_depth_order", stream, frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream));
         if (tile_bits <= 16) {
             // scan of the tile counts, key emission and the sort histograms in one kernel (offsets[n] = M only)
             FRB_STAGE("frb_bin_sort_dev", stream,
@@ -161,11 +194,11 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
         FRB_STAGE("frb_ranges_and_gather", stream,
                   frb_ranges_and_gather_dev(m_capacity, offsets + n, keys, gids, tiles, ranges, records,
                                             sorted_records, nullptr, nullptr, stream));
+        FRB_STAGE("frb_tile_schedule", stream, frb_tile_schedule(tiles, ranges, tile_order, stream));
     } else {
         FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
+        FRB_STAGE("frb_tile_schedule", stream, frb_tile_schedule(tiles, ranges, tile_order, stream));
     }
-    int32_t* tile_order = (int32_t*)(P + L.tile_order);
-    FRB_STAGE("frb_tile_schedule", stream, frb_tile_schedule(tiles, ranges, tile_order, stream));
     FRB_STAGE("frb_composite_fwd", stream,
               frb_composite_fwd_sched(n_views, width, height, tile_order, ranges, sorted_records, nullptr, 0.0f,
                                       background_host, t_eps, image, depth, alpha, (float*)(P + L.state_T),

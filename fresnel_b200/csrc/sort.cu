@@ -95,7 +95,8 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
                       const uint32_t* __restrict__ vals_in,
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
                       const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
-                      uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag) {
+                      uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag,
+                      uint32_t* __restrict__ rank_out) {
     frb_pdl_prologue();
     __shared__ uint32_t cnt[SORT_WARPS][RADIX];
     __shared__ uint32_t digit_base[RADIX];
@@ -212,7 +213,9 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
             uint32_t dg = digit_of(key[r], shift, mask);
             uint32_t pos = digit_base[dg] + cnt[warp][dg] + rank[r];
             keys_out[pos] = key[r];
-            vals_out[pos] = GEN_VALS ? (uint32_t)i : vals_in[i];
+            const uint32_t val = GEN_VALS ? (uint32_t)i : vals_in[i];
+            vals_out[pos] = val;
+            if (rank_out) rank_out[val] = pos;            // last pass of frb_depth_order: the inverse permutation
         }
     }
     }   // while: next tile
@@ -236,7 +239,7 @@ size_t sort_ws_words(int m, int n_passes) {
 template <typename KeyT>
 int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
                     KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
-                    bool* result_in_b, bool hist_ready = false) {
+                    bool* result_in_b, bool hist_ready = false, uint32_t* rank_out = nullptr) {
     PassPlan plan;
     plan.n_passes = 0;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
@@ -265,7 +268,7 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
 #define FRB_ONESWEEP(GEN, IPT_)                                                                                     \
     frb_launch(radix_onesweep_kernel<KeyT, GEN, IPT_>, dim3(grid), dim3(SORT_THREADS), 0, st,                                           \
         m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,              \
-        ws + WS_TICKET + p, ws + WS_ERROR)
+        ws + WS_TICKET + p, ws + WS_ERROR, (p == plan.n_passes - 1) ? rank_out : (uint32_t*)nullptr)
         if (vin == nullptr) {
             if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL); else FRB_ONESWEEP(true, SORT_IPT);
         } else {
@@ -590,6 +593,11 @@ extern "C" size_t frb_depth_order_workspace_bytes(int n) {
 
 extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* workspace,
                                void* stream) {
+    return frb_depth_order_rank(n, depth_bits, order, nullptr, workspace, stream);
+}
+
+extern "C" int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t* order, uint32_t* rank,
+                                    void* workspace, void* stream) {
     if (n < 0) return FRB_E_INVALID;
     if (n == 0) return 0;
     if (!depth_bits || !order || !workspace) return FRB_E_INVALID;
@@ -602,7 +610,8 @@ extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* orde
     uint32_t* ws = (uint32_t*)(w + 3 * a);
     // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
     bool in_b = false;
-    int rc = radix_sort_impl<uint32_t>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b);
+    int rc = radix_sort_impl<uint32_t>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b,
+                                       false, rank);
     if (rc) return rc;
     if (!in_b) return FRB_E_INVALID;   // cannot happen with an even number of passes
     return 0;

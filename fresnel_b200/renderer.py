@@ -140,7 +140,7 @@ class TileBins:
     """Sorted tile instance lists of one batch of views (result of the binning stage)."""
 
     __slots__ = ("m", "m_alloc", "m_dev", "ranges", "sorted_records", "sorted_gids", "sorted_phases", "keys", "order",
-                 "records", "rects", "depth_bits", "touched")
+                 "records", "rects", "depth_bits", "touched", "tile_order")
 
 
 def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.ndarray, n_views: int,
@@ -175,6 +175,7 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     cam = np.ascontiguousarray(cam_vecs, np.float32)
 
     b = TileBins()
+    b.tile_order = None
     b.records = torch.empty(n, RECORD_FLOATS, dtype=torch.float32, device=dev)
     b.depth_bits = torch.empty(n, **i32)
     b.touched = torch.empty(n, **i32)
@@ -189,10 +190,17 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
     if low_word_fn is not None:
         b.depth_bits = low_word_fn(b)
     b.order = None
+    rank = None
     if sort and presort and n > 0:
         b.order = torch.empty(n, **i32)
+        rank = torch.empty(n, **i32)
         ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=dev)
-        _call("frb_depth_order", L.frb_depth_order, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(ws), st)
+        _call("frb_depth_order", L.frb_depth_order_rank, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(rank), _ptr(ws), st)
+
+    if (sort and presort and low_word_fn is None and project_fn is None and n > 0 and TILE_LISTS
+            and n <= L.frb_tile_lists_max_gaussians() and n_tiles <= L.frb_tile_lists_max_tiles()):
+        return _tile_lists(b, rank, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync, mode, dev,
+                           st)
 
     offsets = torch.empty(n + 1, **i32)
     ws = torch.empty(max(L.frb_scan_workspace_bytes(n), 4), dtype=torch.uint8, device=dev)
@@ -243,6 +251,51 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
               _ptr(b.sorted_gids), n_tiles, _ptr(b.ranges), _ptr(b.records), _ptr(b.sorted_records), _ptr(phases),
               _ptr(b.sorted_phases), st)
     b.m_dev = m_dev
+    return b
+
+
+TILE_LISTS = True       # tile lists by counting + bitmap ranking (csrc/tile_lists.cu); False = the 64-bit key sort
+
+
+def _tile_lists(b: TileBins, rank, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync, mode, dev,
+                st):
+    """Binning without a sort over the instances: frb_tile_count -> frb_tile_scan -> frb_tile_emit ->
+    frb_tile_rank_gather (csrc/tile_lists.cu).  Same lists, bit for bit, as the key sort (``b.keys`` is produced
+    only with ``keep_debug``)."""
+    L = _lib.lib()
+    i32 = dict(dtype=torch.int32, device=dev)
+    ws = torch.empty(L.frb_tile_lists_workspace_bytes(n, n_tiles), dtype=torch.uint8, device=dev)
+    _call("frb_tile_count", L.frb_tile_count, n, n_views, width, height, _ptr(b.records), _ptr(ws), st)
+    worst = worst_case_instances(n, n_views, width, height, max_radius)
+    if sync is None:
+        sync = keep_debug or phases is not None or mode != 0 or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES
+    b.ranges = torch.empty(n_tiles, 2, **i32)
+    tile_order = torch.empty(n_tiles, **i32)
+    m_out = torch.empty(1, **i32)
+    # sync: scan without a capacity, read the instance count back (the one host sync), size the buffers exactly;
+    # otherwise the buffers hold the worst case and the count stays on the device
+    cap = (2 ** 31 - 1) if sync else worst
+    _call("frb_tile_scan", L.frb_tile_scan, n, n_tiles, cap, _ptr(b.ranges), _ptr(tile_order), _ptr(m_out), _ptr(ws),
+          st)
+    if sync:
+        m, m_dev = int(m_out.item()), None
+        cap = b.m_alloc = instance_capacity(m)
+    else:
+        m, m_dev = worst, m_out
+        b.m_alloc = worst
+    b.m, b.m_dev = m, m_dev
+    b.tile_order = tile_order
+    b.sorted_gids = torch.empty(cap, **i32)[:m]
+    b.sorted_records = torch.empty(max(cap, 1), RECORD_FLOATS, dtype=torch.float32, device=dev)[:max(m, 1)]
+    b.sorted_phases = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)[:max(m, 1)] if phases is not None else None
+    b.keys = torch.empty(cap, dtype=torch.int64, device=dev)[:m] if keep_debug else None
+    if m > 0:
+        inst_rank = torch.empty(cap, **i32)
+        _call("frb_tile_emit", L.frb_tile_emit, n, n_views, width, height, _ptr(b.records), _ptr(rank), cap,
+              _ptr(ws), _ptr(inst_rank), st)
+        _call("frb_tile_rank_gather", L.frb_tile_rank_gather, n, n_tiles, _ptr(tile_order), _ptr(b.ranges),
+              _ptr(inst_rank), _ptr(b.order), _ptr(b.records), _ptr(b.depth_bits), _ptr(phases), _ptr(b.sorted_gids),
+              _ptr(b.sorted_records), _ptr(b.sorted_phases), _ptr(b.keys), st)
     return b
 
 
@@ -370,8 +423,10 @@ class _TileRenderFn(torch.autograd.Function):
         if phases is not None:
             n_tiles = bins.ranges.shape[0]
             ckpt = torch.empty(max(L.frb_phase_ckpt_floats(bins.m_alloc, n_tiles), 1), **f32)
-        tile_order = torch.empty(bins.ranges.shape[0], dtype=torch.int32, device=dev)
-        _call("frb_tile_schedule", L.frb_tile_schedule, bins.ranges.shape[0], _ptr(bins.ranges), _ptr(tile_order), st)
+        tile_order = bins.tile_order
+        if tile_order is None:
+            tile_order = torch.empty(bins.ranges.shape[0], dtype=torch.int32, device=dev)
+            _call("frb_tile_schedule", L.frb_tile_schedule, bins.ranges.shape[0], _ptr(bins.ranges), _ptr(tile_order), st)
         _call("frb_composite_fwd", L.frb_composite_fwd_sched, n_views, width, height, _ptr(tile_order),
               _ptr(bins.ranges), _ptr(bins.sorted_records),
                                        _ptr(bins.sorted_phases), float(phase_amp), bg_host.ctypes.data,

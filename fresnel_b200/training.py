@@ -22,9 +22,14 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+import ctypes
+
+import numpy as np
+
 from . import _lib
 from .camera import Camera
 from .renderer import TileBasedRenderer, _ptr, _stream
+from .zones import DepthEdgeDetector, FresnelZones
 
 
 def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
@@ -61,13 +66,31 @@ def rotation_6d_to_quaternion(rot_6d: torch.Tensor) -> torch.Tensor:
     return F.normalize(torch.stack(q, dim=-1), dim=-1, eps=1e-6)
 
 
+def _head_extras(edge, edge_scale_factor, edge_opacity_boost, zones, pose_trig):
+    """(FrbHeadExtras, keep-alive list) for the C call: host arrays of the zone buffers, device pointers of the rest."""
+    ex = _lib.HeadExtras()
+    keep = []
+    ex.edge = _ptr(edge)
+    ex.edge_scale_factor, ex.edge_opacity_boost = float(edge_scale_factor), float(edge_opacity_boost)
+    ex.num_zones = 0
+    if zones is not None:
+        zb, zc = zones
+        ex.num_zones = int(zc.shape[0])
+        ex.zone_boundaries_host, ex.zone_centers_host = zb.ctypes.data, zc.ctypes.data
+        keep += [zb, zc]
+    ex.pose_trig = _ptr(pose_trig)
+    return ex, keep
+
+
 class _DecodeHeadFn(torch.autograd.Function):
     """The decoder output head as one CUDA kernel per direction (csrc/head.cu):
     raw (B, N, 16) -> positions / scales / rotations / colours / opacities of the Gaussians in ``idx`` (all N
-    when ``idx`` is None), written directly in the renderer's layout."""
+    when ``idx`` is None), written directly in the renderer's layout.  ``edge`` (B, H, W) is the edge strength
+    (differentiable: the edge detector is trained), ``zones`` = (boundaries, centres) host arrays of the Fresnel
+    depth zones, ``pose_trig`` (B, 4) = cos / sin of azimuth and elevation (gaussian_decoder_models.py:51-104)."""
 
     @staticmethod
-    def forward(ctx, raw, depth_grid, depth_offset, idx, shape):
+    def forward(ctx, raw, depth_grid, depth_offset, edge, idx, shape, edge_factors, zones, pose_trig):
         B, H, W, K = shape
         L = _lib.lib()
         dev = raw.device
@@ -81,29 +104,54 @@ class _DecodeHeadFn(torch.autograd.Function):
         scl = buf[7 * m:10 * m].view(B, n_out, 3)
         col = buf[10 * m:13 * m].view(B, n_out, 3)
         opa = buf[13 * m:].view(B, n_out)
-        _lib.check(L.frb_decode_head_fwd(B, H, W, K, _ptr(raw), _ptr(depth_grid), _ptr(depth_offset), None, 0.0, 0.0,
-                                         _ptr(idx), n_out if idx is not None else 0, _ptr(pos), _ptr(scl), _ptr(rot),
-                                         _ptr(col), _ptr(opa), _stream()), "frb_decode_head_fwd")
-        ctx.shape = shape
-        ctx.has_idx = idx is not None
+        edge = None if edge is None else edge.contiguous().float()
+        pose_trig = None if pose_trig is None else pose_trig.contiguous().float()
+        ex, keep = _head_extras(edge, edge_factors[0], edge_factors[1], zones, pose_trig)
+        _lib.check(L.frb_decode_head_fwd_ex(B, H, W, K, _ptr(raw), _ptr(depth_grid), _ptr(depth_offset),
+                                            ctypes.byref(ex), _ptr(idx), n_out if idx is not None else 0, _ptr(pos),
+                                            _ptr(scl), _ptr(rot), _ptr(col), _ptr(opa), _stream()),
+                   "frb_decode_head_fwd_ex")
+        ctx.shape, ctx.edge_factors, ctx.zones = shape, edge_factors, zones
+        ctx.has_idx, ctx.has_edge, ctx.has_pose = idx is not None, edge is not None, pose_trig is not None
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(raw, idx if idx is not None else raw.new_empty(0))
+        empty = raw.new_empty(0)
+        ctx.save_for_backward(raw, idx if idx is not None else empty, edge if edge is not None else empty,
+                              pose_trig if pose_trig is not None else empty)
         return pos, scl, rot, col, opa
 
     @staticmethod
     def backward(ctx, g_pos, g_scl, g_rot, g_col, g_opa):
         B, H, W, K = ctx.shape
-        raw, idx = ctx.saved_tensors
+        raw, idx, edge, pose_trig = ctx.saved_tensors
         idx = idx if ctx.has_idx else None
+        edge = edge if ctx.has_edge else None
+        pose_trig = pose_trig if ctx.has_pose else None
         n_out = H * W * K if idx is None else int(idx.numel())
         L = _lib.lib()
         g = [None if t is None else t.contiguous().float() for t in (g_pos, g_scl, g_rot, g_col, g_opa)]
+        if g[2] is not None and g[2].data_ptr() % 16:
+            g[2] = g[2].clone()
         g_raw = torch.empty_like(raw)
         g_off = torch.empty(1, dtype=torch.float32, device=raw.device)
-        _lib.check(L.frb_decode_head_bwd(B, H, W, K, _ptr(raw), None, 0.0, 0.0, _ptr(idx),
-                                         n_out if idx is not None else 0, *(_ptr(t) for t in g), _ptr(g_raw),
-                                         _ptr(g_off), _stream()), "frb_decode_head_bwd")
-        return g_raw, None, g_off.reshape(()), None, None
+        g_edge = torch.empty(B, H, W, dtype=torch.float32, device=raw.device) if edge is not None else None
+        ex, keep = _head_extras(edge, ctx.edge_factors[0], ctx.edge_factors[1], ctx.zones, pose_trig)
+        _lib.check(L.frb_decode_head_bwd_ex(B, H, W, K, _ptr(raw), ctypes.byref(ex), _ptr(idx),
+                                            n_out if idx is not None else 0, *(_ptr(t) for t in g), _ptr(g_raw),
+                                            _ptr(g_off), _ptr(g_edge), _stream()), "frb_decode_head_bwd_ex")
+        return g_raw, None, g_off.reshape(()), g_edge, None, None, None, None, None
+
+
+def rotate_positions_for_pose(positions: torch.Tensor, elevation: torch.Tensor, azimuth: torch.Tensor) -> torch.Tensor:
+    """(B, ..., 3) positions rotated to face the camera at (elevation, azimuth): Ry(azimuth) then Rx(elevation),
+    gaussian_decoder_models.py:51-104 (PyTorch restatement; the CUDA head applies it in csrc/frb_head.h)."""
+    B = positions.shape[0]
+    shape = (B,) + (1,) * (positions.dim() - 2)
+    ca, sa = torch.cos(azimuth).view(shape), torch.sin(azimuth).view(shape)
+    ce, se = torch.cos(elevation).view(shape), torch.sin(elevation).view(shape)
+    x, y, z = positions[..., 0], positions[..., 1], positions[..., 2]
+    x_rot = x * ca + z * sa
+    z_rot = -x * sa + z * ca
+    return torch.stack([x_rot, y * ce - z_rot * se, y * se + z_rot * ce], dim=-1)
 
 
 class PatchGaussianDecoder(nn.Module):
@@ -111,11 +159,16 @@ class PatchGaussianDecoder(nn.Module):
 
     MLP 384 -> 512 -> 512 -> 256 -> 128 -> K*16 with ReLU + dropout, grid positions with a learned 0.25
     offset, z locked to depth_offset - 2 * depth, softplus scales, 6D rotations, sigmoid colour / opacity
-    (gaussian_decoder_models.py:740-948, default flags).
+    (gaussian_decoder_models.py:622-948), with the reference's Fresnel options: ``use_fresnel_zones`` snaps the
+    depth grid to ``num_fresnel_zones`` zone centres (:833-838), ``use_edge_aware`` shrinks scales / boosts
+    opacity by a learned edge strength (:881-895), and ``elevation`` / ``azimuth`` rotate the grid to face the
+    camera (:51-104, :860).  Module names follow the reference, so its ``state_dict`` loads
+    (``mlp.net.*`` -> ``mlp.*``).
     """
 
     def __init__(self, feature_dim: int = 384, gaussians_per_patch: int = 4, hidden_dims=(512, 512, 256, 128),
-                 dropout: float = 0.1):
+                 dropout: float = 0.1, use_fresnel_zones: bool = False, num_fresnel_zones: int = 8,
+                 use_edge_aware: bool = False, edge_scale_factor: float = 0.5, edge_opacity_boost: float = 0.2):
         super().__init__()
         self.gaussians_per_patch = gaussians_per_patch
         layers, prev = [], feature_dim
@@ -127,10 +180,26 @@ class PatchGaussianDecoder(nn.Module):
         layers.append(nn.Linear(prev, gaussians_per_patch * 16))
         self.mlp = nn.Sequential(*layers)
         self.depth_offset = nn.Parameter(torch.tensor(-2.0))
+        self.use_fresnel_zones, self.use_edge_aware = use_fresnel_zones, use_edge_aware
+        self.edge_scale_factor, self.edge_opacity_boost = edge_scale_factor, edge_opacity_boost
+        self.fresnel_zones = (FresnelZones(num_zones=num_fresnel_zones, depth_range=(0.0, 1.0), soft_boundaries=True)
+                              if use_fresnel_zones else None)
+        self.edge_detector = DepthEdgeDetector(1, 16, True) if use_edge_aware else None
         self.fused_head = True          # CUDA inputs: csrc/head.cu; False keeps the PyTorch ops (A/B checks)
+        self._zone_host = None
+
+    def _zones_host(self):
+        """(boundaries, centres) of the zone buffers as host fp32 arrays (cached: no device read per step)."""
+        if self.fresnel_zones is None:
+            return None
+        if self._zone_host is None:
+            self._zone_host = (np.ascontiguousarray(self.fresnel_zones.zone_boundaries.detach().cpu().numpy(), np.float32),
+                               np.ascontiguousarray(self.fresnel_zones.zone_centers.detach().cpu().numpy(), np.float32))
+        return self._zone_host
 
     def forward(self, features: torch.Tensor, depth: Optional[torch.Tensor] = None,
-                stochastic_k: Optional[int] = None, generator: Optional[torch.Generator] = None
+                stochastic_k: Optional[int] = None, generator: Optional[torch.Generator] = None,
+                elevation: Optional[torch.Tensor] = None, azimuth: Optional[torch.Tensor] = None
                 ) -> Dict[str, torch.Tensor]:
         """``stochastic_k``: HFTS stochastic rendering - return only K Gaussians per view, drawn without replacement
         with p ~ mean opacity (train_gaussian_decoder.py:1154-1187; same draw as ``subsample_by_opacity``).
@@ -139,41 +208,70 @@ class PatchGaussianDecoder(nn.Module):
         B, C, H, W = features.shape
         K = self.gaussians_per_patch
         raw = self.mlp(features.permute(0, 2, 3, 1).reshape(B * H * W, C))
+        pose = elevation is not None and azimuth is not None
         if features.is_cuda and self.fused_head:
             raw = raw.reshape(B, H * W * K, 16)
-            grid = None
+            grid, edge = None, None
             if depth is not None:
-                grid = F.interpolate(depth, (H, W), mode="bilinear", align_corners=False).reshape(B, H, W).contiguous()
+                grid4 = F.interpolate(depth, (H, W), mode="bilinear", align_corners=False)
+                if self.use_edge_aware:
+                    edge = self.edge_detector(grid4).reshape(B, H, W)
+                grid = grid4.reshape(B, H, W).contiguous()
             idx = None
             if stochastic_k is not None and stochastic_k < H * W * K:
                 with torch.no_grad():
-                    w = torch.sigmoid(raw[..., 15]).mean(dim=0) + 1e-6
+                    op = torch.sigmoid(raw[..., 15])
+                    if edge is not None:        # the reference draws on the FINAL opacities (:1173)
+                        e = edge.detach().reshape(B, H * W, 1).expand(-1, -1, K).reshape(B, H * W * K)
+                        op = torch.clamp(op + self.edge_opacity_boost * e, 0, 1)
+                    w = op.mean(dim=0) + 1e-6
                     idx = torch.multinomial(w / w.sum(), stochastic_k, replacement=False, generator=generator)
-            pos, scl, rot, col, opa = _DecodeHeadFn.apply(raw.contiguous(), grid, self.depth_offset, idx, (B, H, W, K))
+            trig = None
+            if pose:
+                trig = torch.stack([torch.cos(azimuth), torch.sin(azimuth), torch.cos(elevation),
+                                    torch.sin(elevation)], dim=-1).to(raw.device, torch.float32)
+            pos, scl, rot, col, opa = _DecodeHeadFn.apply(
+                raw.contiguous(), grid, self.depth_offset, edge, idx, (B, H, W, K),
+                (self.edge_scale_factor, self.edge_opacity_boost), self._zones_host() if grid is not None else None,
+                trig)
             return {"positions": pos, "scales": scl, "rotations": rot, "colors": col, "opacities": opa}
-        out = self._torch_head(raw.reshape(B, H, W, K, 16), depth)
+        out = self._torch_head(raw.reshape(B, H, W, K, 16), depth, elevation if pose else None,
+                               azimuth if pose else None)
         return subsample_by_opacity(out, stochastic_k, generator)
 
-    def _torch_head(self, out: torch.Tensor, depth: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def _torch_head(self, out: torch.Tensor, depth: Optional[torch.Tensor], elevation=None, azimuth=None
+                    ) -> Dict[str, torch.Tensor]:
         B, H, W, K, _ = out.shape
         ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device=out.device),
                                 torch.linspace(-1, 1, W, device=out.device), indexing="ij")
         base_x = xs[None, :, :, None].expand(B, -1, -1, K)
         base_y = ys[None, :, :, None].expand(B, -1, -1, K)
+        edge = None
         if depth is not None:
             grid = F.interpolate(depth, (H, W), mode="bilinear", align_corners=False)
+            if self.use_edge_aware:
+                edge = self.edge_detector(grid)                                        # (B, 1, H, W), GM:826-829
+            if self.use_fresnel_zones:
+                grid = self.fresnel_zones.get_zone_centers_for_depth(grid.squeeze(1)).unsqueeze(1)   # GM:833-838
             base_z = self.depth_offset + grid.squeeze(1).unsqueeze(-1).expand(-1, -1, -1, K) * (-2)
         else:
             base_z = self.depth_offset.expand(B, H, W, K)
         positions = torch.stack([base_x + out[..., 0] * 0.25, base_y + out[..., 1] * 0.25, base_z], dim=-1)
+        if elevation is not None and azimuth is not None:
+            positions = rotate_positions_for_pose(positions, elevation, azimuth)       # GM:860
         scales = torch.clamp(F.softplus(torch.clamp(out[..., 3:6], min=-10, max=20) + 1.0) * 0.15, min=1e-6, max=2.0)
+        opacities = torch.sigmoid(out[..., 15])
+        if edge is not None:                                                           # GM:881-895
+            e = edge.squeeze(1).unsqueeze(-1).expand(-1, -1, -1, K)
+            scales = scales * (1.0 - self.edge_scale_factor * e.unsqueeze(-1))
+            opacities = torch.clamp(opacities + self.edge_opacity_boost * e, 0, 1)
         N = H * W * K
         return {
             "positions": positions.reshape(B, N, 3),
             "scales": scales.reshape(B, N, 3),
             "rotations": rotation_6d_to_quaternion(out[..., 6:12]).reshape(B, N, 4),
             "colors": torch.sigmoid(out[..., 12:15]).reshape(B, N, 3),
-            "opacities": torch.sigmoid(out[..., 15]).reshape(B, N),
+            "opacities": opacities.reshape(B, N),
         }
 
 
@@ -191,14 +289,20 @@ def subsample_by_opacity(gaussians: Dict[str, torch.Tensor], k: int,
 
 
 def reconstruction_losses(rendered, target, rendered_depth=None, target_depth=None, rgb_weight: float = 1.0,
-                          depth_weight: float = 0.1) -> torch.Tensor:
-    """L1 RGB + normalised depth L1 (compute_losses, train_gaussian_decoder.py:838-930 with the SSIM and
-    LPIPS terms absent - neither package is installed in this image, and the reference then drops them)."""
+                          depth_weight: float = 0.1, fresnel_zones: Optional[FresnelZones] = None,
+                          boundary_weight: float = 0.0) -> torch.Tensor:
+    """L1 RGB + normalised depth L1 + Fresnel boundary emphasis (compute_losses, train_gaussian_decoder.py:838-953
+    with the SSIM and LPIPS terms absent - neither package is installed in this image, and the reference then
+    drops them).  The boundary term (:941-953) weights the per-pixel RGB error by the closeness of the TARGET depth
+    to a zone boundary."""
     loss = rgb_weight * F.l1_loss(rendered, target)
     if rendered_depth is not None and target_depth is not None:
         rd = (rendered_depth - rendered_depth.mean()) / torch.clamp(rendered_depth.std(), min=1e-4)
         td = (target_depth - target_depth.mean()) / torch.clamp(target_depth.std(), min=1e-4)
         loss = loss + depth_weight * F.l1_loss(rd, td)
+    if fresnel_zones is not None and boundary_weight > 0 and target_depth is not None:
+        mask = fresnel_zones.compute_boundary_mask(target_depth)                       # (B, H, W)
+        loss = loss + boundary_weight * (torch.abs(rendered - target).mean(dim=1) * mask).mean()
     return loss
 
 
@@ -206,22 +310,28 @@ class _ReconLossFn(torch.autograd.Function):
     """``reconstruction_losses`` as four CUDA kernels (csrc/loss.cu)."""
 
     @staticmethod
-    def forward(ctx, rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight):
+    def forward(ctx, rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight, zone_cfg):
         L = _lib.lib()
         dev = rendered.device
         rendered, target = rendered.contiguous().float(), target.contiguous().float()
         has_depth = rendered_depth is not None and target_depth is not None
         rd = rendered_depth.contiguous().float() if has_depth else None
-        td = target_depth.contiguous().float() if has_depth else None
+        td = target_depth.contiguous().float() if target_depth is not None else None
+        # zone_cfg: None or (boundary_weight, boundaries (host fp32 array), threshold, soft)
+        bw, zb, thr, soft = zone_cfg if (zone_cfg is not None and td is not None) else (0.0, None, 0.0, True)
+        hw = rendered.shape[-1] * rendered.shape[-2]
+        n_pix = td.numel() if td is not None else 0
         stats = torch.empty(L.frb_recon_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(L.frb_recon_loss_fwd(rendered.numel(), rd.numel() if has_depth else 0, _ptr(rendered), _ptr(target),
-                                        _ptr(rd), _ptr(td), float(rgb_weight), float(depth_weight), _ptr(stats),
-                                        _ptr(loss), _stream()), "frb_recon_loss_fwd")
-        ctx.weights = (float(rgb_weight), float(depth_weight))
-        ctx.has_depth = has_depth
-        ctx.save_for_backward(rendered, target, rd if has_depth else rendered.new_empty(0),
-                              td if has_depth else rendered.new_empty(0), stats)
+        _lib.check(L.frb_recon_loss_fwd_ex(rendered.numel(), n_pix, hw, _ptr(rendered), _ptr(target), _ptr(rd),
+                                           _ptr(td), float(rgb_weight), float(depth_weight), float(bw),
+                                           0 if zb is None else int(zb.shape[0]),
+                                           None if zb is None else zb.ctypes.data, float(thr), int(bool(soft)),
+                                           _ptr(stats), _ptr(loss), _stream()), "frb_recon_loss_fwd_ex")
+        ctx.cfg = (float(rgb_weight), float(depth_weight), float(bw), zb, float(thr), int(bool(soft)), hw, n_pix)
+        ctx.has_depth, ctx.has_td = has_depth, td is not None
+        empty = rendered.new_empty(0)
+        ctx.save_for_backward(rendered, target, rd if has_depth else empty, td if td is not None else empty, stats)
         return loss
 
     @staticmethod
@@ -229,20 +339,32 @@ class _ReconLossFn(torch.autograd.Function):
         rendered, target, rd, td, stats = ctx.saved_tensors
         L = _lib.lib()
         has_depth = ctx.has_depth
+        rgb_w, dep_w, bw, zb, thr, soft, hw, n_pix = ctx.cfg
         g_loss = g_loss.contiguous().float()
         g_rendered = torch.empty_like(rendered)
         g_rd = torch.empty_like(rd) if has_depth else None
-        _lib.check(L.frb_recon_loss_bwd(rendered.numel(), rd.numel() if has_depth else 0, _ptr(rendered), _ptr(target),
-                                        _ptr(rd) if has_depth else None, _ptr(td) if has_depth else None,
-                                        ctx.weights[0], ctx.weights[1], _ptr(stats), _ptr(g_loss), _ptr(g_rendered),
-                                        _ptr(g_rd), _stream()), "frb_recon_loss_bwd")
-        return g_rendered, None, g_rd, None, None, None
+        _lib.check(L.frb_recon_loss_bwd_ex(rendered.numel(), n_pix, hw, _ptr(rendered), _ptr(target),
+                                           _ptr(rd) if has_depth else None, _ptr(td) if ctx.has_td else None,
+                                           rgb_w, dep_w, bw, 0 if zb is None else int(zb.shape[0]),
+                                           None if zb is None else zb.ctypes.data, thr, soft, _ptr(stats),
+                                           _ptr(g_loss), _ptr(g_rendered), _ptr(g_rd), _stream()),
+                   "frb_recon_loss_bwd_ex")
+        return g_rendered, None, g_rd, None, None, None, None
 
 
 def reconstruction_losses_fused(rendered, target, rendered_depth=None, target_depth=None, rgb_weight: float = 1.0,
-                                depth_weight: float = 0.1) -> torch.Tensor:
+                                depth_weight: float = 0.1, fresnel_zones: Optional[FresnelZones] = None,
+                                boundary_weight: float = 0.0) -> torch.Tensor:
     """Same value and gradients as ``reconstruction_losses`` for CUDA tensors, in four kernel launches."""
-    return _ReconLossFn.apply(rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight)
+    zone_cfg = None
+    if fresnel_zones is not None and boundary_weight > 0 and target_depth is not None:
+        zb = getattr(fresnel_zones, "_frb_boundaries_host", None)
+        if zb is None:
+            zb = np.ascontiguousarray(fresnel_zones.zone_boundaries.detach().cpu().numpy(), np.float32)
+            fresnel_zones._frb_boundaries_host = zb            # cached: no device read per step
+        zone_cfg = (float(boundary_weight), zb, float(fresnel_zones.boundary_threshold),
+                    bool(fresnel_zones.soft_boundaries))
+    return _ReconLossFn.apply(rendered, target, rendered_depth, target_depth, rgb_weight, depth_weight, zone_cfg)
 
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: Optional[int] = None,
@@ -288,10 +410,19 @@ class DecoderTrainer:
     """
 
     def __init__(self, model: nn.Module, render_size: int, lr: float = 1e-4, stochastic_k: Optional[int] = None,
-                 seed: int = 0, weight_decay: float = 1e-5, cuda_graph: bool = False):
+                 seed: int = 0, weight_decay: float = 1e-5, cuda_graph: bool = False, boundary_weight: float = 0.0,
+                 use_phase_blending: bool = False):
+        """``boundary_weight`` > 0 adds the Fresnel boundary-emphasis loss (TrainingConfig.boundary_weight,
+        train_gaussian_decoder.py:941-953) with the model's zones (or 8 default zones when it has none, as
+        train_gaussian_decoder.py builds them)."""
         self.model = model
         self.render_size = render_size
-        self.renderer = TileBasedRenderer(render_size, render_size)
+        self.renderer = TileBasedRenderer(render_size, render_size, use_phase_blending=use_phase_blending)
+        self.boundary_weight = float(boundary_weight)
+        self.loss_zones = None
+        if boundary_weight > 0:
+            dev0 = next(model.parameters()).device
+            self.loss_zones = getattr(model, "fresnel_zones", None) or FresnelZones(8, (0.0, 1.0)).to(dev0)
         self.camera = Camera(0.8 * render_size, 0.8 * render_size, render_size / 2, render_size / 2, render_size,
                              render_size)                       # train_gaussian_decoder.py:1910-1917
         self.cuda_graph = cuda_graph
@@ -324,7 +455,8 @@ class DecoderTrainer:
             images = F.interpolate(images, size=(R, R), mode="bilinear", align_corners=False)
         target_depth = F.interpolate(depth, size=(R, R), mode="bilinear", align_corners=False).squeeze(1)
         loss_fn = reconstruction_losses_fused if (rendered.is_cuda and self.fused_loss) else reconstruction_losses
-        loss = loss_fn(rendered, images, rendered_depth, target_depth)
+        loss = loss_fn(rendered, images, rendered_depth, target_depth, fresnel_zones=self.loss_zones,
+                       boundary_weight=self.boundary_weight)
         loss.backward()
         return loss.detach()
 

@@ -109,6 +109,9 @@ int frb_radix_sort_pairs(int m, uint64_t* keys, uint32_t* vals, uint64_t* keys_t
 size_t frb_depth_order_workspace_bytes(int n);
 int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* workspace,
                     void* stream);
+/* The same, and rank[g] = position of Gaussian g in that order (the inverse permutation; nullable). */
+int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t* order, uint32_t* rank, void* workspace,
+                         void* stream);
 /* offsets[k] = sum_{j<k} tiles_touched[order[j]] for k = 0..n (order NULL = identity);
  * offsets[n] = number of tile instances M. */
 size_t frb_scan_workspace_bytes(int n);
@@ -176,6 +179,31 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
                       const float* g_depth, const float* g_alpha, float* grad2d, float* g_phases,
                       void* stream);
 
+/* ---- tile lists by counting + bitmap ranking (csrc/tile_lists.cu) ----------------------------------------
+ * The same sorted per-tile lists as the key sort above (ascending tile, depth bits, Gaussian index), built without
+ * sorting M keys: count the instances per tile, scan, emit each Gaussian's DEPTH RANK into its tiles' spans
+ * (arbitrary order inside a span), then one CTA per tile orders its span with a shared-memory bitmap over the ranks
+ * and gathers the records.  Needs n <= frb_tile_lists_max_gaussians() (the bitmap must fit one SM's shared memory).
+ * and the image must have at most frb_tile_lists_max_tiles() tiles over all views (one counter per tile in shared
+ * memory).  workspace: frb_tile_lists_workspace_bytes(n, n_tiles), written by frb_tile_count and frb_tile_scan,
+ * consumed by frb_tile_emit (counting and scanning need no depth order: they may run beside the depth sort);
+ * order / rank: frb_depth_order_rank's outputs; *m_out = total number of instances (may exceed
+ * m_capacity: then the lists are truncated to the capacity and the caller must retry with more room); inst_rank:
+ * m_capacity words; sorted_keys (nullable): the 64-bit (tile | depth bits) keys, for checks. */
+int frb_tile_lists_max_gaussians(void);
+int frb_tile_lists_max_tiles(void);
+size_t frb_tile_lists_workspace_bytes(int n, int n_tiles);
+int frb_tile_count(int n, int n_views, int width, int height, const float* records, void* workspace,
+                   void* stream);
+int frb_tile_scan(int n, int n_tiles, int m_capacity, int32_t* ranges, int32_t* tile_order, uint32_t* m_out,
+                  void* workspace, void* stream);
+int frb_tile_emit(int n, int n_views, int width, int height, const float* records, const uint32_t* rank,
+                  int m_capacity, void* workspace, uint32_t* inst_rank, void* stream);
+int frb_tile_rank_gather(int n, int n_tiles, const int32_t* tile_order, const int32_t* ranges,
+                         const uint32_t* inst_rank, const uint32_t* order, const float* records,
+                         const uint32_t* depth_bits, const float* phases, uint32_t* sorted_gids,
+                         float* sorted_records, float* sorted_phases, uint64_t* sorted_keys, void* stream);
+
 /* ---- whole-pass entry points (capacity mode, no host synchronisation) ------------------ */
 /* One call enqueues projection, binning and compositing of TileBasedRenderer.forward (DR:489-686)
  * for n_views views; buffers are carved from two arenas laid out by frb_tile_layout: `persist`
@@ -193,7 +221,7 @@ int frb_bin_sort_dev(int n, int n_views, int width, int height, const float* rec
 typedef struct FrbTileLayout {
     size_t ranges, tile_order, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
     size_t records, depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,
-        sort_ws, scratch_bytes;
+        sort_ws, tile_ws, inst_rank, rank, scratch_bytes;
 } FrbTileLayout;
 int frb_tile_layout(int n, int n_views, int width, int height, int m_capacity, FrbTileLayout* layout);
 int frb_tile_render_fwd(int n, int n_views, const float* positions, const float* scales,
@@ -331,6 +359,28 @@ int frb_decode_head_bwd(int B, int H, int W, int K, const float* raw, const floa
                         const float* g_scales, const float* g_rotations, const float* g_colors,
                         const float* g_opacities, float* g_raw, float* g_depth_offset, void* stream);
 
+/* The full tail of DirectPatchDecoder.forward: the above plus the Fresnel depth-zone snap of the depth grid
+ * (gaussian_decoder_models.py:833-838 with FresnelZones.get_zone_centers_for_depth, utils/fresnel_zones.py:96-139),
+ * the pose rotation of the positions (rotate_positions_for_pose :51-104, applied at :860) and the gradient of the
+ * edge strength (the edge detector is a trained module).  ex may be NULL (= all extras off).
+ * g_edge: [B, H, W], nullable, zeroed and accumulated here. */
+typedef struct FrbHeadExtras {
+    const float* edge;                  /* device [B, H, W] edge strength, NULL = edge-aware placement off */
+    float edge_scale_factor, edge_opacity_boost;
+    int num_zones;                      /* 0 = no zone snap */
+    const float* zone_boundaries_host;  /* num_zones + 1 floats (FresnelZones.zone_boundaries), host */
+    const float* zone_centers_host;     /* num_zones floats (FresnelZones.zone_centers), host */
+    const float* pose_trig;             /* device [B, 4]: cos az, sin az, cos el, sin el; NULL = no rotation */
+} FrbHeadExtras;
+int frb_decode_head_fwd_ex(int B, int H, int W, int K, const float* raw, const float* depth_grid,
+                           const float* depth_offset, const FrbHeadExtras* ex, const long long* idx, int n_sel,
+                           float* positions, float* scales, float* rotations, float* colors, float* opacities,
+                           void* stream);
+int frb_decode_head_bwd_ex(int B, int H, int W, int K, const float* raw, const FrbHeadExtras* ex,
+                           const long long* idx, int n_sel, const float* g_positions, const float* g_scales,
+                           const float* g_rotations, const float* g_colors, const float* g_opacities, float* g_raw,
+                           float* g_depth_offset, float* g_edge, void* stream);
+
 /* ---- reconstruction loss front-end -------------------------------------------
  * compute_losses, scripts/training/train_gaussian_decoder.py:838-930 (L1 RGB + normalised-depth L1; the SSIM /
  * LPIPS terms need packages that are absent and are dropped by the reference too).
@@ -345,6 +395,23 @@ int frb_recon_loss_bwd(long long n_rgb, long long n_pix, const float* rendered, 
                        const float* rendered_depth, const float* target_depth, float rgb_weight,
                        float depth_weight, const void* stats, const float* g_loss, float* g_rendered,
                        float* g_rendered_depth, void* stream);
+
+/* The same with the Fresnel boundary-emphasis term of train_gaussian_decoder.py:941-953:
+ *   + boundary_weight * mean_{view,pixel} [ mean_c |rendered - target| * mask(target_depth) ],
+ * mask = FresnelZones.compute_boundary_mask (scripts/utils/fresnel_zones.py:141-180): soft
+ * sigmoid(10 / thr * (thr - min_k |d - boundary_k|)) or hard 1[min_k |d - boundary_k| < thr].
+ * rendered / target: [views, 3, hw]; target_depth: [views, hw] (needed for the mask even without rendered_depth);
+ * boundaries_host: the n_boundaries = num_zones + 1 zone boundaries (torch.linspace values, at most 65);
+ * boundary_weight = 0 disables the term. */
+int frb_recon_loss_fwd_ex(long long n_rgb, long long n_pix, long long hw, const float* rendered, const float* target,
+                          const float* rendered_depth, const float* target_depth, float rgb_weight,
+                          float depth_weight, float boundary_weight, int n_boundaries, const float* boundaries_host,
+                          float boundary_threshold, int soft_boundaries, void* stats, float* loss, void* stream);
+int frb_recon_loss_bwd_ex(long long n_rgb, long long n_pix, long long hw, const float* rendered, const float* target,
+                          const float* rendered_depth, const float* target_depth, float rgb_weight,
+                          float depth_weight, float boundary_weight, int n_boundaries, const float* boundaries_host,
+                          float boundary_threshold, int soft_boundaries, const void* stats, const float* g_loss,
+                          float* g_rendered, float* g_rendered_depth, void* stream);
 
 /* ---- gradient exchange fused with the optimiser step over NVLink peer memory ---
  * Multi-view optimisation of one replicated cloud (BASELINE configs[4]): replaces the pair

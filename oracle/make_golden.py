@@ -200,6 +200,40 @@ def run_tile(name, inp, cam, W, H, bg=(0.0, 0.0, 0.0), max_radius=64, phase=Fals
           f"{time.time() - t0:.1f}s")
 
 
+def add_f64_companion(name, kind):
+    """Appends image64 / depth64 to tests/golden/NAME.npz: the SAME unmodified reference module run in float64
+    (torch default dtype switched for the call).  It tells which side of a 1e-5 disagreement is the noisy one: at
+    ~1000 overlaps per pixel the reference's own fp32 run is ~1e-5 away from its fp64 run."""
+    path = os.path.join(GOLD, name + ".npz")
+    z = dict(np.load(path))
+    W, H = int(z["W"]), int(z["H"])
+    c = z["cam"]
+    torch.set_default_dtype(torch.float64)
+    try:
+        rc = dr.Camera(float(c[12]), float(c[13]), float(c[14]), float(c[15]), W, H, float(c[18]), float(c[19]))
+        view = torch.eye(4)
+        view[:3, :] = torch.from_numpy(np.asarray(c[:12], np.float32).reshape(3, 4)).double()
+        rc.set_view(view)
+        names = GRAD_NAMES + (("phases",) if kind == "wave" else ())
+        inp = {k: torch.from_numpy(z["in_" + k]).double() for k in names}
+        bg = tuple(float(x) for x in z["bg"])
+        with torch.no_grad():
+            if kind == "wave":
+                ren = dr.WaveFieldRenderer(W, H, background=bg)
+                img, dep = ren(inp["positions"], inp["scales"], inp["rotations"], inp["colors"], inp["opacities"], rc,
+                               return_depth=True, phases=inp["phases"])
+            else:
+                ren = dr.TileBasedRenderer(W, H, background=bg, max_radius=int(z["max_radius"]))
+                img, dep = ren(inp["positions"], inp["scales"], inp["rotations"], inp["colors"], inp["opacities"], rc,
+                               return_depth=True)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    z["image64"], z["depth64"] = img.numpy(), dep.numpy()
+    np.savez_compressed(path, **z)
+    print(f"{name}: fp64 run of the reference added; fp32 reference vs fp64: image {rel(z['image'], z['image64']):.2e} "
+          f"depth {rel(z['depth'], z['depth64']):.2e}")
+
+
 def run_wave(name, inp, cam, W, H, bg, per_channel, note=""):
     gi, gd = upstream(H, W)
     rc = ref_camera(cam)
@@ -468,6 +502,8 @@ def fx_wave():
     inp3 = dict(inp)
     inp3["phases"] = torch.rand(2048, 3, generator=g) * 2 * math.pi
     run_wave("wave_rgb_2k_128", inp3, cam, W, H, (0.1, 0.2, 0.3), True, note="(N,3) phases")
+    add_f64_companion("wave_scalar_2k_128", "wave")
+    add_f64_companion("wave_rgb_2k_128", "wave")
 
 
 def fx_wave_rot():
@@ -487,6 +523,7 @@ def fx_wave_rot():
     inp["phases"] = torch.rand(1500, 3, generator=g) * 2 * math.pi
     run_wave("wave_rot_1500_112x80", inp, cam, W, H, (0.05, 0.2, 0.1), True,
              note="look-at camera el 25 az -50, W=112 H=80, (N,3) phases")
+    add_f64_companion("wave_rot_1500_112x80", "wave")
 
 
 def fx_asm():
@@ -562,6 +599,47 @@ def fx_bin():
     print(f"cloud_97.bin: {os.path.getsize(path)} bytes, reference save -> load round trip exact")
 
 
+def fx_ply():
+    """3DGS .ply fixture written and read back by the REFERENCE's own C++ functions (GaussianCloud::save_ply / load_ply,
+    src/core/renderer/renderer.cpp:649-793), compiled by oracle/build_ref.sh into oracle/_ref/libref_cloud_io.so.
+    Rows include the transforms' edge cases: scales below the 1e-7 floor, opacity 0 / 1 (logit of 0 and of 1 / 1e-7),
+    colours outside [0, 1] (clamped on load)."""
+    import ctypes
+    import subprocess
+    subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_cloud_io.so"))
+    inp = fo.synthetic_cloud(97, seed=31)
+    rows = np.concatenate([inp[k].numpy().reshape(97, -1) for k in GRAD_NAMES], axis=1).astype(np.float32)
+    rows[0, 3:6] = (0.0, 1e-9, 3e-8)            # below the 1e-7 floor of save_ply
+    rows[1, 13], rows[2, 13], rows[3, 13] = 0.0, 1.0, 0.9999999
+    rows[4, 10:13] = (-0.3, 1.7, 0.5)           # outside [0, 1]: clamped by load_ply
+    rows[5, 3:6] = (40.0, 1e-3, 7.0)
+    rows = np.ascontiguousarray(rows)
+    ply = os.path.join(GOLD, "cloud_97.ply")
+    fp = ctypes.POINTER(ctypes.c_float)
+    assert lib.ref_save_ply(rows.ctypes.data_as(fp), 97, ply.encode()) == 0
+    back = np.zeros((97, 14), np.float32)
+    assert lib.ref_load_ply(ply.encode(), back.ctypes.data_as(fp), 97) == 97
+    # the reference's .bin functions on the same cloud: C++ writer against the Python reader / writer of DR:1461-1497
+    binp = os.path.join("/tmp", "cloud_97_cpp.bin")
+    assert lib.ref_save_binary(rows.ctypes.data_as(fp), 97, binp.encode()) == 0
+    py = dr.load_gaussians_from_binary(binp)
+    assert np.array_equal(np.concatenate([py[k].numpy().reshape(97, -1) for k in GRAD_NAMES], axis=1), rows)
+    body = np.fromfile(ply, dtype="<f4", offset=os.path.getsize(ply) - 97 * 14 * 4).reshape(97, 14)
+    # the oracle's restatement against both directions
+    enc = fo.ply_encode_rows({k: torch.from_numpy(rows[:, a:b].reshape(97, -1) if b - a > 1 else rows[:, a]).numpy()
+                              for k, (a, b) in zip(GRAD_NAMES, ((0, 3), (3, 6), (6, 10), (10, 13), (13, 14)))})
+    with np.errstate(all="ignore"):
+        ok = np.isclose(enc, body, rtol=2e-6, atol=2e-6) | (np.isinf(enc) & np.isinf(body) & (np.sign(enc) == np.sign(body)))
+    assert ok.all(), np.argwhere(~ok)
+    dec = fo.ply_decode_rows(body)
+    dec_rows = np.concatenate([np.asarray(dec[k]).reshape(97, -1) for k in GRAD_NAMES], axis=1)
+    assert np.allclose(dec_rows, back, rtol=2e-6, atol=1e-7), np.abs(dec_rows - back).max()
+    np.savez_compressed(os.path.join(GOLD, "cloud_97_ply.npz"), rows_in=rows, file_rows=body, rows_loaded=back)
+    print(f"cloud_97.ply: {os.path.getsize(ply)} bytes written by the reference's save_ply, read back by its load_ply; "
+          f"oracle encode / decode agree")
+
+
 def fx_simplified():
     """SimplifiedRenderer: rotated look-at camera; Gaussians whose integer radius or integer pixel centre could
     flip under a one-ulp change are re-drawn (the fixture pins the arithmetic, not one rounding)."""
@@ -604,6 +682,7 @@ def fx_overlap():
         inp = settle(inp, cam, W, H, 64, seed, redraw_std)
         run_tile(name, inp, cam, W, H, bg=(0.1, 0.2, 0.3),
                  note=f"20k Gaussians, scales U(0.05,0.15), opacities U(0.1,0.9)*{k}: ~1000 rectangle overlaps per pixel")
+        add_f64_companion(name, "tile")
 
 
 def zone_snap_cloud(n, seed, num_zones=8, s_lo=0.005, s_hi=0.03):
@@ -641,6 +720,7 @@ def fx_c4_small():
                   "use_phase_blending=True; forward from the reference, gradients from the oracle clone restatement")
     run_tile("c4_zones_tile_20k_256", inp, cam, W, H, phase=False,
              note="same inputs without phase blending: forward and gradients from the reference")
+    add_f64_companion("c4_zones_tile_20k_256", "tile")
 
 
 def fx_c2():
@@ -663,7 +743,7 @@ def fx_c4():
                   "pinned by c4_zones_phase_20k_256)", forward_only=True)
 
 
-FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, params=fx_params, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
+FIXTURES = dict(simplified=fx_simplified, bin=fx_bin, ply=fx_ply, dense=fx_dense, fourier=fx_fourier, culled=fx_culled, edge=fx_edge, rot=fx_rot, params=fx_params, phase=fx_phase, phase_rot=fx_phase_rot, wave=fx_wave,
                 wave_rot=fx_wave_rot, asm=fx_asm, asm_rot=fx_asm_rot, asm_params=fx_asm_params, c1=fx_c1, overlap=fx_overlap,
                 c4_small=fx_c4_small)
 # full-size fixtures: tens of minutes of CPU each, only with --only

@@ -94,7 +94,48 @@ void shim_head_bwd(int n, const float* raw, const float* edge, float esf, float 
         for (int k = 0; k < 3; ++k) { g.pos[k] = f[k]; g.scl[k] = f[3 + k]; g.col[k] = f[10 + k]; }
         for (int k = 0; k < 4; ++k) g.rot[k] = f[6 + k];
         g.opa = f[13];
-        frb_head_bwd_one(raw + 16 * i, edge[i], esf, eob, g, g_raw + 16 * i, g_z[i]);
+        float g_edge;
+        frb_head_bwd_one(raw + 16 * i, edge[i], esf, eob, g, g_raw + 16 * i, g_z[i], g_edge);
+    }
+}
+
+// the full head as head.cu sequences it: zone snap of the depth, head, pose rotation; and its backward with the
+// edge-strength gradient.  depth: per-Gaussian depth-grid value; trig: per-Gaussian (cos az, sin az, cos el, sin el).
+void shim_head_full_fwd(int n, const float* raw, const float* base_xy, const float* depth, float depth_offset,
+                        const float* edge, float esf, float eob, int num_zones, const float* boundaries,
+                        const float* centers, const float* trig, float* out) {
+    for (int i = 0; i < n; ++i) {
+        float d = depth[i];
+        if (num_zones > 0) d = frb_zone_center(d, boundaries, centers, num_zones);
+        const float z = depth_offset + d * -2.0f;
+        FrbHeadOut o;
+        frb_head_fwd_one(raw + 16 * i, base_xy[2 * i], base_xy[2 * i + 1], z, edge[i], esf, eob, o);
+        if (trig) {
+            float r[3];
+            frb_pose_rotate(o.pos, trig + 4 * i, r);
+            o.pos[0] = r[0]; o.pos[1] = r[1]; o.pos[2] = r[2];
+        }
+        float* f = out + 14 * i;
+        for (int k = 0; k < 3; ++k) { f[k] = o.pos[k]; f[3 + k] = o.scl[k]; f[10 + k] = o.col[k]; }
+        for (int k = 0; k < 4; ++k) f[6 + k] = o.rot[k];
+        f[13] = o.opa;
+    }
+}
+
+void shim_head_full_bwd(int n, const float* raw, const float* edge, float esf, float eob, const float* trig,
+                        const float* g_out, float* g_raw, float* g_z, float* g_edge) {
+    for (int i = 0; i < n; ++i) {
+        FrbHeadOut g;
+        const float* f = g_out + 14 * i;
+        for (int k = 0; k < 3; ++k) { g.pos[k] = f[k]; g.scl[k] = f[3 + k]; g.col[k] = f[10 + k]; }
+        for (int k = 0; k < 4; ++k) g.rot[k] = f[6 + k];
+        g.opa = f[13];
+        if (trig) {
+            float gp[3];
+            frb_pose_rotate_bwd(g.pos, trig + 4 * i, gp);
+            g.pos[0] = gp[0]; g.pos[1] = gp[1]; g.pos[2] = gp[2];
+        }
+        frb_head_bwd_one(raw + 16 * i, edge[i], esf, eob, g, g_raw + 16 * i, g_z[i], g_edge[i]);
     }
 }
 }

@@ -163,6 +163,54 @@ def test_fused_scan_emit_sort_equals_the_staged_binning(golden, n_views):
     assert torch.equal(keys[:b.m], b.keys) and torch.equal(gids[:b.m], b.sorted_gids)
 
 
+@pytest.mark.parametrize("case", ["two_views_640x480_ties", "one_view_33x17", "three_views_200x136", "n_1000003"])
+def test_tile_lists_by_bitmap_ranking_equal_the_key_sort(case):
+    """csrc/tile_lists.cu (count -> scan -> emit depth ranks -> per-tile bitmap ranking) produces the same sorted
+    keys, Gaussian ids, ranges, gathered records and instance count as the stable 64-bit key sort, bit for bit:
+    more than 1024 tiles (several rounds of the one-CTA scan), exact depth ties (order decided by the index),
+    a tiny image, several views, and a cloud at the bitmap's size limit."""
+    import fresnel_b200.renderer as R
+    d = dev()
+    if case == "two_views_640x480_ties":
+        n1, W, H, views = 30011, 640, 480, 2
+        inp = fo.synthetic_cloud(n1 * views, 61, 0.005, 0.05)
+        inp["positions"][:, 2] = torch.round(inp["positions"][:, 2] * 16) / 16       # massive exact ties
+    elif case == "one_view_33x17":
+        n1, W, H, views = 777, 33, 17, 1
+        inp = fo.synthetic_cloud(n1, 62, 0.01, 0.2)
+    elif case == "three_views_200x136":
+        n1, W, H, views = 4111, 200, 136, 3
+        inp = fo.synthetic_cloud(n1 * views, 63, 0.01, 0.06)
+    else:
+        n1, W, H, views = 1_000_003, 256, 256, 1
+        inp = fo.synthetic_cloud(n1, 64, 0.002, 0.01)
+    t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+    cams = [fresnel_b200.Camera(0.8 * W, 0.8 * W, W / 2 + 2 * v, H / 2 - v, W, H) for v in range(views)]
+    camv = np.stack([camera_vector(c, W, H) for c in cams])
+    assert n1 * views <= _lib.lib().frb_tile_lists_max_gaussians()
+    res = []
+    for lists in (True, False):
+        R.TILE_LISTS = lists
+        try:
+            b = build_bins(t["positions"], t["scales"], t["rotations"], t["colors"], t["opacities"], camv, views, W, H,
+                           64.0, keep_debug=True, sort=True)
+        finally:
+            R.TILE_LISTS = True
+        torch.cuda.synchronize()
+        res.append(b)
+    a, b = res
+    assert a.m == b.m and a.m > 0
+    assert torch.equal(a.ranges, b.ranges)
+    assert torch.equal(a.keys, b.keys)
+    assert torch.equal(a.sorted_gids, b.sorted_gids)
+    assert torch.equal(a.sorted_records[:a.m].view(torch.int32), b.sorted_records[:b.m].view(torch.int32))
+    # the launch order is a permutation of the tiles, longest lists first (buckets of 8 entries)
+    order = a.tile_order.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(order.size))
+    ln = (a.ranges[:, 1] - a.ranges[:, 0]).cpu().numpy()[order] >> 3
+    assert np.all(np.diff(np.minimum(ln, 1023)) <= 0)
+
+
 @pytest.mark.parametrize("presort", [True, False])
 def test_tile_keys_bit_exact(golden, presort):
     """Sorted 64-bit (tile | depth) keys, Gaussian ids and tile ranges equal the oracle's, both via
@@ -404,6 +452,22 @@ def test_phase_blending_config4_zone_inputs(golden, t_eps):
         assert rel(grads[k], z["grad_" + k]) < GRAD_TOL, (k, rel(grads[k], z["grad_" + k]))
 
 
+@pytest.mark.parametrize("t_eps", [0.0, fresnel_b200.DEFAULT_T_EPS])
+def test_phase_blending_config4_full_size_forward(golden, t_eps):
+    """BASELINE configs[3] in full (200,000 Gaussians, 512x512, 8 depth zones, edge-aware inputs, phase blending):
+    image, depth and alpha against the unmodified reference's forward pass (the gradients of this configuration are
+    pinned at 20k / 256x256 by test_phase_blending_config4_zone_inputs)."""
+    z = golden("c4_zones_phase_200k_512")
+    W, H = int(z["W"]), int(z["H"])
+    inp = golden_inputs(z, with_phases=True)
+    cam = oracle_camera(z["cam"], W, H)
+    img, dep, alpha, _ = render_gpu(inp, cam, W, H, tuple(float(x) for x in z["bg"]), t_eps, int(z["max_radius"]),
+                                    phases=True, amp=float(z["phase_amplitude"]))
+    assert rel(img, z["image"]) < IMG_TOL, rel(img, z["image"])
+    assert rel(dep, z["depth"]) < IMG_TOL, rel(dep, z["depth"])
+    assert rel(alpha, z["alpha"]) < IMG_TOL, rel(alpha, z["alpha"])
+
+
 def test_phase_blending_fresh_scene_long_lists():
     """Many overlaps per pixel (several 32-entry checkpoint blocks and TMA batches), coloured background,
     oracle run live; phases of all Gaussians receive gradients."""
@@ -441,7 +505,7 @@ def test_wave_renderer_matches_reference_golden(golden, name):
     img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
                    return_depth=True, phases=L["phases"])
     assert rel(img.detach().cpu(), z["image"]) < IMG_TOL, rel(img.detach().cpu(), z["image"])
-    assert rel(dep.detach().cpu(), z["depth"]) < 5e-5, rel(dep.detach().cpu(), z["depth"])
+    assert rel(dep.detach().cpu(), z["depth"]) < IMG_TOL, rel(dep.detach().cpu(), z["depth"])     # measured 1.4e-6
     torch.autograd.backward((img, dep), (torch.from_numpy(z["gimage"]).to(d), torch.from_numpy(z["gdepth"]).to(d)))
     for k in GRAD_NAMES + ("phases",):
         assert rel(L[k].grad.cpu(), z["grad_" + k]) < GRAD_TOL, (k, rel(L[k].grad.cpu(), z["grad_" + k]))
@@ -752,6 +816,74 @@ def test_fused_decoder_head_matches_torch_ops():
     model.fused_head = True
 
 
+def test_fused_decoder_head_fresnel_options_match_torch_ops():
+    """csrc/head.cu with the Fresnel zone snap, the trained edge detector's modulation (incl. the gradient that flows
+    back into the detector's convolutions) and the pose rotation, against the PyTorch restatement (which
+    tests/test_training_cpu.py pins to the reference's DirectPatchDecoder): outputs and every parameter gradient."""
+    from fresnel_b200.training import PatchGaussianDecoder
+    torch.manual_seed(0)
+    model = PatchGaussianDecoder(384, 4, use_fresnel_zones=True, num_fresnel_zones=8, use_edge_aware=True,
+                                 edge_opacity_boost=0.6).to(dev()).eval()
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(3, 384, 37, 37, generator=g).to(dev())
+    depth = torch.rand(3, 1, 64, 64, generator=g).to(dev())
+    el = torch.tensor([0.1, -0.3, 0.5], device=dev())
+    az = torch.tensor([0.0, 1.5708, 3.5], device=dev())
+    weights = {k: torch.randn(s, generator=g).to(dev()) for k, s in
+               (("positions", 3), ("scales", 3), ("rotations", 4), ("colors", 3), ("opacities", 1))}
+    for k_sel in (None, 300):
+        res = {}
+        for fused in (True, False):
+            model.fused_head = fused
+            model.zero_grad(set_to_none=True)
+            gen = torch.Generator(device=dev()).manual_seed(5)
+            out = model(feats, depth, stochastic_k=k_sel, generator=gen, elevation=el, azimuth=az)
+            loss = sum((out[k] * (weights[k] if k != "opacities" else weights[k][0])).sum() for k in weights)
+            loss.backward()
+            res[fused] = ({k: v.detach().clone() for k, v in out.items()},
+                          {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+        for k in weights:
+            a, b = res[True][0][k], res[False][0][k]
+            assert a.shape == b.shape
+            assert rel(a.cpu(), b.cpu()) < 1e-5, (k_sel, k, rel(a.cpu(), b.cpu()))
+        assert set(res[True][1]) == set(res[False][1]) and any(n.startswith("edge_detector") for n in res[True][1])
+        for n in res[True][1]:
+            assert rel(res[True][1][n].cpu(), res[False][1][n].cpu()) < 1e-4, (k_sel, n)
+    # the snapped depths: eight distinct z values before the rotation -> check through an unrotated call
+    model.fused_head = True
+    with torch.no_grad():
+        z = model(feats, depth)["positions"][..., 2]
+    assert torch.unique(z).numel() <= 8
+
+
+def test_fused_loss_with_boundary_term_matches_torch_ops():
+    """csrc/loss.cu with the Fresnel boundary-emphasis term (train_gaussian_decoder.py:941-953) against the PyTorch
+    restatement (pinned to the reference's compute_losses in tests/test_training_cpu.py): soft and hard masks."""
+    from fresnel_b200.training import reconstruction_losses, reconstruction_losses_fused
+    from fresnel_b200.zones import FresnelZones
+    g = torch.Generator().manual_seed(14)
+    B, R = 4, 56
+    target = torch.rand(B, 3, R, R, generator=g).to(dev())
+    tdep = torch.rand(B, R, R, generator=g).to(dev())
+    for soft in (True, False):
+        zones = FresnelZones(8, (0.0, 1.0), soft_boundaries=soft).to(dev())
+        for with_depth in (True, False):
+            res = []
+            for fn in (reconstruction_losses_fused, reconstruction_losses):
+                r = torch.rand(B, 3, R, R, generator=torch.Generator().manual_seed(15)).to(dev()).requires_grad_(True)
+                d = (torch.rand(B, R, R, generator=torch.Generator().manual_seed(16)) * 3).to(dev()).requires_grad_(True)
+                if with_depth:
+                    loss = fn(r, target, d, tdep, fresnel_zones=zones, boundary_weight=0.3)
+                else:   # the mask needs the target depth even when no depth was rendered
+                    loss = fn(r, target, None, tdep, fresnel_zones=zones, boundary_weight=0.3)
+                loss.backward()
+                res.append((float(loss), r.grad.cpu(), d.grad.cpu() if with_depth else None))
+            assert abs(res[0][0] - res[1][0]) <= 2e-6 * max(abs(res[1][0]), 1.0), (soft, with_depth, res[0][0], res[1][0])
+            assert rel(res[0][1], res[1][1]) < 1e-5, (soft, with_depth)
+            if with_depth:
+                assert rel(res[0][2], res[1][2]) < 1e-4, (soft, with_depth)
+
+
 def test_full_size_properties_config4_phase_blending():
     """BASELINE.json configs[3] (200k Gaussians, 512x512, phase blending): size-independent properties.
     (a) input permutation leaves the image bit-identical when depths are tie-free (the running phase makes the
@@ -762,6 +894,16 @@ def test_full_size_properties_config4_phase_blending():
     inp = fo.synthetic_cloud(N, seed=0)
     cam = fo.default_camera(W)
     g = torch.Generator().manual_seed(1)
+    # make the depths pairwise distinct: with ties the order (and, through the running phase, the image) legitimately
+    # depends on the input order, and the permutation property below could only be stated with a tolerance
+    for _ in range(20):
+        db = fo.depth_bits(fo.project(inp["positions"], inp["scales"], inp["rotations"], cam)["depth"])
+        _, first = np.unique(db, return_index=True)
+        dup = np.ones(N, bool)
+        dup[first] = False
+        if not dup.any():
+            break
+        inp["positions"][torch.from_numpy(dup), 2] += (torch.rand(int(dup.sum()), generator=g) - 0.5) * 1e-3
     gi, gd = (torch.rand(3, H, W, generator=g) * 2 - 1), (torch.rand(H, W, generator=g) * 2 - 1)
     img0, dep0, a0, gr0 = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.25)
     assert np.isfinite(img0).all() and np.isfinite(dep0).all() and a0.min() >= 0 and a0.max() <= 1 + 1e-6
@@ -771,12 +913,10 @@ def test_full_size_properties_config4_phase_blending():
     pin = {k: v[perm] for k, v in inp.items()}
     img1, dep1, _, gr1 = render_gpu(pin, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.25)
     db = fo.depth_bits(fo.project(inp["positions"], inp["scales"], inp["rotations"], cam)["depth"])
-    if len(np.unique(db)) == N:
-        assert np.array_equal(img0, img1) and np.array_equal(dep0, dep1)
-    else:
-        assert rel(img1, img0) < 1e-4 and rel(dep1, dep0) < 1e-4
+    assert len(np.unique(db)) == N
+    assert np.array_equal(img0, img1) and np.array_equal(dep0, dep1)        # measured: bit-identical
     for k in GRAD_NAMES + ("phases",):
-        assert rel(gr1[k], gr0[k][perm.numpy()]) < 1e-4, k
+        assert rel(gr1[k], gr0[k][perm.numpy()]) < GRAD_TOL, k
     # amplitude 0: interference factor is exactly 1 -> the plain tile compositor (sum form vs product form of T)
     imgz, depz, _, grz = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd, phases=True, amp=0.0)
     imgp, depp, _, grp = render_gpu(inp, cam, W, H, (0.1, 0.0, 0.2), 0.0, 64, gi, gd)
@@ -821,7 +961,7 @@ def test_full_size_properties_config5_asm():
         assert bool(torch.isfinite(L0[k].grad).all()), k
     perm = torch.randperm(N, generator=g)
     img1, _ = run({k: v[perm] for k, v in inp.items()})
-    assert rel(img1.cpu(), img0.cpu()) < 1e-4
+    assert rel(img1.cpu(), img0.cpu()) < IMG_TOL          # summation order only; measured 6e-7
     dcol = (torch.rand(N, 3, generator=g) - 0.5)
     eps = 1e-3
     plus = dict(inp); plus["colors"] = inp["colors"] + eps * dcol

@@ -92,3 +92,48 @@ def test_head_backward_matches_autograd(host_shim):
         assert err.max() < 2e-3, (float(err.max()), int(err.max(axis=1).argmax()))
         assert np.median(err.max(axis=1)) < 1e-5
         assert rel(g_z, b.grad.numpy()[:, 2]) < 1e-6
+
+
+def test_full_head_zone_snap_pose_rotation_and_edge_gradient(host_shim):
+    """The head as head.cu sequences it (frb_zone_center -> frb_head_fwd_one -> frb_pose_rotate, and the backward with
+    frb_pose_rotate_bwd and the edge-strength gradient) against the PyTorch restatement of
+    gaussian_decoder_models.py:833-838, :51-104 / :860 and :881-895 and its autograd."""
+    from fresnel_b200.training import rotate_positions_for_pose
+    from fresnel_b200.zones import FresnelZones
+    g = torch.Generator().manual_seed(21)
+    n = 4000
+    raw = torch.randn(n, 16, generator=g) * 1.5
+    base_xy = torch.rand(n, 2, generator=g) * 2 - 1
+    depth = torch.rand(n, generator=g) * 1.3 - 0.15            # some outside the zone range: clamped
+    zones = FresnelZones(8, (0.0, 1.0))
+    depth[:9] = zones.zone_boundaries                          # exactly on the boundaries (bucketize, right=False)
+    edge = torch.rand(n, generator=g)
+    el, az = torch.rand(n, generator=g) - 0.5, torch.rand(n, generator=g) * 6.28
+    trig = torch.stack([torch.cos(az), torch.sin(az), torch.cos(el), torch.sin(el)], -1).contiguous()
+    off, esf, eob = -2.0, 0.5, 0.9
+    zb, zc = zones.zone_boundaries.numpy().copy(), zones.zone_centers.numpy().copy()
+
+    def restatement(raw_t, edge_t, off_t):
+        z = off_t + zones.get_zone_centers_for_depth(depth) * (-2)
+        base = torch.cat([base_xy, z[:, None]], -1)
+        out = torch_head(raw_t, base, edge_t, esf, eob)
+        pos = rotate_positions_for_pose(out[:, None, :3], el, az)[:, 0]      # one "view" per Gaussian
+        return torch.cat([pos, out[:, 3:]], -1)
+
+    out = np.zeros((n, 14), np.float32)
+    host_shim.shim_head_full_fwd(n, P(raw.numpy()), P(base_xy.numpy()), P(depth.numpy()), ctypes.c_float(off),
+                                 P(edge.numpy()), ctypes.c_float(esf), ctypes.c_float(eob), 8, P(zb), P(zc),
+                                 P(trig.numpy()), P(out))
+    want = restatement(raw, edge, torch.tensor(off)).numpy()
+    assert np.allclose(out, want, rtol=2e-5, atol=3e-6), float(np.abs(out - want).max())
+
+    r, e, o = raw.clone().requires_grad_(True), edge.clone().requires_grad_(True), torch.tensor(off, requires_grad=True)
+    g_out = torch.randn(n, 14, generator=torch.Generator().manual_seed(5))
+    (restatement(r, e, o) * g_out).sum().backward()
+    g_raw, g_z, g_e = np.zeros((n, 16), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    host_shim.shim_head_full_bwd(n, P(raw.numpy()), P(edge.numpy()), ctypes.c_float(esf), ctypes.c_float(eob),
+                                 P(trig.numpy()), P(np.ascontiguousarray(g_out.numpy())), P(g_raw), P(g_z), P(g_e))
+    err = np.abs(g_raw - r.grad.numpy()) / np.maximum(np.abs(r.grad.numpy()).max(axis=1, keepdims=True), 1e-3)
+    assert err.max() < 2e-3 and np.median(err.max(axis=1)) < 1e-5, float(err.max())
+    assert rel(g_e, e.grad.numpy()) < 1e-5
+    assert abs(float(g_z.astype(np.float64).sum()) - float(o.grad)) < 1e-3 * max(1.0, abs(float(o.grad)))

@@ -105,3 +105,51 @@ def test_ply_device_transforms_match_oracle(tmp_path):
     for k in GRAD_NAMES:
         assert np.allclose(back[k].cpu().numpy(), want[k], rtol=2e-6, atol=1e-7), k
         assert np.allclose(back[k].cpu().numpy(), inp[k].numpy(), rtol=1e-5, atol=1e-6), k   # save -> load round trip
+
+
+def _ply_fixture():
+    z = np.load(os.path.join(GOLD, "cloud_97_ply.npz"))
+    return z["rows_in"], z["file_rows"], z["rows_loaded"]
+
+
+def _split(rows):
+    return {"positions": rows[:, 0:3], "scales": rows[:, 3:6], "rotations": rows[:, 6:10], "colors": rows[:, 10:13],
+            "opacities": rows[:, 13]}
+
+
+def _close_or_same_inf(a, b, rtol, atol):
+    with np.errstate(all="ignore"):
+        return np.isclose(a, b, rtol=rtol, atol=atol) | (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)))
+
+
+def test_oracle_ply_matches_reference_cpp_fixture():
+    """The .ply pin: tests/golden/cloud_97.ply was written by the reference's own GaussianCloud::save_ply and read back
+    by its load_ply (renderer.cpp:649-793, compiled by oracle/build_ref.sh).  The oracle's encode reproduces the file
+    body, its decode the loaded values, including the 1e-7 scale floor, logit(0) = -inf, logit(1) and the colour clamp."""
+    rows_in, file_rows, rows_loaded = _ply_fixture()
+    body = fio.read_ply_rows(os.path.join(GOLD, "cloud_97.ply"))
+    assert np.array_equal(body.view(np.uint32), file_rows.view(np.uint32))
+    enc = fo.ply_encode_rows(_split(rows_in))
+    assert _close_or_same_inf(enc, file_rows, 2e-6, 2e-6).all()
+    dec = fo.ply_decode_rows(file_rows)
+    for k, v in _split(rows_loaded).items():
+        assert np.allclose(np.asarray(dec[k]).reshape(v.shape), v, rtol=2e-6, atol=1e-7), k
+
+
+@pytest.mark.gpu
+def test_ply_device_loader_and_saver_match_reference_cpp_fixture(tmp_path):
+    """frb_unpack_gaussians / frb_pack_gaussians (ply mode) against the file the reference's C++ wrote and the values
+    its C++ loaded."""
+    dev = torch.device("cuda:0")
+    rows_in, file_rows, rows_loaded = _ply_fixture()
+    g = fresnel_b200.load_gaussians_from_ply(os.path.join(GOLD, "cloud_97.ply"), device=dev)
+    for k, v in _split(rows_loaded).items():
+        assert np.allclose(g[k].cpu().numpy().reshape(v.shape), v, rtol=2e-6, atol=1e-7), k
+    out = tmp_path / "mine.ply"
+    fresnel_b200.save_gaussians_to_ply(str(out), {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+                                                  for k, v in _split(rows_in).items()})
+    mine = fio.read_ply_rows(str(out))
+    assert _close_or_same_inf(mine, file_rows, 2e-6, 2e-6).all(), np.argwhere(~_close_or_same_inf(mine, file_rows, 2e-6, 2e-6))
+    # same header as the reference's writer, byte for byte
+    ref_bytes = open(os.path.join(GOLD, "cloud_97.ply"), "rb").read()
+    assert out.read_bytes()[:-97 * 14 * 4] == ref_bytes[:-97 * 14 * 4]

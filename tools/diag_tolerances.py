@@ -42,6 +42,31 @@ for name in ("wave_scalar_2k_128", "wave_rgb_2k_128", "wave_rot_1500_112x80"):
         row["ref32_vs_f64"] = rel(z["depth"], z["depth64"])
     out[name] = row
 
+# high-overlap tile fixtures: where and how large is the deviation from the reference (and from its fp64 run)?
+for name in ("tile_overlap_faint_20k_128", "tile_overlap_20k_128", "c4_zones_tile_20k_256"):
+    z = gold(name)
+    W, H = int(z["W"]), int(z["H"])
+    cam = oracle_camera(z["cam"], W, H)
+    L = {k: torch.from_numpy(z["in_" + k]).to(d) for k in GRAD_NAMES}
+    row = {}
+    for t_eps in (0.0, fresnel_b200.DEFAULT_T_EPS):
+        ren = fresnel_b200.TileBasedRenderer(W, H, background=tuple(float(x) for x in z["bg"]),
+                                             max_radius=int(z["max_radius"]), t_eps=t_eps)
+        img, dep, alpha = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
+                              return_depth=True, return_alpha=True)
+        e = np.abs(dep.cpu().numpy().astype(np.float64) - z["depth"])
+        i = np.unravel_index(e.argmax(), e.shape)
+        r = {"image": rel(img.cpu(), z["image"]), "depth": rel(dep.cpu(), z["depth"]), "alpha": rel(alpha.cpu(), z["alpha"]),
+             "worst_px": [int(i[0]), int(i[1])], "gpu": float(dep[i]), "ref": float(z["depth"][i]),
+             "alpha_there": float(alpha[i]), "depth_max": float(np.abs(z["depth"]).max())}
+        f64 = os.path.join("/tmp/gold", name + "_f64.npz")
+        if "depth64" in z:
+            r.update({"image_vs_f64": rel(img.cpu(), z["image64"]), "depth_vs_f64": rel(dep.cpu(), z["depth64"]),
+                      "ref32_image_vs_f64": rel(z["image"], z["image64"]), "ref32_depth_vs_f64": rel(z["depth"], z["depth64"]),
+                      "depth64_there": float(z["depth64"][i])})
+        row[str(t_eps)] = r
+    out[name] = row
+
 # config-4 / config-5 sized permutation checks on tie-free clouds
 def unique_depth_cloud(n, **kw):
     inp = fo.synthetic_cloud(n, **kw)
