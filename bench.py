@@ -340,7 +340,7 @@ def measure_train(args, rank, world, dev, full, steps, flush, sampler=None):
     result dictionary (identical on every rank: times are the max over ranks)."""
     from fresnel_b200 import _lib
     from fresnel_b200.host import BatchPrefetcher
-    from fresnel_b200.training import DecoderTrainer, PatchGaussianDecoder, allreduce_gradients
+    from fresnel_b200.training import DecoderTrainer, PatchGaussianDecoder
     L = _lib.lib()
     torch.manual_seed(0)
     model = PatchGaussianDecoder(384, 4).to(dev)
@@ -367,7 +367,7 @@ def measure_train(args, rank, world, dev, full, steps, flush, sampler=None):
         prefetch.fence()
 
     def exchange_only():
-        allreduce_gradients(model.parameters())
+        trainer.exchange()
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -402,10 +402,11 @@ def measure_train(args, rank, world, dev, full, steps, flush, sampler=None):
                                   "decoder gradients per step"},
         "e2e": {"value": world * TRAIN_B * steps / (tot_e2e * 1e-3), "unit": "views/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": tot_e2e / steps},
-        "exchange": {"kind": "NCCL all-reduce (SUM) of the flat decoder gradient + 1/world scale" if world > 1
+        "exchange": {"kind": "one NCCL all-reduce (SUM) of the flat decoder gradient buffer" if world > 1
                              else "none (one rank)",
                      "bytes": 4 * n_par, "ms": x_ms, "share_of_step": x_ms / step_ms,
-                     "note": "timed alone (cat + all-reduce + scatter back), median, max over ranks"},
+                     "note": "the collective timed alone (the pack / unpack kernels are inside the two captured "
+                             "halves of the step), median, max over ranks"},
         "gpu_launches": int(launches)}
 
 
@@ -714,7 +715,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--t-eps", type=float, default=None)
-    ap.add_argument("--workload", default="render", choices=["render", "train", "train_full", "multiview"])
+    ap.add_argument("--workload", default="render", choices=["render", "train", "train_full", "multiview", "phase"])
     ap.add_argument("--mv-gaussians", type=int, default=1_000_000)
     ap.add_argument("--mv-res", type=int, default=1024)
     ap.add_argument("--pipeline-depth", type=int, default=6, help="render e2e: host-to-host steps in flight")
@@ -740,6 +741,18 @@ def main():
             run_multiview_reference(args, rank)
         else:
             run_multiview(args, rank, world, local)
+        return
+    if args.workload == "phase":
+        if args.impl == "reference":
+            raise SystemExit("bench.py: --workload phase has no CPU arm (use the render / train / multiview arms)")
+        import torch.distributed as dist
+        dev = init_distributed(local, world)
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        line = measure_phase(args, rank, world, dev, args.steps, flush)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
         return
     if args.workload != "render":
         full = args.workload == "train_full"

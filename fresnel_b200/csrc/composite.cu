@@ -464,12 +464,12 @@ extern "C" int frb_tile_schedule(int n_tiles, const int32_t* ranges, int32_t* ti
 }
 
 // composite_phase.cu
-int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* ranges,
-                                   const float* sorted_records, const float* sorted_phases, float phase_amplitude,
+int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* tile_order,
+                                   const int32_t* ranges, const float* sorted_records, const float* sorted_phases, float phase_amplitude,
                                    const float* background_host, float t_eps, float* image, float* depth,
                                    float* alpha, float* state_T, int32_t* state_n, float* ckpt, cudaStream_t st);
-int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int32_t* ranges,
-                                   const float* sorted_records, const uint32_t* sorted_gids,
+int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int32_t* tile_order,
+                                   const int32_t* ranges, const float* sorted_records, const uint32_t* sorted_gids,
                                    const float* sorted_phases, float phase_amplitude, const float* background_host,
                                    const float* state_T, const int32_t* state_n, const float* ckpt,
                                    const float* g_image, const float* g_depth, const float* g_alpha, float* grad2d,
@@ -512,7 +512,7 @@ extern "C" int frb_composite_fwd_cap(int n_views, int width, int height, const i
     if (rc) return rc;
     if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n) return FRB_E_INVALID;
     if (sorted_phases)
-        return frb_composite_phase_fwd_launch(n_views, width, height, ranges, sorted_records, sorted_phases,
+        return frb_composite_phase_fwd_launch(n_views, width, height, tile_order, ranges, sorted_records, sorted_phases,
                                               phase_amplitude, background_host, t_eps, image, depth, alpha,
                                               state_T, state_n, ckpt, (cudaStream_t)stream);
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
@@ -563,7 +563,7 @@ extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const i
     if (rc) return rc;
     if (!ranges || !background_host || !state_T || !state_n || !g_image || !grad2d) return FRB_E_INVALID;
     if (sorted_phases)
-        return frb_composite_phase_bwd_launch(n_views, width, height, ranges, sorted_records, sorted_gids,
+        return frb_composite_phase_bwd_launch(n_views, width, height, tile_order, ranges, sorted_records, sorted_gids,
                                               sorted_phases, phase_amplitude, background_host, state_T, state_n,
                                               ckpt, g_image, g_depth, g_alpha, grad2d, g_phases,
                                               (cudaStream_t)stream);

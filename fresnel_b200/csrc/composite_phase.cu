@@ -50,7 +50,8 @@ __device__ __forceinline__ void phase_step(float g, float o, float phi, float A,
 }
 
 __global__ void __launch_bounds__(CTA_THREADS)
-composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
+composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view,
+                           const int* __restrict__ tile_order, const int2* __restrict__ ranges,
                            const float4* __restrict__ sorted_records, const float* __restrict__ sorted_phases,
                            float A, float3 bg, float t_eps, float* __restrict__ image,
                            float* __restrict__ depth_out, float* __restrict__ alpha_out,
@@ -59,7 +60,7 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     __shared__ float phase_s[STAGES][BATCH];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;   // heaviest tiles first
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
@@ -181,7 +182,8 @@ struct PhaseBwdSmem {
 };
 
 __global__ void __launch_bounds__(CTA_THREADS, 2)
-composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int2* __restrict__ ranges,
+composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view,
+                           const int* __restrict__ tile_order, const int2* __restrict__ ranges,
                            const float4* __restrict__ sorted_records, const uint32_t* __restrict__ sorted_gids,
                            const float* __restrict__ sorted_phases, float A, float3 bg,
                            const float* __restrict__ state_T, const int* __restrict__ state_n,
@@ -191,7 +193,7 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhaseBwdSmem& sm = *reinterpret_cast<PhaseBwdSmem*>(smem_raw);
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;   // heaviest tiles first
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
@@ -432,7 +434,8 @@ extern "C" size_t frb_phase_ckpt_floats(int m, int n_tiles) {
     return ((size_t)(m >> 5) + (size_t)n_tiles + 2) * CTA_THREADS * 2;
 }
 
-int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* ranges,
+int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int32_t* tile_order,
+                                   const int32_t* ranges,
                                    const float* sorted_records, const float* sorted_phases, float phase_amplitude,
                                    const float* background_host, float t_eps, float* image, float* depth,
                                    float* alpha, float* state_T, int32_t* state_n, float* ckpt, cudaStream_t st) {
@@ -440,14 +443,15 @@ int frb_composite_phase_fwd_launch(int n_views, int width, int height, const int
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     composite_phase_fwd_kernel<<<n_views * tpv, CTA_THREADS, 0, st>>>(
-        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_phases,
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_phases,
         phase_amplitude, bg, t_eps, image, depth, alpha, state_T, state_n, (float2*)ckpt);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
 }
 
-int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int32_t* ranges,
+int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int32_t* tile_order,
+                                   const int32_t* ranges,
                                    const float* sorted_records, const uint32_t* sorted_gids,
                                    const float* sorted_phases, float phase_amplitude, const float* background_host,
                                    const float* state_T, const int32_t* state_n, const float* ckpt,
@@ -460,8 +464,9 @@ int frb_composite_phase_bwd_launch(int n_views, int width, int height, const int
     static unsigned long long smem_opted_in = 0;          // per-device bitmask
     FRB_CUDA_OK(frb_opt_in_smem(composite_phase_bwd_kernel, (int)sizeof(PhaseBwdSmem), &smem_opted_in));
     composite_phase_bwd_kernel<<<n_views * tpv, CTA_THREADS, sizeof(PhaseBwdSmem), st>>>(
-        width, height, tiles_x, tpv, (const int2*)ranges, (const float4*)sorted_records, sorted_gids, sorted_phases,
-        phase_amplitude, bg, state_T, state_n, (const float2*)ckpt, g_image, g_depth, g_alpha, grad2d, g_phases);
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
+        sorted_phases, phase_amplitude, bg, state_T, state_n, (const float2*)ckpt, g_image, g_depth, g_alpha, grad2d,
+        g_phases);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

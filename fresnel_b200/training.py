@@ -403,9 +403,9 @@ class DecoderTrainer:
     """One optimisation step of experiment 2: decoder -> [subsample] -> batched render -> losses ->
     backward -> gradient all-reduce -> clip -> AdamW (train_epoch, train_gaussian_decoder.py:1031-1266).
 
-    ``cuda_graph=True`` captures [decoder .. backward] and [clip + AdamW] as two CUDA graphs and replays
-    them (the renderer's forward is sync-free and allocation-static, so the whole step is capturable);
-    the gradient all-reduce runs between the two replays.  The step is launch-bound otherwise
+    ``cuda_graph=True`` captures [decoder .. backward, gradient pack] and [unpack, clip, AdamW] as two CUDA graphs
+    and replays them (the renderer's forward is sync-free and allocation-static, so the whole step is capturable);
+    between the two replays runs the step's only collective, ONE all-reduce of the flat gradient buffer.  The step is launch-bound otherwise
     (about 250 small kernels for 16 views of 256 Gaussians).
     """
 
@@ -438,6 +438,7 @@ class DecoderTrainer:
         elif dev.type == "cuda":
             torch.cuda.manual_seed(seed)
         self._graphs = None
+        self._flat_grad = None
         self.kernels_per_replay = 0
 
     def broadcast_parameters(self):
@@ -458,11 +459,50 @@ class DecoderTrainer:
         loss = loss_fn(rendered, images, rendered_depth, target_depth, fresnel_zones=self.loss_zones,
                        boundary_weight=self.boundary_weight)
         loss.backward()
+        if self._world() > 1:
+            self._pack_gradients()
         return loss.detach()
 
+    # ---- gradient exchange: pack -> ONE all-reduce -> unpack, with the pack / unpack inside the captured halves ----
+    def _world(self) -> int:
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _grad_params(self):
+        return [p for p in self.model.parameters() if p.requires_grad]
+
+    def _pack_gradients(self):
+        """All decoder gradients into one persistent flat buffer (one ``cat`` kernel; captured with the backward)."""
+        params = self._grad_params()
+        if self._flat_grad is None:
+            n = sum(p.numel() for p in params)
+            self._flat_grad = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        torch.cat([p.grad.reshape(-1) for p in params], out=self._flat_grad)
+
+    def _unpack_gradients(self, world: int):
+        """Mean over ranks written back into the parameters' .grad (captured with the update)."""
+        params = self._grad_params()
+        self._flat_grad.div_(world)
+        views, off = [], 0
+        for p in params:
+            views.append(self._flat_grad[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        torch._foreach_copy_([p.grad for p in params], views)
+
     def _update(self):
+        world = self._world()
+        if world > 1:
+            self._unpack_gradients(world)
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
         self.optimizer.step()
+
+    def exchange(self):
+        """The collective of the step: one NCCL all-reduce (SUM) of the flat gradient buffer - 2.5 MB for the
+        632,257-parameter decoder; the packing and the 1 / world scaling live in the captured halves around it."""
+        if self._world() > 1:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
 
     def _capture(self, features, depth, images):
         static = [torch.empty_like(t) for t in (features, depth, images)]
@@ -510,12 +550,12 @@ class DecoderTrainer:
             for s, t in zip(static, (features, depth, images)):
                 s.copy_(t, non_blocking=True)
             g1.replay()                                         # gradients are rewritten in place by the replay
-            allreduce_gradients(self.model.parameters())
+            self.exchange()
             g2.replay()
             return loss
         self.optimizer.zero_grad(set_to_none=True)
         loss = self._forward_backward(features, depth, images)
-        allreduce_gradients(self.model.parameters())
+        self.exchange()
         self._update()
         return loss
 

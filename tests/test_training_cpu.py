@@ -175,6 +175,56 @@ def test_gradient_allreduce_world_size_2_gloo():
     assert res[0][2] == 6 * 5 + 5 + 5 * 2 + 2
 
 
+def _trainer_worker(rank, world, port, q):
+    """DecoderTrainer's exchange path on the CPU: pack -> one all-reduce of the flat buffer -> unpack (mean), then
+    clip + AdamW, against the single-process mean of both ranks' gradients."""
+    from fresnel_b200.training import DecoderTrainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        ref.load_state_dict(model.state_dict())
+        tr = DecoderTrainer(model, 8, lr=1e-2)
+        data = [torch.randn(4, 6, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        grads = []
+        for r in range(world):
+            ref.zero_grad()
+            ref(data[r]).pow(2).mean().backward()
+            grads.append([p.grad.clone() for p in ref.parameters()])
+        want = [sum(g[i] for g in grads) / world for i in range(len(grads[0]))]
+        model.zero_grad()
+        model(data[rank]).pow(2).mean().backward()
+        tr._pack_gradients()
+        tr.exchange()
+        tr._unpack_gradients(world)
+        ok = all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(model.parameters(), want))
+        # the whole update (unpack is part of _update): both ranks must end with identical parameters
+        model.zero_grad()
+        model(data[rank]).pow(2).mean().backward()
+        tr._pack_gradients()
+        tr.exchange()
+        tr._update()
+        q.put((rank, bool(ok), float(sum(p.detach().double().sum() for p in model.parameters()))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_packed_exchange_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+    assert res[0][2] == res[1][2]
+
+
 class _ToyRenderer(torch.nn.Module):
     """CPU stand-in with the renderer call signature (the CUDA renderers have no CPU path): a smooth function
     of all five parameter tensors and the camera's fx."""
