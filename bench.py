@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
     est = t * (N_GAUSS / n_s)
     sampled = (f"{args.steps} sampled steps of the first {n_s} of {N_GAUSS} Gaussians at {RES}x{RES}: fwd+bwd "
                f"{t:.2f} s/step, scaled linearly in N -> {est:.1f} s/frame ({1.0 / est:.5f} frames/s, extrapolated)")
-    full_s = None
+    full_s, full_note = None, "not attempted (--ref-full-budget 0)"
     if args.ref_full_budget > 0:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-full-child"],
@@ -185,8 +185,9 @@ def run_reference(args, rank, world):
             for ln in r.stdout.splitlines():
                 if ln.startswith("FULL_FRAME_SECONDS "):
                     full_s = float(ln.split()[1])
+            full_note = "ok" if full_s is not None else f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"
         except subprocess.TimeoutExpired:
-            full_s = None
+            full_s, full_note = None, f"child killed after {args.ref_full_budget:.0f} s"
     if full_s is not None:
         value, ms_per_step, steps, warmup = 1.0 / full_s, full_s * 1e3, 1, 0
         how = (f"oracle port of TileBasedRenderer (reference is Python and absent from the GPU box): ONE full frame, "
@@ -203,7 +204,7 @@ def run_reference(args, rank, world):
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"single-view render fwd+bwd, {N_GAUSS} Gaussians, {RES}x{RES} (BASELINE configs[1])",
-                   "full_frame_measured": measured},
+                   "full_frame_measured": measured, "full_frame_child": full_note},
         "extrapolated_from_sample": {"value": 1.0 / est, "unit": UNIT, "sample_gaussians": n_s,
                                      "sample_ms_per_step": t * 1e3},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -214,9 +215,30 @@ def run_reference(args, rank, world):
 
 def run_reference_full_child():
     """Child of run_reference: one full frame of the port, prints its wall time."""
+    import resource
+    import threading
     torch.set_num_threads(os.cpu_count() or 1)
-    cpu_frame_time(200)                       # import / allocator warm-up
-    print(f"FULL_FRAME_SECONDS {cpu_frame_time(N_GAUSS):.3f}", flush=True)
+    n = int(os.environ.get("FRB_REF_FULL_N", N_GAUSS))      # (test hook: a smaller cloud)
+    # The tape of the full frame is a chain of ~10^5 in-place slice updates; tearing it down recurses about that deep in
+    # libtorch and overflows the default 8 MB stack (the child died with SIGSEGV on the GPU box): run the frame on a
+    # thread with a 1 GiB stack, with the process limit lifted where the hard limit allows.
+    try:
+        soft, hard = resource.getrlimit(resource.RLIMIT_STACK)
+        resource.setrlimit(resource.RLIMIT_STACK, (hard, hard))
+    except (ValueError, OSError):
+        pass
+    out = {}
+
+    def work():
+        cpu_frame_time(200)                   # import / allocator warm-up
+        out["t"] = cpu_frame_time(n)
+
+    threading.stack_size(1 << 30)
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    print(f"FULL_FRAME_SECONDS {out['t']:.3f}", flush=True)
+    os._exit(0)                               # skip interpreter teardown of whatever is left of the tape
 
 
 # --------------------------------------------------------------------------------------
@@ -805,11 +827,20 @@ def main():
     # graph (fresnel_b200/host.py HostRenderPipeline).  Every step still copies its inputs up and its results down
     # inside the bracket; step i+1's H2D and step i's D2H overlap the other step's kernels.
     from fresnel_b200.host import HostRenderPipeline
-    pipe = HostRenderPipeline(ren, N_GAUSS, dev, depth=args.pipeline_depth)
+    pipe = pipe_full = HostRenderPipeline(ren, N_GAUSS, dev, depth=args.pipeline_depth)
     for s_ in pipe.slots:
         s_.load(host, gi_h, gd_h)
 
-    def timed_pipeline(steps, with_flush=True):
+    # the same pipeline returning the gradients only (image and depth stay on the device: what a training loop needs)
+    pipe_lean = HostRenderPipeline(ren, N_GAUSS, dev, depth=args.pipeline_depth, outputs=("grads",))
+    for s_ in pipe_lean.slots:
+        s_.load(host, gi_h, gd_h)
+
+    def timed_pipeline(steps, with_flush=True, pipe=None):
+        pipe = pipe_full if pipe is None else pipe
+        return _timed_pipeline(pipe, steps, with_flush)
+
+    def _timed_pipeline(pipe, steps, with_flush=True):
         """ONE bracket around ``steps`` pipelined steps (they overlap, so per-step brackets would double count).
         The 256 MiB L2 flush is enqueued on the slot's stream before every step and is INSIDE the bracket."""
         main = torch.cuda.current_stream()
@@ -905,6 +936,10 @@ def main():
     barrier()
     pipe_noflush_ms = timed_pipeline(args.steps, with_flush=False)
     barrier()
+    timed_pipeline(2 * pipe_lean.depth, pipe=pipe_lean)
+    barrier()
+    pipe_lean_ms = timed_pipeline(args.steps, pipe=pipe_lean)
+    barrier()
 
     # Host-link ceiling of the e2e figure, measured here with every rank copying at once (the same pinned buffers,
     # H2D and D2H concurrently on two streams, no kernels): frames/s the PCIe / host-memory side could deliver if
@@ -934,7 +969,7 @@ def main():
         return a.elapsed_time(b) / reps
 
     link_probe(2)
-    link_ms = link_probe()
+    link_ms = min(link_probe(16) for _ in range(3))      # best of three: a ceiling, not an average
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -944,13 +979,14 @@ def main():
         timed(step_resident, args.steps)
     stages = {k: sum(v) / len(v) for k, v in st.summary().items()}
 
-    tot = _max_over_ranks([sum(ms), sum(ms_e2e), pipe_ms, pipe_noflush_ms, link_ms], dev, world)
-    tot_ms, tot_e2e_ms, tot_pipe_ms, tot_pipe_nf_ms, link_ms = tot
+    tot = _max_over_ranks([sum(ms), sum(ms_e2e), pipe_ms, pipe_noflush_ms, link_ms, pipe_lean_ms], dev, world)
+    tot_ms, tot_e2e_ms, tot_pipe_ms, tot_pipe_nf_ms, link_ms, tot_lean_ms = tot
+    lean_d2h = pipe_lean.d2h_bytes
 
     # the workloads north_star asks scaling numbers for, measured in this same invocation at this same N
     workloads = {}
     if not args.no_workloads:
-        del pipe, session
+        del pipe, pipe_full, pipe_lean, session
         torch.cuda.empty_cache()
         w_steps = max(5, min(args.steps, 20))
         workloads["train"] = measure_train(args, rank, world, dev, False, args.steps, flush)
@@ -1016,11 +1052,17 @@ def main():
                     "ms_per_step": tot_pipe_ms / args.steps, "pipeline_depth": args.pipeline_depth,
                     "value_no_flush": world * args.steps / (tot_pipe_nf_ms * 1e-3),
                     "serial": {"value": e2e_serial, "ms_per_step": tot_e2e_ms / args.steps},
+                    "gradients_only": {"value": world * args.steps / (tot_lean_ms * 1e-3), "unit": UNIT,
+                                       "ms_per_step": tot_lean_ms / args.steps, "h2d_bytes_per_step": h2d,
+                                       "d2h_bytes_per_step": lean_d2h,
+                                       "note": "same pipeline with outputs=('grads',): image and depth stay on the "
+                                               "device (HostRenderSession(outputs=...)), the five gradients return"},
                     "host_link_ceiling": {
                         "value": world / (link_ms * 1e-3), "unit": UNIT, "ms_per_step": link_ms,
                         "h2d_gbs_per_gpu": h2d / (link_ms * 1e-3) / 1e9, "d2h_gbs_per_gpu": d2h / (link_ms * 1e-3) / 1e9,
                         "note": "this step's H2D and D2H copies alone (same pinned buffers, both directions at once, "
-                                "all ranks at once, no kernels), max over ranks: the e2e figure cannot exceed it"}},
+                                "all ranks at once, no kernels; best of three 16-step trials), max over ranks: the "
+                                "host-to-host figure is bounded by about this"}},
             "step_ms": {"min": min(ms), "median": statistics.median(ms), "max": max(ms),
                         "e2e_min": min(ms_e2e), "e2e_median": statistics.median(ms_e2e), "e2e_max": max(ms_e2e),
                         "host_enqueue": enqueue.get(step_timed.__name__)},
@@ -1054,7 +1096,9 @@ def stage_algorithmic_bytes(N, HW, M):
         "frb_tile_offsets": 3 * 4 * N,
         "frb_bin_emit": 20 * N + 12 * M,
         "frb_bin_sort_dev": 20 * N + 12 * M + 2 * (2 * 12 * M),
-        "frb_bin_tiles": 20 * N + 8 * M,
+        "frb_tile_count_scan": 8 * N + 8 * (HW // 256) * 98,
+        "frb_tile_emit": 12 * N + 4 * M,
+        "frb_tile_rank_gather": 8 * M + 4 * M + 96 * M,
         "frb_radix_sort_pairs": 2 * (2 * 12 * M),
         "frb_tile_ranges": 8 * M,
         "frb_gather_records": 4 * M + 96 * M,

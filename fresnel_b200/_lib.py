@@ -30,6 +30,7 @@ _SIGNATURES = {
     "frb_depth_order_workspace_bytes": (c_size_t, [c_int]),
     "frb_depth_order": (c_int, [c_int, P, P, P, P]),
     "frb_depth_order_rank": (c_int, [c_int, P, P, P, P, P]),
+    "frb_depth_order_range": (c_int, [c_int, P, c_float, c_float, P, P, P, P]),
     "frb_scan_workspace_bytes": (c_size_t, [c_int]),
     "frb_tile_offsets": (c_int, [c_int, P, P, P, P, P]),
     "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
@@ -49,7 +50,9 @@ _SIGNATURES = {
     "frb_tile_lists_max_tiles": (c_int, []),
     "frb_tile_lists_workspace_bytes": (c_size_t, [c_int, c_int]),
     "frb_tile_count": (c_int, [c_int, c_int, c_int, c_int, P, P, P]),
-    "frb_tile_scan": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "frb_tile_scan": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "frb_depth_order_error_word": (P, [c_int, P]),
+    "frb_tile_count_scan": (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, P, P]),
     "frb_tile_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
     "frb_tile_rank_gather": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
     "frb_stage_timing_enable": (c_int, [c_int]),

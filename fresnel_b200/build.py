@@ -76,7 +76,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcufft", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    # --no-undefined: a function declared in the header but lost from the sources must fail the build, not the first load
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcufft", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+           "-Xlinker", "--no-undefined"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -285,75 +285,128 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         const int local_n = my_n - base_n;           // entries j < local_n were applied by this pixel
 
         if (gmask != 0) {
+            // Both walks handle TWO candidates per iteration: everything that does not depend on the running state is
+            // evaluated for both first, then the two serial chains run back to back.  A warp issues in order, so
+            // without this the ~25-instruction dependent chain of one candidate (|phi - Phi| -> cos -> clamp -> c ->
+            // 1 / acc -> Phi' forward; the adjoints Tb, Pb backward) stalls the 70 independent instructions of the
+            // next one behind it (ncu, profiles/r2_g_*: issue slots 57 % busy, "wait" the top stall at 16 warps / SM).
             // ---- phase 1a: forward recompute from the checkpoint ----
             float acc = 0.0f, Phi = 0.0f;
             if (local_n > 0) {
                 const float2 c0 = ckpt[ckpt_slot(range.x, tile, k) * CTA_THREADS + threadIdx.x];
                 acc = c0.x; Phi = c0.y;
             }
+            struct FwdPre { float a0, phi; bool active; };
+            auto fwd_pre = [&](int j) {
+                FwdPre p;
+                p.phi = __shfl_sync(0xffffffffu, phi_l, j);
+                const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                p.active = (j < local_n) &&
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                const float4 r0 = rec[3 * j + 0];
+                const float dx = fpx - r0.x, dy = fpy - r0.y;
+                const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                p.a0 = frb_ex2(power) * r1.y;
+                return p;
+            };
+            auto fwd_step = [&](int j, const FwdPre& p) {
+                my_pair[j * PH_STRIDE + lane] = make_float2(acc, Phi);          // the state BEFORE entry j
+                if (p.active) {
+                    // phase_step with a0 = g * o already formed
+                    const float d0 = fabsf(p.phi - Phi);
+                    const float d = fminf(d0, 1.0f - d0);
+                    const float mm = (1.0f - A) + A * __cosf(d * TWO_PI_REF);
+                    const float alpha = fminf(fmaxf(p.a0 * mm, 0.0f), FRB_ALPHA_MAX);
+                    const float c = alpha * (1.0f - acc);
+                    acc = acc + c;
+                    const float pc = __fdividef(c, fmaxf(acc, 1e-6f));
+                    Phi = Phi * (1.0f - pc) + p.phi * pc;
+                }
+            };
             uint32_t m = gmask;
             while (m) {
-                const int j = __ffs(m) - 1;
+                const int j0 = __ffs(m) - 1;
                 m &= m - 1;
-                const float phi = __shfl_sync(0xffffffffu, phi_l, j);
-                my_pair[j * PH_STRIDE + lane] = make_float2(acc, Phi);
-                const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                if (j < local_n &&
-                    rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
-                    const float4 r0 = rec[3 * j + 0];
-                    const float dx = fpx - r0.x, dy = fpy - r0.y;
-                    const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                    PhaseStep st;
-                    phase_step(frb_ex2(power), r1.y, phi, A, acc, Phi, st);
-                    acc = st.accn; Phi = st.Phin;
+                if (m) {
+                    const int j1 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const FwdPre p0 = fwd_pre(j0), p1 = fwd_pre(j1);
+                    fwd_step(j0, p0);
+                    fwd_step(j1, p1);
+                } else {
+                    const FwdPre p0 = fwd_pre(j0);
+                    fwd_step(j0, p0);
                 }
             }
             // ---- phase 1b: walk back ----
-            m = gmask;
-            while (m) {
-                const int j = 31 - __clz(m);
-                m ^= 1u << j;
+            // State-independent part of entry j (replayed from the remembered state before it), reduced to the
+            // coefficients the adjoint chain needs:
+            //   pcb = Pb K1;  Tb_tot = Tb + pcb q;  cb = pcb iden + w - Tb_tot;  Tb' = Tb_tot + cb alpha;
+            //   a1b = gate ? cb T0 : 0;  t = a1b E;  dL/dphi = Pb pc + t;  Pb' = Pb (1 - pc) - t;  dL/da0 = a1b m
+            struct BwdPre { float K1, pc, iden, q, w, alpha, T0, mm, E, c, g; bool active, gate; };
+            auto bwd_pre = [&](int j) {
+                BwdPre p;
                 const float phi = __shfl_sync(0xffffffffu, phi_l, j);
                 const float2 before = my_pair[j * PH_STRIDE + lane];
                 const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                p.active = (j < local_n) &&
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                const float4 r0 = rec[3 * j + 0];
+                const float Phi0 = before.y;
+                const float dx = fpx - r0.x, dy = fpy - r0.y;
+                const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                p.g = frb_ex2(power);
+                PhaseStep st;
+                phase_step(p.g, r1.y, phi, A, before.x, Phi0, st);           // replay from the remembered state
+                const float sn = __sinf(st.d * TWO_PI_REF);
+                p.T0 = 1.0f - before.x;
+                p.iden = frb_rcp(st.den);
+                p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                p.K1 = phi - Phi0;
+                p.pc = st.pc;
+                p.q = (st.accn >= 1e-6f) ? st.c * p.iden * p.iden : 0.0f;
+                p.alpha = st.alpha;
+                p.gate = (st.alpha == st.a1);                                  // clamp gate (inclusive)
+                p.mm = st.m;
+                // d0b * sg with db = -mb A 2pi sn, mb = a1b a0: everything but a1b
+                const float s1 = (st.d0 < 1.0f - st.d0) ? 1.0f : ((st.d0 > 1.0f - st.d0) ? -1.0f : 0.0f);
+                const float sg = (phi > Phi0) ? 1.0f : ((phi < Phi0) ? -1.0f : 0.0f);
+                p.E = -st.a0 * A * TWO_PI_REF * sn * s1 * sg;
+                p.c = st.c;
+                return p;
+            };
+            auto bwd_step = [&](int j, const BwdPre& p) {
                 float2 out = make_float2(0.f, 0.f);
                 float phib = 0.0f;
-                if (j < local_n &&
-                    rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
-                    const float4 r0 = rec[3 * j + 0];
-                    const float Phi0 = before.y;
-                    const float dx = fpx - r0.x, dy = fpy - r0.y;
-                    const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
-                    const float g = frb_ex2(power);
-                    PhaseStep st;
-                    phase_step(g, r1.y, phi, A, before.x, Phi0, st);   // replay from the remembered state
-                    const float sn = __sinf(st.d * TWO_PI_REF);
-                    const float T0 = 1.0f - before.x;
-                    const float iden = frb_rcp(st.den);
-                    // reverse mode
-                    const float w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
-                    const float pcb = Pb * (phi - Phi0);
-                    phib = Pb * st.pc;
-                    float Pb0 = Pb * (1.0f - st.pc);
-                    float cb_ = pcb * iden + w;
-                    const float Tb_tot = Tb + ((st.accn >= 1e-6f) ? pcb * st.c * iden * iden : 0.0f);
-                    cb_ -= Tb_tot;
-                    const float Tb0 = Tb_tot + cb_ * st.alpha;
-                    const float alphab = cb_ * T0;
-                    const float a1b = (st.alpha == st.a1) ? alphab : 0.0f;      // clamp gate (inclusive)
-                    const float a0b = a1b * st.m;
-                    const float mb = a1b * st.a0;
-                    const float db = -mb * A * TWO_PI_REF * sn;
-                    const float d0b = (st.d0 < 1.0f - st.d0) ? db : ((st.d0 > 1.0f - st.d0) ? -db : 0.0f);
-                    const float sg = (phi > Phi0) ? 1.0f : ((phi < Phi0) ? -1.0f : 0.0f);
-                    phib += d0b * sg;
-                    Pb0 -= d0b * sg;
-                    out.x = st.c;
-                    out.y = g * a0b;                                            // dL/dopacity part
-                    Tb = Tb0; Pb = Pb0;
+                if (p.active) {
+                    const float pcb = Pb * p.K1;
+                    const float Tb_tot = fmaf(pcb, p.q, Tb);
+                    const float cb_ = fmaf(pcb, p.iden, p.w) - Tb_tot;
+                    const float a1b = p.gate ? cb_ * p.T0 : 0.0f;
+                    const float t = a1b * p.E;
+                    phib = fmaf(Pb, p.pc, t);
+                    Pb = fmaf(Pb, 1.0f - p.pc, -t);
+                    Tb = fmaf(cb_, p.alpha, Tb_tot);
+                    out.x = p.c;
+                    out.y = p.g * (a1b * p.mm);                                 // dL/dopacity part
                 }
                 my_pair[j * PH_STRIDE + lane] = out;
                 my_phib[j * PH_STRIDE + lane] = phib;
+            };
+            m = gmask;
+            while (m) {
+                const int j0 = 31 - __clz(m);
+                m ^= 1u << j0;
+                if (m) {
+                    const int j1 = 31 - __clz(m);
+                    m ^= 1u << j1;
+                    const BwdPre p0 = bwd_pre(j0), p1 = bwd_pre(j1);
+                    bwd_step(j0, p0);
+                    bwd_step(j1, p1);
+                } else {
+                    const BwdPre p0 = bwd_pre(j0);
+                    bwd_step(j0, p0);
+                }
             }
             __syncwarp();
             // ---- phase 2: lane = Gaussian ----

@@ -110,7 +110,7 @@ extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_
     L->touched = s.take(4 * (size_t)n);
     L->order = s.take(4 * (size_t)n);
     L->rank = s.take(4 * (size_t)n);
-    L->offsets = s.take(4 * ((size_t)n + 1));
+    L->offsets = s.take(4 * ((size_t)n + 2));      // [n]: instance count, [n + 1]: status (frb_tile_scan)
     L->depth_ws = s.take(frb_depth_order_workspace_bytes(n));
     L->scan_ws = s.take(frb_scan_workspace_bytes(n));
     if (frb_use_tile_lists(n, (int)tiles)) {
@@ -164,11 +164,17 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
         // (counting and scanning need no depth order; running them on a forked stream beside the depth sort was
         // measured and dropped: 2564-2577 frames/s against 2586-2588 in stream order - inside the replayed graph the
         // cross-stream edges cost the programmatic-launch overlap they replace, profiles/r2_e_overlap_ab.txt)
-        FRB_STAGE("frb_tile_count", stream, frb_tile_count(n, n_views, width, height, records, S + L.tile_ws, stream));
-        FRB_STAGE("frb_tile_scan", stream,
-                  frb_tile_scan(n, tiles, m_capacity, ranges, tile_order, offsets + n, S + L.tile_ws, stream));
+        // depth order over the camera's [near, far] only (fewer radix passes for narrow slabs): widest range over the views
+        float near_d = camera_host[18], far_d = camera_host[19];
+        for (int v = 1; v < n_views; ++v) {
+            near_d = fminf(near_d, camera_host[v * FRB_CAMERA_FLOATS + 18]);
+            far_d = fmaxf(far_d, camera_host[v * FRB_CAMERA_FLOATS + 19]);
+        }
         FRB_STAGE("frb_depth_order", stream,
-                  frb_depth_order_rank(n, depth_bits, order, rank, S + L.depth_ws, stream));
+                  frb_depth_order_range(n, depth_bits, near_d, far_d, order, rank, S + L.depth_ws, stream));
+        FRB_STAGE("frb_tile_count_scan", stream,
+                  frb_tile_count_scan(n, n_views, width, height, records, m_capacity, ranges, tile_order, offsets + n,
+                                      frb_depth_order_error_word(n, S + L.depth_ws), S + L.tile_ws, stream));
         FRB_STAGE("frb_tile_emit", stream,
                   frb_tile_emit(n, n_views, width, height, records, rank, m_capacity, S + L.tile_ws, inst_rank,
                                 stream));

@@ -18,10 +18,14 @@
 // work with coalesced loads and shared-memory digit counters.
 #include "frb_common.cuh"
 
+#include <string.h>
+
 namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int RADIX_BITS_MAX = 9;                          // frb_depth_order_range: 27 key bits in three 9-bit passes
+constexpr int RADIX_MAX = 1 << RADIX_BITS_MAX;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT = 8;                                // items per thread
@@ -48,33 +52,54 @@ struct PassPlan {
     uint32_t mask[MAX_PASSES];
 };
 
-// Sort workspace layout (uint32 words): [hist: MAX_PASSES*256][tickets: MAX_PASSES][error: 1]
-// [pad to 16 words][status: n_passes * n_blocks * 256]
+// Key transform of the first pass (and of the histogram kernel) for frb_depth_order_range: depth bits clamped to
+// [lo, hi] (the bit patterns of the near and far planes; positive floats order like their bits) minus lo.  Visible
+// Gaussians (near < depth < far, DR:541) keep their exact relative order in hi - lo + 1 values; culled ones (behind
+// the camera: sign bit set, i.e. negative as int32; beyond far; NaN) collapse to the ends, where their mutual order
+// does not matter - they never reach a tile.  on = 0: identity.
+struct KeyRange {
+    uint32_t lo, hi;
+    int on;
+};
+template <typename KeyT>
+__device__ __forceinline__ KeyT key_xform(KeyT k, const KeyRange& kr) { return k; }
+template <>
+__device__ __forceinline__ uint32_t key_xform<uint32_t>(uint32_t k, const KeyRange& kr) {
+    if (!kr.on) return k;
+    if ((int32_t)k <= (int32_t)kr.lo) return 0u;
+    return (k >= kr.hi ? kr.hi : k) - kr.lo;
+}
+
+// Sort workspace layout (uint32 words): [hist: MAX_PASSES*RADIX_MAX][tickets: MAX_PASSES][error: 1]
+// [pad to 16 words][status: n_passes * n_blocks * radix]
 constexpr int WS_HIST = 0;
-constexpr int WS_TICKET = MAX_PASSES * RADIX;
+constexpr int WS_TICKET = MAX_PASSES * RADIX_MAX;
 constexpr int WS_ERROR = WS_TICKET + MAX_PASSES;
 constexpr int WS_STATUS = WS_ERROR + 8;
 
-// Global digit histograms of all passes in one read of the keys.
-template <typename KeyT>
+// Global digit histograms of all passes in one read of the keys.  RDX: digits per pass (256 or 512).
+template <typename KeyT, int RDX>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_all_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys,
-                      const __grid_constant__ PassPlan plan, uint32_t* __restrict__ hist) {
+                      const __grid_constant__ PassPlan plan, const __grid_constant__ KeyRange kr,
+                      uint32_t* __restrict__ hist) {
     frb_pdl_prologue();
-    __shared__ uint32_t cnt[MAX_PASSES][RADIX];
+    __shared__ uint32_t cnt[MAX_PASSES / (RDX / RADIX)][RDX];      // 8 passes of 256 digits or 4 of 512: 8 KB
     if (m_dev) m = min(m, (int)*m_dev);
-    for (int p = 0; p < plan.n_passes; ++p) cnt[p][threadIdx.x] = 0;
+    for (int p = 0; p < plan.n_passes; ++p)
+        for (int d = threadIdx.x; d < RDX; d += SORT_THREADS) cnt[p][d] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * SORT_THREADS + threadIdx.x; i < m;
          i += (long long)gridDim.x * SORT_THREADS) {
-        KeyT k = keys[i];
+        KeyT k = key_xform<KeyT>(keys[i], kr);
         for (int p = 0; p < plan.n_passes; ++p) atomicAdd(&cnt[p][digit_of(k, plan.shift[p], plan.mask[p])], 1u);
     }
     __syncthreads();
-    for (int p = 0; p < plan.n_passes; ++p) {
-        uint32_t c = cnt[p][threadIdx.x];
-        if (c) atomicAdd(&hist[p * RADIX + threadIdx.x], c);
-    }
+    for (int p = 0; p < plan.n_passes; ++p)
+        for (int d = threadIdx.x; d < RDX; d += SORT_THREADS) {
+            uint32_t c = cnt[p][d];
+            if (c) atomicAdd(&hist[p * RDX + d], c);
+        }
 }
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
@@ -87,19 +112,22 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 }
 
 // One pass: rank (stable), look back, scatter.  Warp w of a block owns the contiguous items
-// [w*256, (w+1)*256) of the block's tile, visited in 8 rounds of 32 consecutive items, so
+// [w*32*IPT, (w+1)*32*IPT) of the block's tile, visited in IPT rounds of 32 consecutive items, so
 // (tile, warp, round, lane) order is input order.  GEN_VALS: values are the input indices.
-template <typename KeyT, bool GEN_VALS, int IPT>
+// RDX digits per pass (256 or 512); thread t owns the digits [t * DPT, (t + 1) * DPT), DPT = RDX / 256.
+// XFORM: the keys read are raw depth bits and are transformed by key_xform (first pass of frb_depth_order_range).
+template <typename KeyT, bool GEN_VALS, int IPT, int RDX, bool XFORM>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                       const uint32_t* __restrict__ vals_in,
                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, uint32_t mask,
                       const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag,
-                      uint32_t* __restrict__ rank_out) {
+                      uint32_t* __restrict__ rank_out, const __grid_constant__ KeyRange kr) {
     frb_pdl_prologue();
-    __shared__ uint32_t cnt[SORT_WARPS][RADIX];
-    __shared__ uint32_t digit_base[RADIX];
+    constexpr int DPT = RDX / SORT_THREADS;
+    __shared__ uint32_t cnt[SORT_WARPS][RDX];
+    __shared__ uint32_t digit_base[RDX];
     __shared__ uint32_t scan_ws[SORT_WARPS];
     __shared__ uint32_t tile_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,7 +137,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     while (true) {
     __syncthreads();                                        // shared arrays of the previous tile are free
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-    for (int d = lane; d < RADIX; d += 32) cnt[warp][d] = 0;
+    for (int d = lane; d < RDX; d += 32) cnt[warp][d] = 0;
     __syncthreads();
     const uint32_t tile = tile_s;
     if ((long long)tile * (SORT_THREADS * IPT) >= m) return;           // past the end: nobody looks back at this tile
@@ -122,13 +150,14 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         key[r] = (i < m) ? keys_in[i] : (KeyT)0;
+        if (XFORM) key[r] = key_xform<KeyT>(key[r], kr);
     }
-    // the eight match.any operations are independent: issue them back to back, then update the counters
+    // the match.any operations are independent: issue them back to back, then update the counters
     uint32_t peers[IPT];
 #pragma unroll
     for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
-        uint32_t d = (i < m) ? digit_of(key[r], shift, mask) : RADIX;   // invalid lanes match each other only
+        uint32_t d = (i < m) ? digit_of(key[r], shift, mask) : RDX;     // invalid lanes match each other only
         peers[r] = __match_any_sync(0xffffffffu, d);
     }
 #pragma unroll
@@ -148,50 +177,77 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     }
     __syncthreads();
 
-    // thread d owns digit d: per-warp counts -> warp-exclusive offsets; tile count -> look-back
-    const int d = threadIdx.x;
-    uint32_t run = 0;
+    // thread t owns DPT consecutive digits: per-warp counts -> warp-exclusive offsets; tile count -> look-back
+    uint32_t excl[DPT], run[DPT], h[DPT];
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) {
-        uint32_t c = cnt[w][d];
-        cnt[w][d] = run;
-        run += c;
+    for (int q = 0; q < DPT; ++q) {
+        const int d = threadIdx.x * DPT + q;
+        uint32_t r_ = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = cnt[w][d];
+            cnt[w][d] = r_;
+            r_ += c;
+        }
+        run[q] = r_;
+        excl[q] = 0;
+        h[q] = hist_pass[d];
     }
-    uint32_t* my_status = status + (size_t)tile * RADIX + d;
-    uint32_t excl = 0;
     if (tile == 0) {
-        st_volatile_u32(my_status, run | FLAG_PREFIX);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) st_volatile_u32(status + threadIdx.x * DPT + q, run[q] | FLAG_PREFIX);
     } else {
-        st_volatile_u32(my_status, run | FLAG_AGG);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q)
+            st_volatile_u32(status + (size_t)tile * RDX + threadIdx.x * DPT + q, run[q] | FLAG_AGG);
         // Look back LOOK_WINDOW predecessors per round trip: the loads are independent, so a walk over k
-        // published counts costs k / LOOK_WINDOW L2 latencies instead of k.
-        long long look = (long long)tile - 1;
+        // published counts costs k / LOOK_WINDOW L2 latencies instead of k.  The DPT digits of a thread walk
+        // together (all their loads of a round are issued before the first is used).
+        long long look[DPT];
+        bool done[DPT];
         int spins = 0;
-        bool done = false;
-        while (!done) {
-            uint32_t v[LOOK_WINDOW];
 #pragma unroll
-            for (int k = 0; k < LOOK_WINDOW; ++k)
-                v[k] = (look - k >= 0) ? ld_volatile_u32(status + (size_t)(look - k) * RADIX + d) : FLAG_PREFIX;
+        for (int q = 0; q < DPT; ++q) { look[q] = (long long)tile - 1; done[q] = false; }
+        bool all_done = false;
+        while (!all_done) {
+            uint32_t v[DPT][LOOK_WINDOW];
 #pragma unroll
-            for (int k = 0; k < LOOK_WINDOW; ++k) {
-                if (done) break;
-                const uint32_t f = v[k] & FLAG_MASK;
-                if (f == 0) {                      // not published yet: poll again from this tile
-                    look -= k;
-                    if (++spins > SPIN_LIMIT) { *error_flag = 1; done = true; }
-                    break;
+            for (int q = 0; q < DPT; ++q) {
+                const int d = threadIdx.x * DPT + q;
+#pragma unroll
+                for (int k = 0; k < LOOK_WINDOW; ++k)
+                    v[q][k] = (!done[q] && look[q] - k >= 0)
+                                  ? ld_volatile_u32(status + (size_t)(look[q] - k) * RDX + d) : FLAG_PREFIX;
+            }
+            all_done = true;
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) {
+                if (done[q]) continue;
+#pragma unroll
+                for (int k = 0; k < LOOK_WINDOW; ++k) {
+                    if (done[q]) break;
+                    const uint32_t f = v[q][k] & FLAG_MASK;
+                    if (f == 0) {                      // not published yet: poll again from this tile
+                        look[q] -= k;
+                        if (++spins > SPIN_LIMIT) { *error_flag = 1; done[q] = true; }
+                        break;
+                    }
+                    excl[q] += v[q][k] & VALUE_MASK;
+                    if (f == FLAG_PREFIX) done[q] = true;
+                    else if (k == LOOK_WINDOW - 1) look[q] -= LOOK_WINDOW;
                 }
-                excl += v[k] & VALUE_MASK;
-                if (f == FLAG_PREFIX) done = true;
-                else if (k == LOOK_WINDOW - 1) look -= LOOK_WINDOW;
+                all_done = all_done && done[q];
             }
         }
-        st_volatile_u32(my_status, (excl + run) | FLAG_PREFIX);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q)
+            st_volatile_u32(status + (size_t)tile * RDX + threadIdx.x * DPT + q, (excl[q] + run[q]) | FLAG_PREFIX);
     }
-    // exclusive scan of the global digit histogram (256 values, one per thread)
-    uint32_t h = hist_pass[d];
-    uint32_t incl = h;
+    // exclusive scan of the global digit histogram (RDX values, DPT consecutive ones per thread)
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) tsum += h[q];
+    uint32_t incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -203,7 +259,12 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w)
         if (w < warp) woff += scan_ws[w];
-    digit_base[d] = woff + incl - h + excl;
+    uint32_t before = woff + incl - tsum;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        digit_base[threadIdx.x * DPT + q] = before + excl[q];
+        before += h[q];
+    }
     __syncthreads();
 
 #pragma unroll
@@ -229,22 +290,25 @@ constexpr int SORT_SMALL_MAX = 1 << 19;                    // below this many ke
 
 inline int sort_tile_of(int m) { return m <= SORT_SMALL_MAX ? SORT_TILE_SMALL : SORT_TILE; }
 
-size_t sort_ws_words(int m, int n_passes) {
-    return (size_t)WS_STATUS + (size_t)n_passes * (size_t)frb_div_up(m, sort_tile_of(m)) * RADIX;
+size_t sort_ws_words(int m, int n_passes, int radix = RADIX) {
+    return (size_t)WS_STATUS + (size_t)n_passes * (size_t)frb_div_up(m, sort_tile_of(m)) * radix;
 }
 
 // Sorts on bits [begin_bit, end_bit).  Pass p reads buffer (p even ? A : B) and writes the other;
 // when first_in is given, pass 0 reads keys from there (and generates values if vals_first is null).
 // Returns in *result_in_b whether the sorted data ended in the B buffers.
-template <typename KeyT>
+// RB: digit width (8, or 9 for frb_depth_order_range); kr: key transform applied to first_keys (kr.on).
+template <typename KeyT, int RB>
 int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
                     KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
-                    bool* result_in_b, bool hist_ready = false, uint32_t* rank_out = nullptr) {
+                    bool* result_in_b, bool hist_ready = false, uint32_t* rank_out = nullptr,
+                    KeyRange kr = KeyRange{0u, 0u, 0}) {
+    constexpr int RDX = 1 << RB;
     PassPlan plan;
     plan.n_passes = 0;
-    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
-        if (plan.n_passes == MAX_PASSES) return FRB_E_INVALID;
-        int nb = min(RADIX_BITS, end_bit - bit);
+    for (int bit = begin_bit; bit < end_bit; bit += RB) {
+        if (plan.n_passes == MAX_PASSES / (RDX / RADIX)) return FRB_E_INVALID;
+        int nb = min(RB, end_bit - bit);
         plan.shift[plan.n_passes] = bit;
         plan.mask[plan.n_passes] = (1u << nb) - 1u;
         ++plan.n_passes;
@@ -252,9 +316,9 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
     const bool small = sort_tile_of(m) == SORT_TILE_SMALL;
     const int n_blocks = frb_div_up(m, sort_tile_of(m));
     if (!hist_ready) {      // otherwise the caller zeroed ws and the producer of the keys filled the histograms
-        FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes), st));
-        frb_launch(radix_hist_all_kernel<KeyT>, dim3(min(n_blocks, 592)), dim3(SORT_THREADS), 0, st, m, m_dev,
-                   first_keys, plan, ws + WS_HIST);
+        FRB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(uint32_t) * sort_ws_words(m, plan.n_passes, RDX), st));
+        frb_launch(radix_hist_all_kernel<KeyT, RDX>, dim3(min(n_blocks, 592)), dim3(SORT_THREADS), 0, st, m, m_dev,
+                   first_keys, plan, kr, ws + WS_HIST);
         frb_note_launches(1);
     }
     const KeyT* kin = first_keys;
@@ -263,16 +327,18 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
     for (int p = 0; p < plan.n_passes; ++p) {
         KeyT* kout = to_b ? keys_b : keys_a;
         uint32_t* vout = to_b ? vals_b : vals_a;
-        uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RADIX;
+        uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RDX;
         const int grid = min(n_blocks, SORT_GRID_MAX);
-#define FRB_ONESWEEP(GEN, IPT_)                                                                                     \
-    frb_launch(radix_onesweep_kernel<KeyT, GEN, IPT_>, dim3(grid), dim3(SORT_THREADS), 0, st,                                           \
-        m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RADIX, status,              \
-        ws + WS_TICKET + p, ws + WS_ERROR, (p == plan.n_passes - 1) ? rank_out : (uint32_t*)nullptr)
+        const bool xf = kr.on && p == 0;
+#define FRB_ONESWEEP(GEN, IPT_, XF)                                                                                 \
+    frb_launch(radix_onesweep_kernel<KeyT, GEN, IPT_, RDX, XF>, dim3(grid), dim3(SORT_THREADS), 0, st,              \
+        m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RDX, status,                \
+        ws + WS_TICKET + p, ws + WS_ERROR, (p == plan.n_passes - 1) ? rank_out : (uint32_t*)nullptr, kr)
         if (vin == nullptr) {
-            if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL); else FRB_ONESWEEP(true, SORT_IPT);
+            if (xf) { if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL, true); else FRB_ONESWEEP(true, SORT_IPT, true); }
+            else { if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL, false); else FRB_ONESWEEP(true, SORT_IPT, false); }
         } else {
-            if (small) FRB_ONESWEEP(false, SORT_IPT_SMALL); else FRB_ONESWEEP(false, SORT_IPT);
+            if (small) FRB_ONESWEEP(false, SORT_IPT_SMALL, false); else FRB_ONESWEEP(false, SORT_IPT, false);
         }
 #undef FRB_ONESWEEP
         frb_note_launches(1);
@@ -563,7 +629,7 @@ static int sort_pairs(int m, const uint32_t* m_dev, uint64_t* keys, uint32_t* va
     if (!keys || !vals || !keys_tmp || !vals_tmp || !workspace) return FRB_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     bool in_b = false;
-    int rc = radix_sort_impl<uint64_t>(m, m_dev, keys, vals, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit,
+    int rc = radix_sort_impl<uint64_t, RADIX_BITS>(m, m_dev, keys, vals, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit,
                                        (uint32_t*)workspace, st, &in_b);
     if (rc) return rc;
     if (in_b) {
@@ -588,7 +654,7 @@ extern "C" int frb_radix_sort_pairs_dev(int m_capacity, const uint32_t* m_dev, u
 
 extern "C" size_t frb_depth_order_workspace_bytes(int n) {
     if (n < 0) n = 0;
-    return 3 * align256(sizeof(uint32_t) * (size_t)n) + align256(sizeof(uint32_t) * sort_ws_words(n, 4));
+    return 3 * align256(sizeof(uint32_t) * (size_t)n) + align256(sizeof(uint32_t) * sort_ws_words(n, 4, RADIX_MAX));
 }
 
 extern "C" int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* workspace,
@@ -610,11 +676,61 @@ extern "C" int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t*
     uint32_t* ws = (uint32_t*)(w + 3 * a);
     // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
     bool in_b = false;
-    int rc = radix_sort_impl<uint32_t>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b,
+    int rc = radix_sort_impl<uint32_t, RADIX_BITS>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b,
                                        false, rank);
     if (rc) return rc;
     if (!in_b) return FRB_E_INVALID;   // cannot happen with an even number of passes
     return 0;
+}
+
+// The depth order of what a camera can see: keys = depth bits clamped to [near_bits, far_bits] minus near_bits
+// (key_xform), sorted on the bits that range needs (27 for the default [0.01, 100]: four 8-bit passes as before; three
+// when far < 2 near, one or two for thin slabs); ranges of 2^27 values and more fall back to the full 32-bit sort.
+// The order of the VISIBLE Gaussians (near < depth < far) is exactly frb_depth_order's; culled ones end up at the two
+// ends in index order.
+extern "C" int frb_depth_order_range(int n, const uint32_t* depth_bits, float near_depth, float far_depth,
+                                     uint32_t* order, uint32_t* rank, void* workspace, void* stream) {
+    if (n < 0) return FRB_E_INVALID;
+    if (n == 0) return 0;
+    if (!depth_bits || !order || !workspace) return FRB_E_INVALID;
+    uint32_t lo, hi;
+    memcpy(&lo, &near_depth, 4);
+    memcpy(&hi, &far_depth, 4);
+    const bool usable = near_depth > 0.0f && far_depth > near_depth && far_depth < 3.0e38f &&
+                        (hi - lo) < (1u << (3 * RADIX_BITS_MAX));
+    if (!usable) return frb_depth_order_rank(n, depth_bits, order, rank, workspace, stream);
+    int nbits = 1;
+    while ((1u << nbits) <= (hi - lo)) ++nbits;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    size_t a = align256(sizeof(uint32_t) * (size_t)n);
+    uint32_t* keys_a = (uint32_t*)w;
+    uint32_t* keys_b = (uint32_t*)(w + a);
+    uint32_t* vals_a = (uint32_t*)(w + 2 * a);
+    uint32_t* ws = (uint32_t*)(w + 3 * a);
+    KeyRange kr{lo, hi, 1};
+    bool in_b = false;
+    int rc;
+    uint32_t *va = vals_a, *vb = order;
+    // Digit width: 8 bits.  Three 9-bit passes for the default [0.01, 100] (27 key bits) were measured against four
+    // 8-bit ones: 45-48 us against 41 us at 100k keys - a 512-digit pass costs more (twice the counters to clear and
+    // scan per warp, two look-back words per thread) than the pass it saves; the 9-bit instantiation is kept out of
+    // the build.  The range still pays whenever it fits 24 bits (near / far within a factor of two: three passes).
+    const int passes8 = (nbits + 7) / 8;
+    if (passes8 % 2 == 1) { va = order; vb = vals_a; }
+    rc = radix_sort_impl<uint32_t, RADIX_BITS>(n, nullptr, depth_bits, nullptr, keys_a, va, keys_b, vb, 0, nbits, ws, st,
+                                               &in_b, false, rank, kr);
+    if (rc) return rc;
+    if (in_b != (passes8 % 2 == 0)) return FRB_E_INVALID;
+    return 0;
+}
+
+// Device address of the word the radix passes of frb_depth_order* set when a look-back gave up (SPIN_LIMIT): a
+// consumer that synchronises anyway (frb_tile_scan's instance count) carries it to the host.
+extern "C" const uint32_t* frb_depth_order_error_word(int n, const void* workspace) {
+    if (n <= 0 || !workspace) return nullptr;
+    const size_t a = align256(sizeof(uint32_t) * (size_t)n);
+    return (const uint32_t*)((const char*)workspace + 3 * a) + WS_ERROR;
 }
 
 extern "C" size_t frb_scan_workspace_bytes(int n) {
@@ -683,7 +799,7 @@ extern "C" int frb_bin_sort_dev(int n, int n_views, int width, int height, const
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     bool in_b = false;
-    int rc = radix_sort_impl<uint64_t>(m_capacity, m_out, keys, gids, keys, gids, keys_tmp, vals_tmp, 32, 32 + tile_bits,
+    int rc = radix_sort_impl<uint64_t, RADIX_BITS>(m_capacity, m_out, keys, gids, keys, gids, keys_tmp, vals_tmp, 32, 32 + tile_bits,
                                        (uint32_t*)sort_ws, st, &in_b, /*hist_ready=*/true);
     if (rc) return rc;
     if (in_b) {

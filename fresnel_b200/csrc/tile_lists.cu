@@ -108,20 +108,24 @@ tile_column_prefix_kernel(int n_chunks, int n_tiles, uint32_t* __restrict__ chun
     }
 }
 
-// One CTA: exclusive scan of the tile counts (ranges, cursors, total) and the launch order of the tiles
-// (descending list length in buckets of 8 entries: the long centre tiles start first, the short ones fill the tail).
-// Entries past m_capacity do not exist: ranges are clamped to it and flags[0] is set.
-__global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(int n_tiles, const uint32_t* __restrict__ tile_count, uint32_t m_capacity, int2* __restrict__ ranges,
-                 int* __restrict__ tile_order, uint32_t* __restrict__ tile_start, uint32_t* __restrict__ m_out,
-                 uint32_t* __restrict__ flags) {
-    frb_pdl_prologue();
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry_s;
-    __shared__ int hist[SCHED_BUCKETS];
+// One CTA (1024 threads): exclusive scan of the tile counts (ranges, cursors, total) and the launch order of the
+// tiles (descending list length in buckets of 8 entries: the long centre tiles start first, the short ones fill the
+// tail).  Entries past m_capacity do not exist: ranges are clamped to it and the status says so.
+// tile_count may live in shared or global memory.
+struct ScanSmem {
+    uint32_t warp_tot[32];
+    uint32_t carry;
+    int hist[SCHED_BUCKETS];
+};
+
+__device__ __forceinline__ void tile_scan_body(ScanSmem& sc, int n_tiles, const uint32_t* tile_count,
+                                               uint32_t m_capacity, int2* __restrict__ ranges,
+                                               int* __restrict__ tile_order, uint32_t* __restrict__ tile_start,
+                                               uint32_t* __restrict__ m_out, uint32_t* __restrict__ flags,
+                                               const uint32_t* __restrict__ upstream_error) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sc.carry = 0;
+    sc.hist[threadIdx.x] = 0;
     __syncthreads();
     auto bucket = [](uint32_t c) { return SCHED_BUCKETS - 1 - (int)min(c >> 3, (uint32_t)(SCHED_BUCKETS - 1)); };
     for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
@@ -133,61 +137,157 @@ tile_scan_kernel(int n_tiles, const uint32_t* __restrict__ tile_count, uint32_t 
             uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += x;
         }
-        if (lane == 31) warp_tot[warp] = incl;
+        if (lane == 31) sc.warp_tot[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            uint32_t w = warp_tot[lane], wi = w;
+            uint32_t w = sc.warp_tot[lane], wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t x = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += x;
             }
-            warp_tot[lane] = wi - w;
+            sc.warp_tot[lane] = wi - w;
         }
         __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t start = carry + warp_tot[warp] + incl - c;
+        const uint32_t carry = sc.carry;
+        const uint32_t start = carry + sc.warp_tot[warp] + incl - c;
         if (t < n_tiles) {
             const uint32_t s = min(start, m_capacity), e = min(start + c, m_capacity);
             ranges[t] = make_int2((int)s, (int)e);
             tile_start[t] = start;               // unclamped: frb_tile_emit drops slots past the capacity
-            atomicAdd(&hist[bucket(e - s)], 1);
+            atomicAdd(&sc.hist[bucket(e - s)], 1);
         }
         __syncthreads();
-        if (threadIdx.x == SCAN_THREADS - 1) carry_s = start + c;
+        if (threadIdx.x == SCAN_THREADS - 1) sc.carry = start + c;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        *m_out = carry_s;
-        flags[0] = carry_s > m_capacity ? 1u : 0u;
+        m_out[0] = sc.carry;
+        // m_out[1]: status the host reads with the count - 1 = lists truncated to the capacity, 2 = the depth sort's
+        // look-back gave up (its order is not trustworthy)
+        const uint32_t st = (sc.carry > m_capacity ? 1u : 0u) | ((upstream_error && *upstream_error) ? 2u : 0u);
+        m_out[1] = st;
+        flags[0] = st;
     }
     // exclusive scan of the 1024 schedule buckets (bucket 0 = longest lists), then place the tiles
     {
-        int v = hist[threadIdx.x], incl = v;
+        int v = sc.hist[threadIdx.x], incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int x = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += x;
         }
-        if (lane == 31) warp_tot[warp] = (uint32_t)incl;
+        if (lane == 31) sc.warp_tot[warp] = (uint32_t)incl;
         __syncthreads();
         if (warp == 0) {
-            uint32_t w = warp_tot[lane], wi = w;
+            uint32_t w = sc.warp_tot[lane], wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t x = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += x;
             }
-            warp_tot[lane] = wi - w;
+            sc.warp_tot[lane] = wi - w;
         }
         __syncthreads();
-        hist[threadIdx.x] = (int)warp_tot[warp] + incl - v;
+        sc.hist[threadIdx.x] = (int)sc.warp_tot[warp] + incl - v;
         __syncthreads();
     }
     for (int t = threadIdx.x; t < n_tiles; t += SCAN_THREADS) {
-        const int2 r = ranges[t];
-        tile_order[atomicAdd(&hist[bucket((uint32_t)(r.y - r.x))], 1)] = t;
+        const uint32_t c = tile_count[t];
+        // same length as ranges[t] (read from the counts: the ranges written above by other threads need no fence)
+        const uint32_t s = min(tile_start[t], m_capacity), e = min(tile_start[t] + c, m_capacity);
+        tile_order[atomicAdd(&sc.hist[bucket(e - s)], 1)] = t;
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int n_tiles, const uint32_t* __restrict__ tile_count, uint32_t m_capacity, int2* __restrict__ ranges,
+                 int* __restrict__ tile_order, uint32_t* __restrict__ tile_start, uint32_t* __restrict__ m_out,
+                 uint32_t* __restrict__ flags, const uint32_t* __restrict__ upstream_error) {
+    frb_pdl_prologue();
+    __shared__ ScanSmem sc;
+    tile_scan_body(sc, n_tiles, tile_count, m_capacity, ranges, tile_order, tile_start, m_out, flags, upstream_error);
+}
+
+// Count, column prefix and tile scan in ONE kernel.  CTA with ticket c histograms the tiles of its chunk in shared
+// memory, publishes the row (status[c][t] = count | AGG), obtains "instances of tile t in chunks before c" by decoupled
+// look-back over the predecessors' rows (thread = tile, LOOK_WINDOW rows per round trip), publishes the inclusive
+// value (| PREFIX) and keeps the exclusive one in base[c][t] for frb_tile_emit.  The CTA with the LAST ticket ends
+// up with the column totals of every tile in its shared memory and runs the tile scan on them.  status must be zero.
+constexpr uint32_t TFLAG_AGG = 1u << 30, TFLAG_PREFIX = 2u << 30, TFLAG_MASK = 3u << 30;
+constexpr int T_LOOK_WINDOW = 8;
+constexpr int T_SPIN_LIMIT = 1 << 24;
+
+__device__ __forceinline__ uint32_t t_ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void t_st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_count_scan_kernel(int n, int chunk, int n_chunks, int n_tiles, int n_per_view, int tiles_x, int tiles_per_view,
+                       const float4* __restrict__ records, uint32_t* __restrict__ status,
+                       uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ ticket, uint32_t m_capacity,
+                       int2* __restrict__ ranges, int* __restrict__ tile_order, uint32_t* __restrict__ tile_start,
+                       uint32_t* __restrict__ m_out, uint32_t* __restrict__ flags,
+                       const uint32_t* __restrict__ upstream_error) {
+    frb_pdl_prologue();
+    extern __shared__ uint32_t hist_s[];
+    __shared__ ScanSmem sc;
+    __shared__ uint32_t chunk_s;
+    if (threadIdx.x == 0) chunk_s = atomicAdd(ticket, 1u);     // chunks are numbered in start order
+    for (int t = threadIdx.x; t < n_tiles; t += SCAN_THREADS) hist_s[t] = 0;
+    __syncthreads();
+    const int c = (int)chunk_s;
+    const int k0 = c * chunk, k1 = min(n, k0 + chunk);
+    for (int k = k0 + threadIdx.x; k < k1; k += SCAN_THREADS) {
+        int tx0, tx1, ty0, ty1;
+        rect_tiles(records, (uint32_t)k, tx0, tx1, ty0, ty1);
+        const uint32_t view_base = ((uint32_t)k / (uint32_t)n_per_view) * (uint32_t)tiles_per_view;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&hist_s[view_base + (uint32_t)(ty * tiles_x + tx)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += SCAN_THREADS) {
+        const uint32_t v = hist_s[t];
+        uint32_t excl = 0;
+        uint32_t* mine = status + (size_t)c * n_tiles + t;
+        if (c == 0) {
+            t_st_volatile(mine, v | TFLAG_PREFIX);
+        } else {
+            t_st_volatile(mine, v | TFLAG_AGG);
+            int look = c - 1, spins = 0;
+            bool done = false;
+            while (!done) {
+                uint32_t w[T_LOOK_WINDOW];
+#pragma unroll
+                for (int q = 0; q < T_LOOK_WINDOW; ++q)
+                    w[q] = (look - q >= 0) ? t_ld_volatile(status + (size_t)(look - q) * n_tiles + t) : TFLAG_PREFIX;
+#pragma unroll
+                for (int q = 0; q < T_LOOK_WINDOW; ++q) {
+                    if (done) break;
+                    const uint32_t f = w[q] & TFLAG_MASK;
+                    if (f == 0) {                       // not published yet: poll again from this row
+                        look -= q;
+                        if (++spins > T_SPIN_LIMIT) { flags[1] = 1; done = true; }
+                        break;
+                    }
+                    excl += w[q] & ~TFLAG_MASK;
+                    if (f == TFLAG_PREFIX) done = true;
+                    else if (q == T_LOOK_WINDOW - 1) look -= T_LOOK_WINDOW;
+                }
+            }
+            t_st_volatile(mine, (excl + v) | TFLAG_PREFIX);
+        }
+        chunk_base[(size_t)c * n_tiles + t] = excl;
+        hist_s[t] = excl + v;                           // the last chunk: the column totals
+    }
+    if (c != n_chunks - 1) return;
+    __syncthreads();
+    tile_scan_body(sc, n_tiles, hist_s, m_capacity, ranges, tile_order, tile_start, m_out, flags, upstream_error);
 }
 
 // CTA c of frb_tile_count again: the slot of an instance = start of its tile's span + instances of the tile in
@@ -361,9 +461,10 @@ ChunkPlan chunk_plan(int n) {
     p.chunks = frb_div_up(std::max(n, 1), p.chunk);
     return p;
 }
-// workspace words: [chunk_hist: chunks * n_tiles][tile_total: n_tiles][tile_start: n_tiles][flags: 4]
+// workspace words: [chunk_hist / chunk_base: chunks * n_tiles][tile_total: n_tiles][tile_start: n_tiles][flags: 4]
+// [ticket: 4][status: chunks * n_tiles] (flags .. status are zeroed by frb_tile_count_scan)
 struct WsView {
-    uint32_t *hist, *total, *start, *flags;
+    uint32_t *hist, *total, *start, *flags, *ticket, *status;
 };
 WsView ws_view(void* workspace, int n, int n_tiles) {
     const ChunkPlan p = chunk_plan(n);
@@ -372,9 +473,11 @@ WsView ws_view(void* workspace, int n, int n_tiles) {
     v.total = v.hist + (size_t)p.chunks * n_tiles;
     v.start = v.total + n_tiles;
     v.flags = v.start + n_tiles;
+    v.ticket = v.flags + 4;
+    v.status = v.ticket + 4;
     return v;
 }
-unsigned long long g_count_opt_in = 0, g_emit_opt_in = 0;
+unsigned long long g_count_opt_in = 0, g_emit_opt_in = 0, g_count_scan_opt_in = 0;
 }  // namespace
 
 extern "C" int frb_tile_lists_max_tiles(void) { return MAX_SMEM_TILES; }
@@ -382,7 +485,7 @@ extern "C" int frb_tile_lists_max_tiles(void) { return MAX_SMEM_TILES; }
 extern "C" size_t frb_tile_lists_workspace_bytes(int n, int n_tiles) {
     if (n < 0) n = 0;
     if (n_tiles < 0) n_tiles = 0;
-    return sizeof(uint32_t) * ((size_t)(chunk_plan(n).chunks + 2) * n_tiles + 4);
+    return sizeof(uint32_t) * ((size_t)(2 * chunk_plan(n).chunks + 2) * n_tiles + 8);
 }
 
 extern "C" int frb_tile_count(int n, int n_views, int width, int height, const float* records,
@@ -406,7 +509,7 @@ extern "C" int frb_tile_count(int n, int n_views, int width, int height, const f
 }
 
 extern "C" int frb_tile_scan(int n, int n_tiles, int m_capacity, int32_t* ranges, int32_t* tile_order,
-                             uint32_t* m_out, void* workspace, void* stream) {
+                             uint32_t* m_out, const uint32_t* upstream_error, void* workspace, void* stream) {
     if (n < 0 || n_tiles < 0 || m_capacity < 0) return FRB_E_INVALID;
     if (n_tiles == 0) return 0;
     if (!ranges || !tile_order || !m_out || !workspace) return FRB_E_INVALID;
@@ -421,7 +524,38 @@ extern "C" int frb_tile_scan(int n, int n_tiles, int m_capacity, int32_t* ranges
         frb_note_launches(1);
     }
     frb_launch(tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, st, n_tiles, (const uint32_t*)w.total,
-               (uint32_t)m_capacity, (int2*)ranges, tile_order, w.start, m_out, w.flags);
+               (uint32_t)m_capacity, (int2*)ranges, tile_order, w.start, m_out, w.flags, upstream_error);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+// frb_tile_count + frb_tile_scan in one kernel launch (what the renderers call): the chunk CTAs obtain their column
+// prefixes by decoupled look-back and the last one runs the tile scan.  Same outputs as the pair.
+extern "C" int frb_tile_count_scan(int n, int n_views, int width, int height, const float* records, int m_capacity,
+                                   int32_t* ranges, int32_t* tile_order, uint32_t* m_out,
+                                   const uint32_t* upstream_error, void* workspace, void* stream) {
+    int rc = check_views(n, n_views, width, height);
+    if (rc) return rc;
+    if (m_capacity < 0) return FRB_E_INVALID;
+    const int tiles_x = frb_div_up(width, FRB_TILE), tiles_y = frb_div_up(height, FRB_TILE);
+    const int n_tiles = n_views * tiles_x * tiles_y;
+    if (n_tiles > MAX_SMEM_TILES) return FRB_E_TOO_LARGE;
+    if (!ranges || !tile_order || !m_out || !workspace) return FRB_E_INVALID;
+    if (n > 0 && (!records || frb_misaligned16(records))) return FRB_E_INVALID;
+    if (n == 0) {
+        rc = frb_tile_count(n, n_views, width, height, records, workspace, stream);
+        return rc ? rc : frb_tile_scan(n, n_tiles, m_capacity, ranges, tile_order, m_out, upstream_error, workspace, stream);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const ChunkPlan p = chunk_plan(n);
+    const WsView w = ws_view(workspace, n, n_tiles);
+    FRB_CUDA_OK(cudaMemsetAsync(w.flags, 0, sizeof(uint32_t) * (8 + (size_t)p.chunks * n_tiles), st));
+    FRB_CUDA_OK(frb_opt_in_smem(tile_count_scan_kernel, 4 * MAX_SMEM_TILES, &g_count_scan_opt_in));
+    frb_launch(tile_count_scan_kernel, dim3(p.chunks), dim3(SCAN_THREADS), sizeof(uint32_t) * (size_t)n_tiles, st, n,
+               p.chunk, p.chunks, n_tiles, n / n_views, tiles_x, tiles_x * tiles_y, (const float4*)records, w.status,
+               w.hist, w.ticket, (uint32_t)m_capacity, (int2*)ranges, tile_order, w.start, m_out, w.flags,
+               upstream_error);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

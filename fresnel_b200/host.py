@@ -51,9 +51,15 @@ class HostRenderSession:
     ``out_image``, ``out_depth`` and ``out_grads[name]`` after synchronising the current stream.
     """
 
-    def __init__(self, renderer, n_gaussians: int, device: torch.device):
+    def __init__(self, renderer, n_gaussians: int, device: torch.device, outputs=("image", "depth", "grads")):
+        """``outputs``: which results are copied back to the host every step (a training loop that keeps the image on
+        the device asks for ("grads",): 5.6 MB instead of 9.8 MB per step at 100k Gaussians / 512x512)."""
         if device.type != "cuda":
             raise TypeError("HostRenderSession needs a CUDA device (fresnel_b200 has no CPU path)")
+        bad = set(outputs) - {"image", "depth", "grads"}
+        if bad:
+            raise ValueError(f"unknown outputs {sorted(bad)}")
+        self.outputs = tuple(outputs)
         self.renderer, self.n, self.device = renderer, int(n_gaussians), device
         n, h, w = self.n, renderer.height, renderer.width
         f32 = dict(dtype=torch.float32, device=device)
@@ -82,7 +88,8 @@ class HostRenderSession:
         mk = lambda: torch.cuda.Event()
         self.e_start, self.e_params, self.e_grads, self.e_fwd, self.e_bwd, self.e_out = (mk() for _ in range(6))
         self.h2d_bytes = 4 * (blk + 4 * h * w)
-        self.d2h_bytes = 4 * (14 * n + 4 * h * w)
+        self.d2h_bytes = 4 * ((14 * n if "grads" in self.outputs else 0) + (3 * h * w if "image" in self.outputs else 0)
+                              + (h * w if "depth" in self.outputs else 0))
 
     def load(self, inputs: Dict[str, torch.Tensor], g_image: torch.Tensor, g_depth: torch.Tensor) -> None:
         """Host-side copy of caller tensors into the staging buffers (not needed if the caller writes there)."""
@@ -110,8 +117,10 @@ class HostRenderSession:
         self.e_fwd.record(main)
         s_out.wait_event(self.e_fwd)
         with torch.cuda.stream(s_out):
-            self.out_image.copy_(image.detach(), non_blocking=True)
-            self.out_depth.copy_(depth.detach(), non_blocking=True)
+            if "image" in self.outputs:
+                self.out_image.copy_(image.detach(), non_blocking=True)
+            if "depth" in self.outputs:
+                self.out_depth.copy_(depth.detach(), non_blocking=True)
         # no record_stream: the step ends with the compute stream waiting for the last copy (e_out), so memory
         # freed after the step cannot be reused before the copies have read it
         main.wait_event(self.e_grads)
@@ -126,7 +135,9 @@ class HostRenderSession:
         for k, off in (("positions", 4 * n), ("scales", 7 * n), ("colors", 10 * n), ("opacities", 13 * n)):
             packed = packed and grads[k].data_ptr() == p0 + 4 * off
         with torch.cuda.stream(s_out):
-            if packed:
+            if "grads" not in self.outputs:
+                pass
+            elif packed:
                 flat = torch.as_strided(g_rot, (14 * n,), (1,), g_rot.storage_offset())
                 self._out_g_block.copy_(flat, non_blocking=True)
             else:
@@ -153,11 +164,12 @@ class HostRenderPipeline:
     Graphs are cached per (slot, camera); a new camera costs one capture.
     """
 
-    def __init__(self, renderer, n_gaussians: int, device: torch.device, depth: int = 2, cuda_graph: bool = True):
+    def __init__(self, renderer, n_gaussians: int, device: torch.device, depth: int = 2, cuda_graph: bool = True,
+                 outputs=("image", "depth", "grads")):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.device, self.depth, self.cuda_graph = device, int(depth), bool(cuda_graph)
-        self.slots = [HostRenderSession(renderer, n_gaussians, device) for _ in range(self.depth)]
+        self.slots = [HostRenderSession(renderer, n_gaussians, device, outputs=outputs) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream(device) for _ in range(self.depth)]
         self.done = [torch.cuda.Event() for _ in range(self.depth)]
         self._busy = [False] * self.depth

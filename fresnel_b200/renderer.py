@@ -191,16 +191,25 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
         b.depth_bits = low_word_fn(b)
     b.order = None
     rank = None
+    sort_err = None
     if sort and presort and n > 0:
         b.order = torch.empty(n, **i32)
         rank = torch.empty(n, **i32)
         ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=dev)
-        _call("frb_depth_order", L.frb_depth_order_rank, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(rank), _ptr(ws), st)
+        sort_err = (ws, L.frb_depth_order_error_word(n, _ptr(ws)))       # ws kept alive with its error word
+        if low_word_fn is None and project_fn is None:
+            # keys = depth bits over the cameras' [near, far] only: fewer radix passes for narrow slabs (csrc/sort.cu)
+            cam2 = cam.reshape(-1, 20)
+            _call("frb_depth_order", L.frb_depth_order_range, n, _ptr(b.depth_bits), float(cam2[:, 18].min()),
+                  float(cam2[:, 19].max()), _ptr(b.order), _ptr(rank), _ptr(ws), st)
+        else:
+            _call("frb_depth_order", L.frb_depth_order_rank, n, _ptr(b.depth_bits), _ptr(b.order), _ptr(rank),
+                  _ptr(ws), st)
 
     if (sort and presort and low_word_fn is None and project_fn is None and n > 0 and TILE_LISTS
             and n <= L.frb_tile_lists_max_gaussians() and n_tiles <= L.frb_tile_lists_max_tiles()):
-        return _tile_lists(b, rank, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync, mode, dev,
-                           st)
+        return _tile_lists(b, rank, sort_err, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync,
+                           mode, dev, st)
 
     offsets = torch.empty(n + 1, **i32)
     ws = torch.empty(max(L.frb_scan_workspace_bytes(n), 4), dtype=torch.uint8, device=dev)
@@ -257,31 +266,34 @@ def build_bins(positions, scales, rotations, colors, opacities, cam_vecs: np.nda
 TILE_LISTS = True       # tile lists by counting + bitmap ranking (csrc/tile_lists.cu); False = the 64-bit key sort
 
 
-def _tile_lists(b: TileBins, rank, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync, mode, dev,
-                st):
+def _tile_lists(b: TileBins, rank, sort_err, n, n_views, n_tiles, width, height, max_radius, phases, keep_debug, sync,
+                mode, dev, st):
     """Binning without a sort over the instances: frb_tile_count -> frb_tile_scan -> frb_tile_emit ->
     frb_tile_rank_gather (csrc/tile_lists.cu).  Same lists, bit for bit, as the key sort (``b.keys`` is produced
     only with ``keep_debug``)."""
     L = _lib.lib()
     i32 = dict(dtype=torch.int32, device=dev)
     ws = torch.empty(L.frb_tile_lists_workspace_bytes(n, n_tiles), dtype=torch.uint8, device=dev)
-    _call("frb_tile_count", L.frb_tile_count, n, n_views, width, height, _ptr(b.records), _ptr(ws), st)
     worst = worst_case_instances(n, n_views, width, height, max_radius)
     if sync is None:
         sync = keep_debug or phases is not None or mode != 0 or worst * INSTANCE_BYTES > SYNC_FREE_BUDGET_BYTES
     b.ranges = torch.empty(n_tiles, 2, **i32)
     tile_order = torch.empty(n_tiles, **i32)
-    m_out = torch.empty(1, **i32)
+    m_out = torch.empty(2, **i32)       # [instance count, status]
     # sync: scan without a capacity, read the instance count back (the one host sync), size the buffers exactly;
     # otherwise the buffers hold the worst case and the count stays on the device
     cap = (2 ** 31 - 1) if sync else worst
-    _call("frb_tile_scan", L.frb_tile_scan, n, n_tiles, cap, _ptr(b.ranges), _ptr(tile_order), _ptr(m_out), _ptr(ws),
-          st)
+    _call("frb_tile_count_scan", L.frb_tile_count_scan, n, n_views, width, height, _ptr(b.records), cap, _ptr(b.ranges),
+          _ptr(tile_order), _ptr(m_out), sort_err[1] if sort_err is not None else None, _ptr(ws), st)
     if sync:
-        m, m_dev = int(m_out.item()), None
+        m, status = m_out.tolist()           # the one host sync: count and status in one read
+        if status & 2:
+            raise _lib.FresnelB200Error("fresnel_b200: the depth sort's decoupled look-back gave up (SPIN_LIMIT); "
+                                        "the tile lists of this call are not trustworthy")
+        m_dev = None
         cap = b.m_alloc = instance_capacity(m)
     else:
-        m, m_dev = worst, m_out
+        m, m_dev = worst, m_out[:1]
         b.m_alloc = worst
     b.m, b.m_dev = m, m_dev
     b.tile_order = tile_order

@@ -112,6 +112,12 @@ int frb_depth_order(int n, const uint32_t* depth_bits, uint32_t* order, void* wo
 /* The same, and rank[g] = position of Gaussian g in that order (the inverse permutation; nullable). */
 int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t* order, uint32_t* rank, void* workspace,
                          void* stream);
+/* The same for what a camera can see: keys are the depth bits clamped to the bit patterns of [near_depth, far_depth]
+ * minus the lower one, sorted on the bits that range needs (fewer passes for narrow slabs; 2^27 values and more fall
+ * back to frb_depth_order_rank).  The order of the visible Gaussians
+ * (near < depth < far, DR:541) is exactly frb_depth_order's; culled ones collapse to the two ends in index order. */
+int frb_depth_order_range(int n, const uint32_t* depth_bits, float near_depth, float far_depth, uint32_t* order,
+                          uint32_t* rank, void* workspace, void* stream);
 /* offsets[k] = sum_{j<k} tiles_touched[order[j]] for k = 0..n (order NULL = identity);
  * offsets[n] = number of tile instances M. */
 size_t frb_scan_workspace_bytes(int n);
@@ -186,9 +192,9 @@ int frb_composite_bwd(int n_views, int width, int height, const int32_t* ranges,
  * and gathers the records.  Needs n <= frb_tile_lists_max_gaussians() (the bitmap must fit one SM's shared memory).
  * and the image must have at most frb_tile_lists_max_tiles() tiles over all views (one counter per tile in shared
  * memory).  workspace: frb_tile_lists_workspace_bytes(n, n_tiles), written by frb_tile_count and frb_tile_scan,
- * consumed by frb_tile_emit (counting and scanning need no depth order: they may run beside the depth sort);
- * order / rank: frb_depth_order_rank's outputs; *m_out = total number of instances (may exceed
- * m_capacity: then the lists are truncated to the capacity and the caller must retry with more room); inst_rank:
+ * consumed by frb_tile_emit; order / rank: frb_depth_order_rank's outputs; m_out[0] = total number of instances
+ * (may exceed m_capacity: then the lists are truncated to the capacity and the caller must retry with more room);
+ * inst_rank:
  * m_capacity words; sorted_keys (nullable): the 64-bit (tile | depth bits) keys, for checks. */
 int frb_tile_lists_max_gaussians(void);
 int frb_tile_lists_max_tiles(void);
@@ -196,7 +202,17 @@ size_t frb_tile_lists_workspace_bytes(int n, int n_tiles);
 int frb_tile_count(int n, int n_views, int width, int height, const float* records, void* workspace,
                    void* stream);
 int frb_tile_scan(int n, int n_tiles, int m_capacity, int32_t* ranges, int32_t* tile_order, uint32_t* m_out,
-                  void* workspace, void* stream);
+                  const uint32_t* upstream_error, void* workspace, void* stream);
+/* m_out: TWO words - [0] the instance count, [1] a status: bit 0 = the lists were truncated to m_capacity, bit 1 =
+ * *upstream_error was set (nullable; frb_depth_order_error_word: a radix pass of the depth sort gave up on a
+ * look-back, its order is not trustworthy).  Callers that read the count read the status with it. */
+const uint32_t* frb_depth_order_error_word(int n, const void* workspace);
+/* frb_tile_count + frb_tile_scan in ONE kernel (what the renderers call): the chunk CTAs obtain "instances of tile t
+ * in earlier chunks" by decoupled look-back over each other's histogram rows, the CTA that started last runs the
+ * tile scan on the column totals it ends up with.  Same outputs. */
+int frb_tile_count_scan(int n, int n_views, int width, int height, const float* records, int m_capacity,
+                        int32_t* ranges, int32_t* tile_order, uint32_t* m_out, const uint32_t* upstream_error,
+                        void* workspace, void* stream);
 int frb_tile_emit(int n, int n_views, int width, int height, const float* records, const uint32_t* rank,
                   int m_capacity, void* workspace, uint32_t* inst_rank, void* stream);
 int frb_tile_rank_gather(int n, int n_tiles, const int32_t* tile_order, const int32_t* ranges,

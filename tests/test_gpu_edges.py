@@ -144,3 +144,68 @@ def test_missing_phases_raise_value_error_like_the_reference():
     for ren in (fresnel_b200.WaveFieldRenderer(W, H), fresnel_b200.ASMWaveFieldRenderer(W, H).to(dev())):
         with pytest.raises(ValueError):                          # DR:779-780, DR:1187-1188
             ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam)
+
+
+def test_parameter_views_at_any_float_offset_are_accepted():
+    """The reference accepts any tensor; the kernels read rotations (and write their gradient) as 16-byte vectors.
+    Contiguous (N, 4) views into a flat buffer that start at a float offset which is not a multiple of four
+    (torch.split of a flat parameter vector, flat[a:b].view(n, 4) with odd n) must render like a fresh tensor instead
+    of faulting on the device - and the C ABI refuses a misaligned pointer with FRB_E_INVALID."""
+    from fresnel_b200 import _lib
+    from fresnel_b200.renderer import _ptr, _stream
+    from fresnel_b200.camera import camera_vector
+    d = dev()
+    W, H, n = 64, 48, 333                                  # odd n: 3n is odd, so the rotations start misaligned
+    inp = fo.synthetic_cloud(n, seed=77, s_lo=0.01, s_hi=0.08)
+    cam = fo.default_camera(W, H)
+    flat = torch.cat([inp["positions"].reshape(-1), inp["rotations"].reshape(-1), inp["scales"].reshape(-1),
+                      inp["colors"].reshape(-1), inp["opacities"]]).to(d).requires_grad_(True)
+    pos, rot, scl, col, opa = torch.split(flat, [3 * n, 4 * n, 3 * n, 3 * n, n])
+    rot_v = rot.view(n, 4)
+    assert rot_v.data_ptr() % 16 != 0
+    ren = fresnel_b200.TileBasedRenderer(W, H, background=(0.1, 0.2, 0.3))
+    img, dep = ren(pos.view(n, 3), scl.view(n, 3), rot_v, col.view(n, 3), opa, cam, return_depth=True)
+    (img.sum() + dep.sum()).backward()
+    L = {k: inp[k].to(d).requires_grad_(True) for k in GRAD_NAMES}
+    img2, dep2 = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam, return_depth=True)
+    (img2.sum() + dep2.sum()).backward()
+    assert torch.equal(img, img2) and torch.equal(dep, dep2)
+    want = torch.cat([L["positions"].grad.reshape(-1), L["rotations"].grad.reshape(-1), L["scales"].grad.reshape(-1),
+                      L["colors"].grad.reshape(-1), L["opacities"].grad])
+    assert rel(flat.grad.cpu(), want.cpu()) < 1e-6
+    # C ABI: the same misaligned pointer is an argument error, not a device fault
+    lib = _lib.lib()
+    rec = torch.empty(n, 12, device=d)
+    db = torch.empty(n, dtype=torch.int32, device=d)
+    tt = torch.empty(n, dtype=torch.int32, device=d)
+    camv = camera_vector(cam, W, H)
+    rc = lib.frb_project_fwd(n, 1, _ptr(L["positions"]), _ptr(L["scales"]), rot_v.data_ptr(), _ptr(L["colors"]),
+                             _ptr(L["opacities"]), camv.ctypes.data, 64.0, _ptr(rec), None, _ptr(db), _ptr(tt), None,
+                             _stream())
+    assert rc != 0 and b"invalid" in lib.frb_error_string(rc)
+    torch.cuda.synchronize()                               # no sticky error
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_forward_and_backward_on_two_devices_of_one_process():
+    """The opt-in for more than 48 KB of dynamic shared memory is a per-DEVICE attribute: one process that renders on
+    cuda:0 and then on cuda:1 must be able to launch the backward kernels (105 KB) on both, for the plain and the
+    phase-blending compositor, and get the same result on both."""
+    W, H, n = 96, 80, 1500
+    inp = fo.synthetic_cloud(n, seed=79, s_lo=0.01, s_hi=0.06)
+    cam = fo.default_camera(W, H)
+    outs = []
+    for idx in (0, 1, 0):
+        d = torch.device("cuda", idx)
+        for phase in (False, True):
+            ren = fresnel_b200.TileBasedRenderer(W, H, use_phase_blending=phase)
+            L = {k: inp[k].to(d).requires_grad_(True) for k in GRAD_NAMES + ("phases",)}
+            img, dep = ren(L["positions"], L["scales"], L["rotations"], L["colors"], L["opacities"], cam,
+                           return_depth=True, phases=L["phases"] if phase else None)
+            (img.sum() + dep.sum()).backward()
+            torch.cuda.synchronize(d)
+            outs.append((idx, phase, img.detach().cpu(), L["positions"].grad.cpu()))
+    for idx, phase, img, g in outs[2:]:
+        ref = outs[1 if phase else 0]
+        assert torch.equal(img, ref[2]), (idx, phase)
+        assert rel(g, ref[3]) < 1e-5, (idx, phase)

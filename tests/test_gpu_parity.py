@@ -127,6 +127,41 @@ def test_depth_order_matches_stable_argsort(n):
     assert np.array_equal(order.cpu().numpy(), np.argsort(bits, kind="stable").astype(np.int32))
 
 
+@pytest.mark.parametrize("near,far", [(0.01, 100.0), (1.4, 2.6), (1e-6, 1e6), (0.5, 0.5000001)])
+@pytest.mark.parametrize("n", [1, 513, 100_000, 600_000])
+def test_depth_order_over_the_camera_range(n, near, far):
+    """frb_depth_order_range (one to four 8-bit passes on the depth bits clamped to [near, far], or the 32-bit
+    fallback for very wide ranges): the VISIBLE Gaussians (near < depth < far) come out in exactly the stable order of
+    the full sort, order is a permutation and rank its inverse.  Inputs include exact ties, depths on and beyond both
+    planes, negative depths, zeros and NaNs."""
+    L = _lib.lib()
+    d = dev()
+    rng = np.random.default_rng(n + int(near * 1000))
+    depth = (rng.random(n, dtype=np.float32) * (far - near) * 1.5 + near * 0.5).astype(np.float32)
+    k = max(n // 7, 1)
+    depth[rng.integers(0, n, k)] = np.float32((near + far) / 2)          # exact ties inside the range
+    depth[rng.integers(0, n, k)] = np.float32(near)                      # on the planes: culled
+    depth[rng.integers(0, n, k)] = np.float32(far)
+    depth[rng.integers(0, n, k)] *= np.float32(-1.0)                     # behind the camera
+    depth[rng.integers(0, n, max(k // 8, 1))] = np.float32(np.nan)
+    depth[rng.integers(0, n, max(k // 8, 1))] = np.float32(0.0)
+    bits = depth.view(np.uint32)
+    db = torch.from_numpy(bits.view(np.int32).copy()).to(d)
+    order = torch.empty(n, dtype=torch.int32, device=d)
+    rank = torch.empty(n, dtype=torch.int32, device=d)
+    ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device=d)
+    _lib.check(L.frb_depth_order_range(n, _ptr(db), float(near), float(far), _ptr(order), _ptr(rank), _ptr(ws),
+                                       _stream()), "frb_depth_order_range")
+    torch.cuda.synchronize()
+    o, r = order.cpu().numpy(), rank.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(n))
+    assert np.array_equal(r[o], np.arange(n))
+    with np.errstate(invalid="ignore"):
+        vis = (depth > np.float32(near)) & (depth < np.float32(far))
+    full = np.argsort(bits, kind="stable")
+    assert np.array_equal(o[vis[o]], full[vis[full]])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_views", [1, 3])
 def test_fused_scan_emit_sort_equals_the_staged_binning(golden, n_views):
@@ -209,6 +244,51 @@ def test_tile_lists_by_bitmap_ranking_equal_the_key_sort(case):
     assert np.array_equal(np.sort(order), np.arange(order.size))
     ln = (a.ranges[:, 1] - a.ranges[:, 0]).cpu().numpy()[order] >> 3
     assert np.all(np.diff(np.minimum(ln, 1023)) <= 0)
+
+
+def test_tile_count_and_scan_stage_functions_equal_the_fused_kernel():
+    """frb_tile_count + frb_tile_scan (column prefix kernel + one-CTA scan) give the ranges, launch order, instance count
+    and per-chunk bases the fused frb_tile_count_scan (decoupled look-back over the chunk rows) gives: 2 views, 1200
+    tiles, 150k Gaussians (147 chunks)."""
+    d = dev()
+    L = _lib.lib()
+    n1, W, H, views = 75_000, 480, 320, 2
+    inp = fo.synthetic_cloud(n1 * views, 71, 0.005, 0.04)
+    t = {k: inp[k].to(d).contiguous() for k in GRAD_NAMES}
+    cams = [fresnel_b200.Camera(0.8 * W, 0.8 * W, W / 2 + 3 * v, H / 2, W, H) for v in range(views)]
+    camv = np.stack([camera_vector(c, W, H) for c in cams])
+    n = n1 * views
+    n_tiles = views * ((W + 15) // 16) * ((H + 15) // 16)
+    rec = torch.empty(n, 12, device=d)
+    db = torch.empty(n, dtype=torch.int32, device=d)
+    tt = torch.empty(n, dtype=torch.int32, device=d)
+    _lib.check(L.frb_project_fwd(n, views, _ptr(t["positions"]), _ptr(t["scales"]), _ptr(t["rotations"]),
+                                 _ptr(t["colors"]), _ptr(t["opacities"]), camv.ctypes.data, 64.0, _ptr(rec), None,
+                                 _ptr(db), _ptr(tt), None, _stream()), "project")
+    out = []
+    for fused in (True, False):
+        ws = torch.zeros(L.frb_tile_lists_workspace_bytes(n, n_tiles), dtype=torch.uint8, device=d)
+        ranges = torch.empty(n_tiles, 2, dtype=torch.int32, device=d)
+        order = torch.empty(n_tiles, dtype=torch.int32, device=d)
+        m_out = torch.empty(2, dtype=torch.int32, device=d)
+        if fused:
+            _lib.check(L.frb_tile_count_scan(n, views, W, H, _ptr(rec), 2 ** 31 - 1, _ptr(ranges), _ptr(order),
+                                             _ptr(m_out), None, _ptr(ws), _stream()), "count_scan")
+        else:
+            _lib.check(L.frb_tile_count(n, views, W, H, _ptr(rec), _ptr(ws), _stream()), "count")
+            _lib.check(L.frb_tile_scan(n, n_tiles, 2 ** 31 - 1, _ptr(ranges), _ptr(order), _ptr(m_out), None, _ptr(ws),
+                                       _stream()), "scan")
+        torch.cuda.synchronize()
+        chunks = -(-n // -(-n // min(148, -(-n // 1024))))
+        base = ws.view(torch.int32)[:chunks * n_tiles].clone()
+        out.append((ranges, m_out.clone(), base, order))
+    assert int(out[0][1][0]) == int(tt.sum()) and int(out[0][1][1]) == 0
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    ln = (out[0][0][:, 1] - out[0][0][:, 0]).cpu().numpy()
+    for o in (out[0][3], out[1][3]):
+        o = o.cpu().numpy()
+        assert np.array_equal(np.sort(o), np.arange(n_tiles))
+        assert np.all(np.diff(np.minimum(ln[o] >> 3, 1023)) <= 0)
 
 
 @pytest.mark.parametrize("presort", [True, False])
