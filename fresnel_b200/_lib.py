@@ -85,6 +85,8 @@ _SIGNATURES = {
     "frb_recon_loss_bwd_ex": (c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, P, P, P, P, c_float,
                                       c_float, c_float, c_int, P, c_float, c_int, P, P, P, P, P]),
     "frb_composite_fwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, c_float, P, c_float, c_float, P, P, P, P, P, P, P]),
+    "frb_composite_fwd_gather": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P, P, c_float, c_float, P, P, P, P, P, P]),
+    "frb_composite_bwd_gather": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P, P, c_float, P, P, P, P, P, P, P]),
     "frb_composite_bwd_cap": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_float, P, c_float, P, P, P, P, P, P, P, P,
                                       P]),
     "frb_simple_project_fwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P]),
@@ -106,7 +108,7 @@ _OPTIONAL = {}
 class TileLayout(ctypes.Structure):
     """FrbTileLayout of include/fresnel_b200.h."""
     _fields_ = [(name, c_size_t) for name in (
-        "ranges", "tile_order", "state_T", "state_n", "sorted_gids", "sorted_records", "persist_bytes", "records", "depth_bits",
+        "ranges", "tile_order", "state_T", "state_n", "sorted_gids", "sorted_records", "records", "persist_bytes", "depth_bits",
         "touched", "order", "offsets", "depth_ws", "scan_ws", "keys", "keys_tmp", "vals_tmp", "sort_ws",
         "tile_ws", "inst_rank", "rank", "scratch_bytes")]
 

@@ -27,14 +27,28 @@
 
 namespace {
 
+// GATHER = false: the tile's records are a contiguous span of sorted_records (one 1D bulk copy per batch, 48-byte rows).
+// GATHER = true: the tile's list is a span of Gaussian ids and the records are fetched from the UNSORTED array by TMA
+// tile::gather4 (SASS UTMALDG.2D.GATHER4: four rows of a 2D tensor map by row index per operation, 64-byte rows in
+// shared memory - the box is 16 floats wide so that every 4-row group lands 256-byte aligned; columns 12..15 are out of
+// bounds and zero-filled).  The gather removes the 48 M-byte write and read-back of the sorted record copy.
+template <bool GATHER>
+struct FwdStage {
+    static constexpr int RS = GATHER ? 4 : 3;           // float4 per record in shared memory
+    float4 rec[BATCH * RS];
+};
+
+template <bool GATHER>
 __global__ void __launch_bounds__(CTA_THREADS)
 composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
-                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records, float3 bg, float t_eps,
-                     float alpha_max, float* __restrict__ image,
+                     const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
+                     const __grid_constant__ CUtensorMap record_map, const uint32_t* __restrict__ sorted_gids,
+                     float3 bg, float t_eps, float alpha_max, float* __restrict__ image,
                      float* __restrict__ depth_out, float* __restrict__ alpha_out, float* __restrict__ state_T,
                      int* __restrict__ state_n) {
     frb_pdl_prologue();
-    __shared__ StageBuf stage[STAGES];
+    constexpr int RS = FwdStage<GATHER>::RS;
+    __shared__ __align__(1024) FwdStage<GATHER> stage[STAGES];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
 
     const int tile = tile_order ? tile_order[blockIdx.x] : blockIdx.x;   // heaviest tiles first
@@ -57,14 +71,37 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         frb_mbar_fence_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < STAGES && b < n_batches; ++b) {
-            int cnt = min(BATCH, count - b * BATCH);
-            frb_mbar_expect_tx(&full_bar[b], cnt * RECORD_BYTES);
-            frb_tma_load_1d(stage[b].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
-                            &full_bar[b]);
+    // producer: thread 0 (bulk copy) or lanes 0..15 of warp 0 (gather: lane q fetches records 4q..4q+3 of the batch)
+    uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);           // gather: ids of my group in the next batch to be issued
+    auto load_ids = [&](int b) {
+        if (GATHER && threadIdx.x < BATCH / 4 && b < n_batches) {
+            const int i0 = b * BATCH + 4 * (int)threadIdx.x, last = count - 1;
+            const uint32_t* g = sorted_gids + range.x;
+            pre_g = make_uint4(g[min(i0, last)], g[min(i0 + 1, last)], g[min(i0 + 2, last)], g[min(i0 + 3, last)]);
         }
+    };
+    auto issue = [&](int b) {
+        const int s = b % STAGES;
+        const int cnt = min(BATCH, count - b * BATCH);
+        if (!GATHER) {
+            if (threadIdx.x == 0) {
+                frb_mbar_expect_tx(&full_bar[s], cnt * RECORD_BYTES);
+                frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
+                                &full_bar[s]);
+            }
+        } else if (threadIdx.x < 32) {
+            const int groups = (cnt + 3) >> 2;
+            if (threadIdx.x == 0) frb_mbar_expect_tx(&full_bar[s], groups * 4 * RS * 16);
+            __syncwarp();
+            if ((int)threadIdx.x < groups)
+                frb_tma_gather4(stage[s].rec + 4 * RS * threadIdx.x, &record_map, pre_g, &full_bar[s]);
+        }
+    };
+    for (int b = 0; b < STAGES && b < n_batches; ++b) {
+        load_ids(b);
+        issue(b);
     }
+    load_ids(STAGES);
 
     float T = 1.0f, acc = 0.0f, W1 = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;   // W1 = 1 - acc
     int consumed = count;               // list entries walked; lowered when the pixel stops early
@@ -78,9 +115,9 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
         if (cnt_pad != cnt) {
             // last batch: pad to a whole chunk with records whose rectangle contains no pixel
-            if (threadIdx.x < (cnt_pad - cnt) * 3) {
-                const int k = threadIdx.x % 3;
-                stage[s].rec[3 * cnt + threadIdx.x] =
+            if (threadIdx.x < (cnt_pad - cnt) * RS) {
+                const int k = threadIdx.x % RS;
+                stage[s].rec[RS * cnt + threadIdx.x] =
                     make_float4(0.f, 0.f, 0.f, k == 1 ? __uint_as_float(NULL_RECT_LO)
                                                       : (k == 2 ? __uint_as_float(NULL_RECT_HI) : 0.f));
             }
@@ -92,9 +129,9 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 #pragma unroll
                 for (int k = 0; k < CHUNK; ++k) {
                     const int j = j0 + k;
-                    float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
+                    float4 r1 = rec[RS * j + 1], r2 = rec[RS * j + 2];
                     if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
-                        float4 r0 = rec[3 * j + 0];
+                        float4 r0 = rec[RS * j + 0];
                         float dx = fpx - r0.x, dy = fpy - r0.y;
                         float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                         float a = frb_ex2(power) * r1.y;
@@ -126,12 +163,9 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 frb_mbar_wait(&full_bar[bb % STAGES], (bb / STAGES) & 1);
             break;
         }
-        if (threadIdx.x == 0 && b + STAGES < n_batches) {
-            int nb = b + STAGES;
-            int ncnt = min(BATCH, count - nb * BATCH);
-            frb_mbar_expect_tx(&full_bar[s], ncnt * RECORD_BYTES);
-            frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + nb * BATCH), ncnt * RECORD_BYTES,
-                            &full_bar[s]);
+        if (b + STAGES < n_batches) {
+            issue(b + STAGES);
+            load_ids(b + STAGES + 1);
         }
     }
 
@@ -180,8 +214,9 @@ constexpr int N_GRADS = 10;
 // occupancy 24 -> 36 %, issue slots 69 -> 76 % busy, but the two-halves loop costs 13 % more instructions (161.2 M
 // against 142.4 M: the cross-half shuffles, a second pass over the candidate mask and record loads) - 199 us against
 // 188 us on the same box (profiles/r2_d_*).  The kernel is bound by instructions issued, not by residency.
+template <bool GATHER>
 struct BwdSmem {
-    StageBuf stage[STAGES];
+    FwdStage<GATHER> stage[STAGES];                 // first: the gather destinations need 128-byte alignment
     float2 pair[BWD_WARPS][32 * PAIR_STRIDE];
     float part[BWD_WARPS][N_GRADS][BATCH];
     float4 pixc[BWD_WARPS][32];
@@ -190,17 +225,19 @@ struct BwdSmem {
     int max_n;
 };
 
+template <bool GATHER>
 __global__ void __launch_bounds__(CTA_THREADS, 2)
 composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
                      const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
-                     const uint32_t* __restrict__ sorted_gids,
+                     const __grid_constant__ CUtensorMap record_map, const uint32_t* __restrict__ sorted_gids,
                      float3 bg, float alpha_max, const float* __restrict__ state_T,
                      const int* __restrict__ state_n, const float* __restrict__ g_image,
                      const float* __restrict__ g_depth, const float* __restrict__ g_alpha,
                      float* __restrict__ grad2d) {
     frb_pdl_prologue();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    constexpr int RS = FwdStage<GATHER>::RS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    BwdSmem<GATHER>& sm = *reinterpret_cast<BwdSmem<GATHER>*>(smem_raw);
 
     const int tile = tile_order ? tile_order[blockIdx.x] : blockIdx.x;   // heaviest tiles first
     const int view = tile / tiles_per_view;
@@ -253,17 +290,40 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const int n_batches = (count + BATCH - 1) / BATCH;
     if (n_batches == 0) return;
 
-    // batches are visited last to first; ring slot (visit % STAGES) holds visit
-    auto issue = [&](int visit) {
-        int b = n_batches - 1 - visit;
-        int s = visit % STAGES;
-        int cnt = min(BATCH, count - b * BATCH);
-        frb_mbar_expect_tx(&sm.full_bar[s], cnt * RECORD_BYTES);
-        frb_tma_load_1d(sm.stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
-                        &sm.full_bar[s]);
+    // batches are visited last to first; ring slot (visit % STAGES) holds visit.  Producer: thread 0 (bulk copy of the
+    // sorted records) or lanes 0..15 of warp 0 (gather4 by Gaussian id, ids prefetched one visit ahead).
+    uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);
+    auto load_ids = [&](int visit) {
+        if (GATHER && threadIdx.x < BATCH / 4 && visit < n_batches) {
+            const int b = n_batches - 1 - visit;
+            const int i0 = b * BATCH + 4 * (int)threadIdx.x, last = count - 1;
+            const uint32_t* g = sorted_gids + range.x;
+            pre_g = make_uint4(g[min(i0, last)], g[min(i0 + 1, last)], g[min(i0 + 2, last)], g[min(i0 + 3, last)]);
+        }
     };
-    if (threadIdx.x == 0)
-        for (int v = 0; v < STAGES && v < n_batches; ++v) issue(v);
+    auto issue = [&](int visit) {
+        const int b = n_batches - 1 - visit;
+        const int s = visit % STAGES;
+        const int cnt = min(BATCH, count - b * BATCH);
+        if (!GATHER) {
+            if (threadIdx.x == 0) {
+                frb_mbar_expect_tx(&sm.full_bar[s], cnt * RECORD_BYTES);
+                frb_tma_load_1d(sm.stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
+                                &sm.full_bar[s]);
+            }
+        } else if (threadIdx.x < 32) {
+            const int groups = (cnt + 3) >> 2;
+            if (threadIdx.x == 0) frb_mbar_expect_tx(&sm.full_bar[s], groups * 4 * RS * 16);
+            __syncwarp();
+            if ((int)threadIdx.x < groups)
+                frb_tma_gather4(sm.stage[s].rec + 4 * RS * threadIdx.x, &record_map, pre_g, &sm.full_bar[s]);
+        }
+    };
+    for (int v = 0; v < STAGES && v < n_batches; ++v) {
+        load_ids(v);
+        issue(v);
+    }
+    load_ids(STAGES);
 
     const float X = gr * bg.x + gg * bg.y + gb * bg.z - ga;
     const float TX = T_final * X;
@@ -287,8 +347,8 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             {
                 bool ok = false;
                 if (lane < sub_cnt) {
-                    const uint32_t lo = __float_as_uint(rec[3 * (sb * 32 + lane) + 1].w);
-                    const uint32_t hi = __float_as_uint(rec[3 * (sb * 32 + lane) + 2].w) & 0x7fff7fffu;
+                    const uint32_t lo = __float_as_uint(rec[RS * (sb * 32 + lane) + 1].w);
+                    const uint32_t hi = __float_as_uint(rec[RS * (sb * 32 + lane) + 2].w) & 0x7fff7fffu;
                     ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
                          (int)(hi >> 16) > wy0;
                 }
@@ -306,10 +366,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             auto stage_a = [&](int j) {
                 Pre p;
                 const int jb = sb * 32 + j;
-                const float4 r1 = rec[3 * jb + 1], r2 = rec[3 * jb + 2];
+                const float4 r1 = rec[RS * jb + 1], r2 = rec[RS * jb + 2];
                 p.active = (j < local_n) &&
                            rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
-                const float4 r0 = rec[3 * jb + 0];
+                const float4 r0 = rec[RS * jb + 0];
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                 const float g = frb_ex2(power);
@@ -353,7 +413,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                   d_g = 0.f, d_b = 0.f;
             if ((gmask >> lane) & 1u) {
                 const int jb = sb * 32 + lane;
-                const float4 r0 = rec[3 * jb + 0], r1 = rec[3 * jb + 1];
+                const float4 r0 = rec[RS * jb + 0], r1 = rec[RS * jb + 1];
                 const float oln2 = r1.y * FRB_LN2;
                 const float ux = wbx - r0.x, uy = wby - r0.y;
                 const float2* row = my_pair + lane * PAIR_STRIDE;
@@ -410,7 +470,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             }
         }
         __syncthreads();    // stage s, gid[s] and part are free
-        if (threadIdx.x == 0 && visit + STAGES < n_batches) issue(visit + STAGES);
+        if (visit + STAGES < n_batches) {
+            issue(visit + STAGES);
+            load_ids(visit + STAGES + 1);
+        }
     }
 }
 
@@ -518,9 +581,35 @@ extern "C" int frb_composite_fwd_cap(int n_views, int width, int height, const i
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    frb_launch(composite_fwd_kernel, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream, 
-        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, bg, t_eps,
-        alpha_max, image, depth, alpha, state_T, state_n);
+    CUtensorMap no_map = {};
+    frb_launch(composite_fwd_kernel<false>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, no_map,
+        (const uint32_t*)nullptr, bg, t_eps, alpha_max, image, depth, alpha, state_T, state_n);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same compositor reading the tile lists as Gaussian ids: records[n_records] is the UNSORTED record array of
+// frb_project_fwd, sorted_gids the per-tile lists; the records are fetched by TMA tile::gather4.
+extern "C" int frb_composite_fwd_gather(int n_views, int width, int height, const int32_t* tile_order,
+                                        const int32_t* ranges, const float* records, int n_records,
+                                        const uint32_t* sorted_gids, const float* background_host, float t_eps,
+                                        float alpha_max, float* image, float* depth, float* alpha, float* state_T,
+                                        int32_t* state_n, void* stream) {
+    if (!(alpha_max > 0.0f && alpha_max < 1.0f)) return FRB_E_INVALID;
+    int rc = check_image_args(n_views, width, height);
+    if (rc) return rc;
+    if (!ranges || !background_host || !image || !depth || !alpha || !state_T || !state_n || !sorted_gids)
+        return FRB_E_INVALID;
+    CUtensorMap map;
+    if ((rc = frb_record_tensor_map(records, n_records, &map))) return rc;
+    int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
+    int tpv = tiles_x * tiles_y;
+    float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
+    frb_launch(composite_fwd_kernel<true>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
+        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map, sorted_gids, bg,
+        t_eps, alpha_max, image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
@@ -571,10 +660,37 @@ extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const i
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     static unsigned long long smem_opted_in = 0;          // per-device bitmask (the attribute is per device)
-    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel, (int)sizeof(BwdSmem), &smem_opted_in));
-    frb_launch(composite_bwd_kernel, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem), (cudaStream_t)stream, 
-        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, sorted_gids,
-        bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<false>, (int)sizeof(BwdSmem<false>), &smem_opted_in));
+    CUtensorMap no_map = {};
+    frb_launch(composite_bwd_kernel<false>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<false>),
+        (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges,
+        (const float4*)sorted_records, no_map, sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha,
+        grad2d);
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+// frb_composite_bwd_cap reading the records of the tile lists by TMA tile::gather4 from the unsorted record array.
+extern "C" int frb_composite_bwd_gather(int n_views, int width, int height, const int32_t* tile_order,
+                                        const int32_t* ranges, const float* records, int n_records,
+                                        const uint32_t* sorted_gids, const float* background_host, float alpha_max,
+                                        const float* state_T, const int32_t* state_n, const float* g_image,
+                                        const float* g_depth, const float* g_alpha, float* grad2d, void* stream) {
+    if (!(alpha_max > 0.0f && alpha_max < 1.0f)) return FRB_E_INVALID;
+    int rc = check_image_args(n_views, width, height);
+    if (rc) return rc;
+    if (!ranges || !background_host || !state_T || !state_n || !g_image || !grad2d || !sorted_gids) return FRB_E_INVALID;
+    CUtensorMap map;
+    if ((rc = frb_record_tensor_map(records, n_records, &map))) return rc;
+    int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
+    int tpv = tiles_x * tiles_y;
+    float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
+    static unsigned long long smem_opted_in = 0;
+    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<true>, (int)sizeof(BwdSmem<true>), &smem_opted_in));
+    frb_launch(composite_bwd_kernel<true>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<true>),
+        (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map,
+        sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;

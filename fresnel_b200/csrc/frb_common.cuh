@@ -1,5 +1,6 @@
 // Shared device helpers: error plumbing, mbarrier + 1D TMA bulk copy (sm_100a PTX), warp utilities.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,10 @@ int frb_fill_views(int n, int n_views, const float* camera_host, FrbViewSet* vs)
         cudaError_t _e = cudaGetLastError();       \
         if (_e != cudaSuccess) return (int)_e;     \
     } while (0)
+
+// 2D tensor map over an array of n 48-byte records (12 floats per row) for frb_tma_gather4: box {16, 1}, no swizzle.
+// Encoded through the driver entry point cuTensorMapEncodeTiled (no link-time dependency on libcuda).
+int frb_record_tensor_map(const float* records, int n, CUtensorMap* out);
 
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 void frb_note_launches(int k);
@@ -119,6 +124,16 @@ __device__ __forceinline__ void frb_tma_load_1d(void* smem_dst, const void* gmem
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             frb_smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(frb_smem_u32(bar))
+        : "memory");
+}
+
+// ---- TMA tile::gather4: four rows of a 2D tensor map (row = one record) by row index (SASS: UTMALDG.2D.GATHER4) ----
+// dst 128-byte aligned; the tensor map's box is {row floats, 1}; completes 4 x row bytes on the mbarrier.
+__device__ __forceinline__ void frb_tma_gather4(void* smem_dst, const CUtensorMap* map, uint4 rows, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(frb_smem_u32(smem_dst)),
+        "l"(map), "r"(0), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(frb_smem_u32(bar))
         : "memory");
 }
 

@@ -5,6 +5,8 @@
 // The stage functions it sequences are the ones declared in include/fresnel_b200.h.
 #include "frb_common.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -51,6 +53,17 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // tile lists by counting + bitmap ranking (tile_lists.cu) when the rank bitmap and the tile counters fit an SM
 bool frb_use_tile_lists(int n, int tiles) {
     return n > 0 && n <= frb_tile_lists_max_gaussians() && tiles <= frb_tile_lists_max_tiles();
+}
+
+// The compositor kernels of the whole-pass calls fetch the records of a tile's list by TMA tile::gather4 from the
+// unsorted record array (frb_composite_fwd_gather / _bwd_gather) instead of reading a sorted copy: no 48-byte-per-
+// instance gather pass, no sorted_records buffer (it was 480 MB of the 560 MB worst-case arena at config 2).
+// Measured on one box: 2579 frames/s against 2494 with the sorted copy (frb_tile_rank_gather 29 -> 19 us, the
+// backward compositor 188 -> 198 us: its two lane-parallel record reads per 32-entry block conflict 16-way on the
+// 64-byte rows the gather needs).  FRB_GATHER=0 selects the sorted copy (A/B).
+bool frb_gather_mode() {
+    static const bool on = !(getenv("FRB_GATHER") && atoi(getenv("FRB_GATHER")) == 0);
+    return on;
 }
 
 struct Carver {
@@ -102,10 +115,11 @@ extern "C" int frb_tile_layout(int n, int n_views, int width, int height, int m_
     L->state_T = p.take(4 * hw);
     L->state_n = p.take(4 * hw);
     L->sorted_gids = p.take(4 * m);
-    L->sorted_records = p.take(48 * (m + 1));
+    // the sorted record copy exists only on the key-sort path and with FRB_GATHER=0
+    L->sorted_records = p.take((frb_gather_mode() && frb_use_tile_lists(n, (int)tiles)) ? 0 : 48 * (m + 1));
+    L->records = p.take(48 * ((size_t)n + 1));      // persist: the backward pass gathers from it too
     L->persist_bytes = p.off;
     Carver s;
-    L->records = s.take(48 * (size_t)n);
     L->depth_bits = s.take(4 * (size_t)n);
     L->touched = s.take(4 * (size_t)n);
     L->order = s.take(4 * (size_t)n);
@@ -143,7 +157,7 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
     const int tiles = n_views * frb_div_up(width, FRB_TILE) * frb_div_up(height, FRB_TILE);
     int tile_bits = 1;
     while ((1 << tile_bits) < tiles) ++tile_bits;
-    float* records = (float*)(S + L.records);
+    float* records = (float*)(P + L.records);
     uint32_t* depth_bits = (uint32_t*)(S + L.depth_bits);
     uint32_t* touched = (uint32_t*)(S + L.touched);
     uint32_t* order = (uint32_t*)(S + L.order);
@@ -180,7 +194,7 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
                                 stream));
         FRB_STAGE("frb_tile_rank_gather", stream,
                   frb_tile_rank_gather(n, tiles, tile_order, ranges, inst_rank, order, records, nullptr, nullptr, gids,
-                                       sorted_records, nullptr, nullptr, stream));
+                                       frb_gather_mode() ? nullptr : sorted_records, nullptr, nullptr, stream));
     } else if (n > 0 && m_capacity > 0) {
         FRB_STAGE("frb_depth_order", stream, frb_depth_order(n, depth_bits, order, S + L.depth_ws, stream));
         if (tile_bits <= 16) {
@@ -205,6 +219,13 @@ extern "C" int frb_tile_render_fwd(int n, int n_views, const float* positions, c
         FRB_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)tiles, (cudaStream_t)stream));
         FRB_STAGE("frb_tile_schedule", stream, frb_tile_schedule(tiles, ranges, tile_order, stream));
     }
+    if (frb_gather_mode() && n > 0 && m_capacity > 0 && frb_use_tile_lists(n, tiles)) {
+        FRB_STAGE("frb_composite_fwd", stream,
+                  frb_composite_fwd_gather(n_views, width, height, tile_order, ranges, records, n, gids, background_host,
+                                           t_eps, FRB_ALPHA_MAX, image, depth, alpha, (float*)(P + L.state_T),
+                                           (int32_t*)(P + L.state_n), stream));
+        return 0;
+    }
     FRB_STAGE("frb_composite_fwd", stream,
               frb_composite_fwd_sched(n_views, width, height, tile_order, ranges, sorted_records, nullptr, 0.0f,
                                       background_host, t_eps, image, depth, alpha, (float*)(P + L.state_T),
@@ -225,6 +246,15 @@ extern "C" int frb_tile_render_bwd(int n, int n_views, const float* positions, c
     if (!persist || !grad2d) return FRB_E_INVALID;
     const char* P = (const char*)persist;
     FRB_CUDA_OK(cudaMemsetAsync(grad2d, 0, sizeof(float) * FRB_GRAD_FLOATS * (size_t)n, (cudaStream_t)stream));
+    const int tiles_b = n_views * frb_div_up(width, FRB_TILE) * frb_div_up(height, FRB_TILE);
+    if (frb_gather_mode() && n > 0 && m_capacity > 0 && frb_use_tile_lists(n, tiles_b)) {
+        FRB_STAGE("frb_composite_bwd", stream,
+                  frb_composite_bwd_gather(n_views, width, height, (const int32_t*)(P + L.tile_order),
+                                           (const int32_t*)(P + L.ranges), (const float*)(P + L.records), n,
+                                           (const uint32_t*)(P + L.sorted_gids), background_host, FRB_ALPHA_MAX,
+                                           (const float*)(P + L.state_T), (const int32_t*)(P + L.state_n), g_image,
+                                           g_depth, g_alpha, grad2d, stream));
+    } else
     FRB_STAGE("frb_composite_bwd", stream,
               frb_composite_bwd_sched(n_views, width, height, (const int32_t*)(P + L.tile_order),
                                       (const int32_t*)(P + L.ranges), (const float*)(P + L.sorted_records),

@@ -8,6 +8,30 @@
 
 #include <atomic>
 static std::atomic<unsigned long long> g_launches{0};
+int frb_record_tensor_map(const float* records, int n, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (!fn) return FRB_E_INVALID;
+        encode = (EncodeFn)fn;
+    }
+    if (!records || n < 1 || frb_misaligned16(records)) return FRB_E_INVALID;
+    cuuint64_t gdim[2] = {FRB_RECORD_FLOATS, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {FRB_RECORD_FLOATS * sizeof(float)};
+    cuuint32_t box[2] = {16, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)records, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : FRB_E_INVALID;
+}
+
 void frb_note_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
 extern "C" unsigned long long frb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -405,6 +405,7 @@ tile_rank_gather_kernel(int words, const int* __restrict__ tile_order, const int
             }
         }
     }
+    if (!sorted_records) return;     // id lists only: the compositor fetches the records itself (TMA gather4)
     __syncthreads();        // the ids written above are read back by other threads of this CTA
     // 3 threads per instance, one float4 each: the tile's records land contiguous and coalesced; four rounds are
     // issued together so that four id -> record load chains overlap (a 3,000-entry tile is 18 rounds, not 70)
@@ -591,8 +592,9 @@ extern "C" int frb_tile_rank_gather(int n, int n_tiles, const int32_t* tile_orde
     if (n < 0 || n_tiles < 0) return FRB_E_INVALID;
     if (n > MAX_RANKED) return FRB_E_TOO_LARGE;
     if (n == 0 || n_tiles == 0) return 0;
-    if (!ranges || !inst_rank || !order || !records || !sorted_gids || !sorted_records) return FRB_E_INVALID;
-    if ((phases == nullptr) != (sorted_phases == nullptr)) return FRB_E_INVALID;
+    if (!ranges || !inst_rank || !order || !sorted_gids) return FRB_E_INVALID;
+    if (sorted_records && !records) return FRB_E_INVALID;        // sorted_records NULL: id lists only
+    if ((phases == nullptr) != (sorted_phases == nullptr) || (sorted_phases && !sorted_records)) return FRB_E_INVALID;
     if (sorted_keys && !depth_bits) return FRB_E_INVALID;
     if (frb_misaligned16(records) || frb_misaligned16(sorted_records)) return FRB_E_INVALID;
     const int words = bitmap_words(n);

@@ -24,7 +24,8 @@ from .camera import camera_vector
 TILE = 16
 RECORD_FLOATS = 12
 DEFAULT_T_EPS = 2.0 ** -20   # pixel stops once transmittance < t_eps; 0 = never (exact mode)
-INSTANCE_BYTES = 2 * 12 + 48 + 32            # keys+ids (two copies), sorted record, side record
+INSTANCE_BYTES = 2 * 12 + 48 + 32            # staged path: keys+ids (two copies), sorted record, side record
+FUSED_INSTANCE_BYTES = 8                     # whole-pass path: depth rank + Gaussian id (records are gathered by TMA)
 SYNC_FREE_BUDGET_BYTES = 4 << 30             # worst-case instance buffers above this use the host-sync path
 
 
@@ -519,9 +520,11 @@ def render_views(positions, scales, rotations, colors, opacities, cameras: Seque
     cfg = (cam_vecs, B, int(width), int(height), np.asarray(background, np.float32), float(max_radius),
            float(t_eps), float(phase_amplitude), int(mode))
     n_total = B * N
+    n_tiles = B * (-(-int(width) // TILE)) * (-(-int(height) // TILE))
+    lists = (n_total <= _lib.lib().frb_tile_lists_max_gaussians() and n_tiles <= _lib.lib().frb_tile_lists_max_tiles())
     fused = (FUSED_CALLS and _TIMER is None and t["phases"] is None and n_total > 0 and mode == 0 and
-             worst_case_instances(n_total, B, int(width), int(height), float(max_radius)) * INSTANCE_BYTES
-             <= SYNC_FREE_BUDGET_BYTES)
+             worst_case_instances(n_total, B, int(width), int(height), float(max_radius))
+             * (FUSED_INSTANCE_BYTES if lists else INSTANCE_BYTES) <= SYNC_FREE_BUDGET_BYTES)
     with torch.cuda.device(t["positions"].device):
         if fused:
             return _TileRenderFusedFn.apply(t["positions"], t["scales"], t["rotations"], t["colors"],

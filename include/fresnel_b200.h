@@ -220,6 +220,20 @@ int frb_tile_rank_gather(int n, int n_tiles, const int32_t* tile_order, const in
                          const uint32_t* depth_bits, const float* phases, uint32_t* sorted_gids,
                          float* sorted_records, float* sorted_phases, uint64_t* sorted_keys, void* stream);
 
+/* frb_composite_fwd_cap reading the tile lists as Gaussian ids: records is the UNSORTED array written by
+ * frb_project_fwd (n_records rows of 12 floats), sorted_gids the per-tile lists; the records are fetched by TMA
+ * tile::gather4 (no sorted copy of the records is needed).  No phase blending. */
+int frb_composite_fwd_gather(int n_views, int width, int height, const int32_t* tile_order, const int32_t* ranges,
+                             const float* records, int n_records, const uint32_t* sorted_gids,
+                             const float* background_host, float t_eps, float alpha_max, float* image, float* depth,
+                             float* alpha, float* state_T, int32_t* state_n, void* stream);
+
+int frb_composite_bwd_gather(int n_views, int width, int height, const int32_t* tile_order, const int32_t* ranges,
+                             const float* records, int n_records, const uint32_t* sorted_gids,
+                             const float* background_host, float alpha_max, const float* state_T,
+                             const int32_t* state_n, const float* g_image, const float* g_depth, const float* g_alpha,
+                             float* grad2d, void* stream);
+
 /* ---- whole-pass entry points (capacity mode, no host synchronisation) ------------------ */
 /* One call enqueues projection, binning and compositing of TileBasedRenderer.forward (DR:489-686)
  * for n_views views; buffers are carved from two arenas laid out by frb_tile_layout: `persist`
@@ -235,8 +249,8 @@ int frb_bin_sort_dev(int n, int n_views, int width, int height, const float* rec
                      void* scan_ws, void* sort_ws, void* stream);
 
 typedef struct FrbTileLayout {
-    size_t ranges, tile_order, state_T, state_n, sorted_gids, sorted_records, persist_bytes;
-    size_t records, depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,
+    size_t ranges, tile_order, state_T, state_n, sorted_gids, sorted_records, records, persist_bytes;
+    size_t depth_bits, touched, order, offsets, depth_ws, scan_ws, keys, keys_tmp, vals_tmp,
         sort_ws, tile_ws, inst_rank, rank, scratch_bytes;
 } FrbTileLayout;
 int frb_tile_layout(int n, int n_views, int width, int height, int m_capacity, FrbTileLayout* layout);
