@@ -72,10 +72,12 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     }
     __syncthreads();
     // producer: thread 0 (bulk copy) or lanes 0..15 of warp 0 (gather: lane q fetches records 4q..4q+3 of the batch)
-    uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);           // gather: ids of my group in the next batch to be issued
+    // (gather: the producer of batch b is warp b % 8, lanes 0..15, so that the work does not always delay the same warp)
+    const int lane_f = threadIdx.x & 31, warp_f = threadIdx.x >> 5;
+    uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);           // gather: ids of my group in the next batch I issue
     auto load_ids = [&](int b) {
-        if (GATHER && threadIdx.x < BATCH / 4 && b < n_batches) {
-            const int i0 = b * BATCH + 4 * (int)threadIdx.x, last = count - 1;
+        if (GATHER && warp_f == (b & 7) && lane_f < BATCH / 4 && b < n_batches) {
+            const int i0 = b * BATCH + 4 * lane_f, last = count - 1;
             const uint32_t* g = sorted_gids + range.x;
             pre_g = make_uint4(g[min(i0, last)], g[min(i0 + 1, last)], g[min(i0 + 2, last)], g[min(i0 + 3, last)]);
         }
@@ -89,12 +91,12 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 frb_tma_load_1d(stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
                                 &full_bar[s]);
             }
-        } else if (threadIdx.x < 32) {
+        } else if (warp_f == (b & 7)) {
             const int groups = (cnt + 3) >> 2;
-            if (threadIdx.x == 0) frb_mbar_expect_tx(&full_bar[s], groups * 4 * RS * 16);
+            if (lane_f == 0) frb_mbar_expect_tx(&full_bar[s], groups * 4 * RS * 16);
             __syncwarp();
-            if ((int)threadIdx.x < groups)
-                frb_tma_gather4(stage[s].rec + 4 * RS * threadIdx.x, &record_map, pre_g, &full_bar[s]);
+            if (lane_f < groups)
+                frb_tma_gather4(stage[s].rec + 4 * RS * lane_f, &record_map, pre_g, &full_bar[s]);
         }
     };
     for (int b = 0; b < STAGES && b < n_batches; ++b) {
@@ -292,11 +294,13 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 
     // batches are visited last to first; ring slot (visit % STAGES) holds visit.  Producer: thread 0 (bulk copy of the
     // sorted records) or lanes 0..15 of warp 0 (gather4 by Gaussian id, ids prefetched one visit ahead).
+    // (the producer of visit v is warp v % 8, so that its few dozen instructions per batch do not always delay the
+    // same warp at the batch barrier)
     uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);
     auto load_ids = [&](int visit) {
-        if (GATHER && threadIdx.x < BATCH / 4 && visit < n_batches) {
+        if (GATHER && warp == (visit & (BWD_WARPS - 1)) && lane < BATCH / 4 && visit < n_batches) {
             const int b = n_batches - 1 - visit;
-            const int i0 = b * BATCH + 4 * (int)threadIdx.x, last = count - 1;
+            const int i0 = b * BATCH + 4 * lane, last = count - 1;
             const uint32_t* g = sorted_gids + range.x;
             pre_g = make_uint4(g[min(i0, last)], g[min(i0 + 1, last)], g[min(i0 + 2, last)], g[min(i0 + 3, last)]);
         }
@@ -311,12 +315,12 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 frb_tma_load_1d(sm.stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
                                 &sm.full_bar[s]);
             }
-        } else if (threadIdx.x < 32) {
+        } else if (warp == (visit & (BWD_WARPS - 1))) {
             const int groups = (cnt + 3) >> 2;
-            if (threadIdx.x == 0) frb_mbar_expect_tx(&sm.full_bar[s], groups * 4 * RS * 16);
+            if (lane == 0) frb_mbar_expect_tx(&sm.full_bar[s], groups * 4 * RS * 16);
             __syncwarp();
-            if ((int)threadIdx.x < groups)
-                frb_tma_gather4(sm.stage[s].rec + 4 * RS * threadIdx.x, &record_map, pre_g, &sm.full_bar[s]);
+            if (lane < groups)
+                frb_tma_gather4(sm.stage[s].rec + 4 * RS * lane, &record_map, pre_g, &sm.full_bar[s]);
         }
     };
     for (int v = 0; v < STAGES && v < n_batches; ++v) {
