@@ -38,7 +38,10 @@ constexpr uint32_t FLAG_AGG = 1u << 30;      // tile count published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;   // inclusive prefix over tiles 0..this published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOK_WINDOW = 8;               // predecessors inspected per look-back round trip
+constexpr int LOOK_WINDOW = 8;               // predecessors inspected per look-back round trip. 32 for the small-tile
+                                             // sort (196 resident tiles at 100k keys) measured SLOWER: depth order 46.9 us
+                                             // vs 42.9 us (profiles/r2_s_bench_lookwindow32.json) - the extra loads per
+                                             // round cost more than the saved round trips
 constexpr int SPIN_LIMIT = 1 << 24;          // a look-back that spins this long reports an error instead of hanging
 
 template <typename KeyT>
