@@ -38,6 +38,11 @@ struct FwdStage {
     float4 rec[BATCH * RS];
 };
 
+// Tried in round 2: two pixels per thread (128 threads, a warp owns an 8x8 block, the pixel-independent part of a
+// record - rectangle words, loop, centre / conic load, dx - paid once for (x, y) and (x, y + 4)).  Bit-identical
+// output and fewer instructions, but a tile then takes twice as long on half the warps and the kernel ends on its
+// longest tiles: 119.5 us against 100.8 us for one frame (profiles/r2_u_*; with six frames in flight, where other
+// frames fill the tail, 2860-2910 against 2855-2860 frames/s).  Kept: one pixel per thread.
 template <bool GATHER>
 __global__ void __launch_bounds__(CTA_THREADS)
 composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
@@ -216,6 +221,9 @@ constexpr int N_GRADS = 10;
 // occupancy 24 -> 36 %, issue slots 69 -> 76 % busy, but the two-halves loop costs 13 % more instructions (161.2 M
 // against 142.4 M: the cross-half shuffles, a second pass over the candidate mask and record loads) - 199 us against
 // 188 us on the same box (profiles/r2_d_*).  The kernel is bound by instructions issued, not by residency.
+// Also tried: the second block-wide barrier of a visit split into bar.arrive by the summing threads / bar.sync before
+// the next visit's first part[] store, so that the cross-warp sum overlaps the next phase 1 - 197.8 us against
+// 194.6 us (profiles/r2_t_*): the barrier stall in the capture is warps whose pixels ended early, not the sum.
 template <bool GATHER>
 struct BwdSmem {
     FwdStage<GATHER> stage[STAGES];                 // first: the gather destinations need 128-byte alignment
