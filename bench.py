@@ -726,6 +726,51 @@ def measure_phase(args, rank, world, dev, steps, flush):
             "gpu_launches": int(launches)}
 
 
+RENDER_BATCH_VIEWS = 4
+
+
+def measure_render_batch(args, rank, world, dev, steps, flush):
+    """The headline render (100k Gaussians @ 512x512, forward + backward) as ``render_batch`` makes it: four clouds of
+    that size with one camera each in ONE pass of the kernels (the call a training step makes,
+    train_gaussian_decoder.py:1209-1223).  The latency-bound stages of the chain - depth order, tile counting, scan -
+    are paid once for the four frames."""
+    import fresnel_b200
+    from fresnel_b200 import _lib
+    L = _lib.lib()
+    B = RENDER_BATCH_VIEWS
+    ren = fresnel_b200.TileBasedRenderer(RES, RES)
+    cam = fresnel_b200.Camera(0.8 * RES, 0.8 * RES, RES / 2, RES / 2, RES, RES)
+    clouds = [synthetic_cloud(N_GAUSS, seed=rank * B + i) for i in range(B)]
+    batch = {k: torch.stack([c[k] for c in clouds]).to(dev).requires_grad_(True) for k in clouds[0]}
+    ups = [upstream(1 + rank * B + i) for i in range(B)]
+    gi = torch.stack([u[0] for u in ups]).to(dev)
+    gd = torch.stack([u[1] for u in ups]).to(dev)
+
+    def step():
+        for v in batch.values():
+            v.grad = None
+        img, dep, _ = ren.render_batch(batch["positions"], batch["scales"], batch["rotations"], batch["colors"],
+                                       batch["opacities"], cam)
+        torch.autograd.backward((img, dep), (gi, gd))
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    _barrier(world)
+    l0 = L.frb_launch_count()
+    ms = _timed_steps(step, steps, flush)
+    launches = L.frb_launch_count() - l0
+    (tot_ms,) = _max_over_ranks([sum(ms)], dev, world)
+    return {"metric": "render fwd+bwd frames/sec (100k Gaussians, 512x512), four frames per call",
+            "value": world * B * steps / (tot_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": tot_ms / steps, "frames_per_step": B, "higher_is_better": True,
+            "scaling": "weak", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"TileBasedRenderer.render_batch: {B} clouds of {N_GAUSS} Gaussians, {RES}x{RES}, "
+                                   "one pass of the kernels, forward + backward, inputs resident",
+                       "l2": "flushed between steps (256 MiB fill), per-step CUDA events summed"},
+            "gpu_launches": int(launches)}
+
+
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
@@ -992,6 +1037,8 @@ def main():
         workloads["train"] = measure_train(args, rank, world, dev, False, args.steps, flush)
         torch.cuda.empty_cache()
         workloads["phase"] = measure_phase(args, rank, world, dev, w_steps, flush)
+        torch.cuda.empty_cache()
+        workloads["render_batch"] = measure_render_batch(args, rank, world, dev, w_steps, flush)
         torch.cuda.empty_cache()
         workloads["multiview"] = measure_multiview(args, rank, world, dev, "peer", w_steps, flush, stages=True)
         if world > 1:

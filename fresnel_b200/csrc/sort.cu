@@ -287,6 +287,8 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
 
 // Small sorts (the depth order of one view's Gaussians) use 512-key tiles: a 100k-key pass is a chain of L2 round
 // trips, not bandwidth, and four times as many, four times shorter tiles put every SM to work on it.
+// (1024-key tiles instead: 42.0 / 43.3 us against 43.2 / 46.5 us for the depth order of 100k keys on one box,
+// profiles/r2_v_sort_tile*.json - no difference: a pass is launch + a fixed chain of dependent L2 round trips.)
 constexpr int SORT_IPT_SMALL = 2;
 constexpr int SORT_TILE_SMALL = SORT_THREADS * SORT_IPT_SMALL;
 constexpr int SORT_SMALL_MAX = 1 << 19;                    // below this many keys: small tiles

@@ -1,9 +1,11 @@
 #!/bin/bash
-# A/B of an environment toggle on one box: bash tools/ab_env.sh TAG VAR  (runs VAR=1,0,1,0), then the GPU tests.
-TAG=${1:-x}; VAR=${2:-FRB_OVERLAP}
+# A/B of an environment toggle on one box: bash tools/ab_env.sh TAG VAR [A B]  (the GPU tests, then VAR=A,B,A,B;
+# A B default to 1 0).  With A given the GPU tests run under VAR=A.
+TAG=${1:-x}; VAR=${2:-FRB_OVERLAP}; A=${3:-1}; B=${4:-0}
+export $VAR=$A
 O=gpurun_out; mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/test_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 $O/test_$TAG.log
-for v in 1 0 1 0; do
+for v in $A $B $A $B; do
   env $VAR=$v python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-workloads > $O/ab_${TAG}_$v.json 2>$O/ab_${TAG}.err
   python - <<PY
 import json
