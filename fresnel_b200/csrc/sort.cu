@@ -38,10 +38,13 @@ constexpr uint32_t FLAG_AGG = 1u << 30;      // tile count published
 constexpr uint32_t FLAG_PREFIX = 2u << 30;   // inclusive prefix over tiles 0..this published
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOK_WINDOW = 8;               // predecessors inspected per look-back round trip. 32 for the small-tile
-                                             // sort (196 resident tiles at 100k keys) measured SLOWER: depth order 46.9 us
-                                             // vs 42.9 us (profiles/r2_s_bench_lookwindow32.json) - the extra loads per
-                                             // round cost more than the saved round trips
+constexpr int LOOK_WINDOW = 8;               // predecessors inspected per look-back round trip.  Wider windows for the
+                                             // small-tile sort (196 resident tiles at 100k keys) measured SLOWER on one
+                                             // box: depth order 41.7 us (8), 43.6 us (16), 46.5 us (32)
+                                             // (profiles/r2_w_look_window*.json).  tools/probes/sort_trace.cu stamps the
+                                             // phases of every tile (profiles/r2_y_sort_trace_100k.txt): a pass is ~1 us
+                                             // of load + rank, ~3 us of look-back (5 rounds on average, 9 at most, of
+                                             // ~0.37 us), ~1.3 us of scatter and ~1.5 us of kernel boundary
 constexpr int SPIN_LIMIT = 1 << 24;          // a look-back that spins this long reports an error instead of hanging
 
 template <typename KeyT>
@@ -119,6 +122,19 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // (tile, warp, round, lane) order is input order.  GEN_VALS: values are the input indices.
 // RDX digits per pass (256 or 512); thread t owns the digits [t * DPT, (t + 1) * DPT), DPT = RDX / 256.
 // XFORM: the keys read are raw depth bits and are transformed by key_xform (first pass of frb_depth_order_range).
+// FRB_SORT_TRACE (tools/probes/sort_trace.cu only): thread 0 of every tile stamps %globaltimer at the phase boundaries.
+#ifdef FRB_SORT_TRACE
+__device__ unsigned long long frb_sort_trace[4][1024][8];
+__device__ __forceinline__ unsigned long long frb_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FRB_TRACE(slot) do { if (threadIdx.x == 0 && tile_tr < 1024) frb_sort_trace[(shift >> 3) & 3][tile_tr][slot] = frb_gtime(); } while (0)
+#else
+#define FRB_TRACE(slot) do { } while (0)
+#endif
+
 template <typename KeyT, bool GEN_VALS, int IPT, int RDX, bool XFORM>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
@@ -127,6 +143,11 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
                       const uint32_t* __restrict__ hist_pass, uint32_t* __restrict__ status,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag,
                       uint32_t* __restrict__ rank_out, const __grid_constant__ KeyRange kr) {
+#ifdef FRB_SORT_TRACE
+    const unsigned long long t_entry = frb_gtime();
+    uint32_t tile_tr = 0xffffffffu;
+    int rounds_tr = 0;
+#endif
     frb_pdl_prologue();
     constexpr int DPT = RDX / SORT_THREADS;
     __shared__ uint32_t cnt[SORT_WARPS][RDX];
@@ -144,6 +165,11 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     __syncthreads();
     const uint32_t tile = tile_s;
     if ((long long)tile * (SORT_THREADS * IPT) >= m) return;           // past the end: nobody looks back at this tile
+#ifdef FRB_SORT_TRACE
+    tile_tr = tile;
+    if (threadIdx.x == 0 && tile_tr < 1024) frb_sort_trace[(shift >> 3) & 3][tile_tr][0] = t_entry;
+#endif
+    FRB_TRACE(1);       // ticket drawn, counters cleared
 
     long long base = (long long)tile * (SORT_THREADS * IPT) + warp * (32 * IPT);
     KeyT key[IPT];
@@ -155,6 +181,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         key[r] = (i < m) ? keys_in[i] : (KeyT)0;
         if (XFORM) key[r] = key_xform<KeyT>(key[r], kr);
     }
+    FRB_TRACE(2);       // keys requested (loads in flight)
     // the match.any operations are independent: issue them back to back, then update the counters
     uint32_t peers[IPT];
 #pragma unroll
@@ -179,6 +206,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         __syncwarp();
     }
     __syncthreads();
+    FRB_TRACE(3);       // ranked within the warps
 
     // thread t owns DPT consecutive digits: per-warp counts -> warp-exclusive offsets; tile count -> look-back
     uint32_t excl[DPT], run[DPT], h[DPT];
@@ -206,6 +234,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         // Look back LOOK_WINDOW predecessors per round trip: the loads are independent, so a walk over k
         // published counts costs k / LOOK_WINDOW L2 latencies instead of k.  The DPT digits of a thread walk
         // together (all their loads of a round are issued before the first is used).
+        FRB_TRACE(4);   // count published
         long long look[DPT];
         bool done[DPT];
         int spins = 0;
@@ -213,6 +242,9 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         for (int q = 0; q < DPT; ++q) { look[q] = (long long)tile - 1; done[q] = false; }
         bool all_done = false;
         while (!all_done) {
+#ifdef FRB_SORT_TRACE
+            ++rounds_tr;
+#endif
             uint32_t v[DPT][LOOK_WINDOW];
 #pragma unroll
             for (int q = 0; q < DPT; ++q) {
@@ -246,6 +278,7 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
         for (int q = 0; q < DPT; ++q)
             st_volatile_u32(status + (size_t)tile * RDX + threadIdx.x * DPT + q, (excl[q] + run[q]) | FLAG_PREFIX);
     }
+    FRB_TRACE(5);       // look-back done, prefix published
     // exclusive scan of the global digit histogram (RDX values, DPT consecutive ones per thread)
     uint32_t tsum = 0;
 #pragma unroll
@@ -282,6 +315,10 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
             if (rank_out) rank_out[val] = pos;            // last pass of frb_depth_order: the inverse permutation
         }
     }
+    FRB_TRACE(6);       // scattered
+#ifdef FRB_SORT_TRACE
+    if (threadIdx.x == 0 && tile_tr < 1024) frb_sort_trace[(shift >> 3) & 3][tile_tr][7] = (unsigned long long)rounds_tr;
+#endif
     }   // while: next tile
 }
 
