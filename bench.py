@@ -1030,6 +1030,7 @@ def main():
 
     # the workloads north_star asks scaling numbers for, measured in this same invocation at this same N
     workloads = {}
+    pipe_cluster_sort = pipe_full.cluster_sort
     if not args.no_workloads:
         del pipe, pipe_full, pipe_lean, session
         torch.cuda.empty_cache()
@@ -1097,6 +1098,9 @@ def main():
                        "parallelism": f"views sharded over {world} rank(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": tot_pipe_ms / args.steps, "pipeline_depth": args.pipeline_depth,
+                    "depth_sort": ("one kernel on a 16-CTA cluster, keys in distributed shared memory "
+                                   "(frb_depth_sort_in_cluster; leaves 132 SMs to the other frames in flight)"
+                                   if pipe_cluster_sort else "one-sweep chain"),
                     "value_no_flush": world * args.steps / (tot_pipe_nf_ms * 1e-3),
                     "serial": {"value": e2e_serial, "ms_per_step": tot_e2e_ms / args.steps},
                     "gradients_only": {"value": world * args.steps / (tot_lean_ms * 1e-3), "unit": UNIT,

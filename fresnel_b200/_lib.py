@@ -31,6 +31,7 @@ _SIGNATURES = {
     "frb_depth_order": (c_int, [c_int, P, P, P, P]),
     "frb_depth_order_rank": (c_int, [c_int, P, P, P, P, P]),
     "frb_depth_order_range": (c_int, [c_int, P, c_float, c_float, P, P, P, P]),
+    "frb_depth_sort_in_cluster": (c_int, [c_int]),
     "frb_scan_workspace_bytes": (c_size_t, [c_int]),
     "frb_tile_offsets": (c_int, [c_int, P, P, P, P, P]),
     "frb_bin_emit": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),

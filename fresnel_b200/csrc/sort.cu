@@ -18,7 +18,10 @@
 // work with coalesced loads and shared-memory digit counters.
 #include "frb_common.cuh"
 
+#include <cooperative_groups.h>
 #include <string.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -657,6 +660,280 @@ gather_records_kernel(int m, const uint32_t* __restrict__ m_dev, const uint32_t*
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster-resident depth sort (sm_100a: thread-block clusters + distributed shared memory).
+//
+// The one-sweep chain above spends a 100k-key pass on round trips, not data: ~1 us of load + rank inside ~7.5 us of
+// look-back rounds through L2, scatter and kernel boundary (profiles/r2_y_sort_trace_100k.txt), times four passes, plus
+// a memset and a histogram kernel.  A view's depth keys fit on chip: ONE cluster of 16 CTAs holds all (key, index)
+// pairs in its shared memory (two buffers of 8 bytes per element, <= 12.4k elements per CTA), and all passes run inside
+// ONE kernel.  CTA c owns positions [c S, (c + 1) S) of the array.  Per 8-bit pass:
+//   1. rank: warp w walks its contiguous chunk in order, 32 elements per round (match.any + per-warp digit counters,
+//      as in the one-sweep kernel), so (CTA, warp, round, lane) order is array order - the pass is stable;
+//   2. thread d scans digit d over the 32 warps and stores the CTA's count of d into EVERY CTA's table (st.shared::cluster);
+//   3. barrier.cluster; thread d adds up the column (all CTAs' counts of d), the counts of the CTAs before this one,
+//      and the 256 column totals are scanned: base[d] = position of this CTA's first element with digit d;
+//   4. local scatter into a staging buffer in (digit, array order) - plain shared-memory stores; then thread i sends
+//      staged element i to position p = base[d] + (i - first staged index of d): CTA p / S, slot p % S of that CTA's
+//      third buffer (st.shared::cluster.u64).  Consecutive threads hold consecutive positions of a digit run, so the
+//      remote stores of a warp are a few contiguous spans.  (Scattering straight from the rank order - 32 unrelated
+//      8-byte remote stores per warp instruction - was packet-bound: 14 us per pass, profiles/r2_z_cluster_sort_v1_*.)
+//   5. barrier.cluster; rotate the three buffers.
+// No global memory between the load of the depth bits and the store of order / rank, no look-back, no histogram
+// kernel, no workspace.  Same result bit for bit (a stable LSD sort of the same keys).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CS_THREADS = 1024;
+constexpr int CS_WARPS = CS_THREADS / 32;
+constexpr int CS_MAX_CTAS = 16;
+constexpr int CS_FIXED_SMEM = CS_MAX_CTAS * 256 * 4 + 2 * 256 * 4 + 2 * CS_WARPS * 4 + CS_WARPS * 256 * 2;
+constexpr int CS_MAX_SMEM = 227 * 1024;
+constexpr int CS_MAX_W = (CS_MAX_SMEM - CS_FIXED_SMEM) / 24 / 32;      // elements per warp: 256 -> 8192 per CTA
+
+inline size_t cluster_sort_smem(int W) { return (size_t)24 * 32 * W + CS_FIXED_SMEM; }
+
+#ifdef FRB_SORT_TRACE
+__device__ unsigned long long frb_cluster_trace[CS_MAX_CTAS][6][10];     // [CTA][0 = load, 1.. = pass, 5 = store][stamp]
+#define FRB_CTRACE(row, slot) do { if (threadIdx.x == 0) frb_cluster_trace[me][row][slot] = frb_gtime(); } while (0)
+#else
+#define FRB_CTRACE(row, slot) do { } while (0)
+#endif
+
+template <int IPT>      // rounds of 32 elements per warp: IPT >= ceil(W / 32)
+__global__ void __launch_bounds__(CS_THREADS, 1)
+cluster_sort_kernel(int n, const uint32_t* __restrict__ depth_bits, const __grid_constant__ KeyRange kr, int n_passes,
+                    uint32_t last_mask, int W, uint32_t div_magic, uint32_t* __restrict__ order,
+                    uint32_t* __restrict__ rank_out, uint32_t* __restrict__ error_word) {
+    frb_pdl_prologue();
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank(), n_ctas = cluster.num_blocks();
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    const int S = 32 * W;
+    uint64_t* buf0 = reinterpret_cast<uint64_t*>(cs_smem);
+    uint64_t* buf1 = buf0 + S;
+    uint64_t* buf2 = buf1 + S;
+    uint32_t* all_tot = reinterpret_cast<uint32_t*>(buf2 + S);      // [CS_MAX_CTAS][256], row c written by CTA c
+    uint32_t* base = all_tot + CS_MAX_CTAS * 256;                   // [256] array position of my first element of d
+    uint32_t* lstart = base + 256;                                  // [256] staged index of my first element of d
+    uint32_t* wsum = lstart + 256;                                  // [2][CS_WARPS]
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(wsum + 2 * CS_WARPS);   // [CS_WARPS][256]: a chunk is < 2^16 elements
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const long long g0 = (long long)me * S;
+
+    FRB_CTRACE(0, 0);
+    for (int j = threadIdx.x; j < S; j += CS_THREADS) {
+        const long long g = g0 + j;
+        if (g < n) buf0[j] = ((uint64_t)key_xform<uint32_t>(depth_bits[g], kr) << 32) | (uint32_t)g;
+    }
+    if (me == 0 && threadIdx.x == 0 && error_word) *error_word = 0;     // what the one-sweep path's memset leaves there
+    FRB_CTRACE(0, 1);
+    cluster.sync();         // every CTA of the cluster is running (its shared memory may be written) and loaded
+    FRB_CTRACE(0, 2);
+
+    uint64_t *cur = buf0, *stg = buf1, *nxt = buf2;
+    const int my_count = (int)max(0ll, min((long long)S, (long long)n - g0));
+    const int wbase = warp * W;
+    const int w_valid = (int)max(0ll, min((long long)W, (long long)n - g0 - wbase));     // elements of my warp's chunk
+    for (int p = 0; p < n_passes; ++p) {
+        const int shift = 32 + 8 * p;
+        const uint32_t mask = (p == n_passes - 1) ? last_mask : 255u;
+        FRB_CTRACE(1 + p, 0);
+        for (int i = threadIdx.x; i < CS_WARPS * 256 / 2; i += CS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
+        __syncthreads();
+        // 1. rank inside the warp's chunk
+        uint32_t rnk[IPT];
+        uint16_t* my_cnt = cnt + warp * 256;
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) {
+            const int j = r * 32 + lane;
+            const bool valid = j < w_valid;
+            const uint32_t d = valid ? ((uint32_t)(cur[wbase + j] >> shift) & mask) : 256u;
+            // lanes holding my digit, from nine ballots: MATCH.ANY iterates over the distinct values of the warp, and
+            // with 32 different digits per round the ranking took 6.5 us of a pass (1.3 us in the 3-bit last pass)
+            uint32_t peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = my_cnt[d];
+                my_cnt[d] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rnk[r] = old + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        FRB_CTRACE(1 + p, 1);       // ranked
+        // 2. digit d over the warps; the CTA's count goes to every CTA's table
+        uint32_t mine = 0;
+        if (threadIdx.x < 256) {
+            const int d = threadIdx.x;
+#pragma unroll 8
+            for (int w = 0; w < CS_WARPS; ++w) {
+                const uint32_t c = cnt[w * 256 + d];
+                cnt[w * 256 + d] = (uint16_t)mine;          // < S <= 12.4k
+                mine += c;
+            }
+            for (unsigned c = 0; c < n_ctas; ++c) cluster.map_shared_rank(all_tot, c)[me * 256 + d] = mine;
+        }
+        FRB_CTRACE(1 + p, 2);       // counts published
+        cluster.sync();     // 3. all counts are here
+        FRB_CTRACE(1 + p, 3);
+        uint32_t col = 0, before = 0, incl = 0, incl_l = 0;
+        if (threadIdx.x < 256) {
+            const int d = threadIdx.x;
+            for (unsigned c = 0; c < n_ctas; ++c) {
+                const uint32_t v = all_tot[c * 256 + d];
+                col += v;
+                if (c < me) before += v;
+            }
+            incl = col;
+            incl_l = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                const uint32_t tl = __shfl_up_sync(0xffffffffu, incl_l, o);
+                if (lane >= o) { incl += t; incl_l += tl; }
+            }
+            if (lane == 31) { wsum[warp] = incl; wsum[CS_WARPS + warp] = incl_l; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t woff = 0, woff_l = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (w < warp) { woff += wsum[w]; woff_l += wsum[CS_WARPS + w]; }
+            base[threadIdx.x] = woff + incl - col + before;
+            lstart[threadIdx.x] = woff_l + incl_l - mine;
+        }
+        __syncthreads();
+        FRB_CTRACE(1 + p, 4);       // bases known
+        // 4a. my elements into the staging buffer, ordered by (digit, array order)
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) {
+            const int j = r * 32 + lane;
+            if (j < w_valid) {
+                const uint64_t e = cur[wbase + j];
+                const uint32_t d = (uint32_t)(e >> shift) & mask;
+                stg[lstart[d] + my_cnt[d] + rnk[r]] = e;
+            }
+        }
+        __syncthreads();
+        FRB_CTRACE(1 + p, 5);       // staged
+        // 4b. staged element i -> its position in the array: the third buffer of the CTA that owns it
+        for (int i = threadIdx.x; i < my_count; i += CS_THREADS) {
+            const uint64_t e = stg[i];
+            const uint32_t d = (uint32_t)(e >> shift) & mask;
+            const uint32_t pos = base[d] + ((uint32_t)i - lstart[d]);
+            uint32_t t = __umulhi(pos, div_magic);          // pos / S (div_magic = ceil(2^32 / S); pos * S < 2^32)
+            uint32_t off = pos - t * (uint32_t)S;
+            if (off >= (uint32_t)S) { off -= (uint32_t)S; ++t; }
+            cluster.map_shared_rank(nxt, t)[off] = e;
+        }
+        FRB_CTRACE(1 + p, 6);       // sent
+        cluster.sync();     // 5. every element is in place
+        FRB_CTRACE(1 + p, 7);
+        uint64_t* tmp = cur; cur = nxt; nxt = stg; stg = tmp;
+    }
+    for (int j = threadIdx.x; j < S; j += CS_THREADS) {
+        const long long g = g0 + j;
+        if (g < n) {
+            const uint32_t id = (uint32_t)cur[j];
+            order[g] = id;
+            if (rank_out) rank_out[id] = (uint32_t)g;
+        }
+    }
+    FRB_CTRACE(5, 0);
+}
+
+// 0: launched.  1: not applicable here (size, device, FRB_CLUSTER_SORT=0) - the caller runs the one-sweep chain.
+template <int IPT>
+int cluster_sort_launch_ipt(int n_ctas, int W, int n, const uint32_t* depth_bits, KeyRange kr, int nbits, uint32_t* order,
+                            uint32_t* rank, uint32_t* error_word, cudaStream_t st) {
+    const size_t smem = cluster_sort_smem(W);
+    int dev = 0;
+    FRB_CUDA_OK(cudaGetDevice(&dev));
+    // per device and instantiation: opt in to the cluster size and the shared memory once, and ask whether such a
+    // cluster can be resident at all
+    static int usable[64][2] = {};          // [device][16 / 8 CTAs]: 0 unknown, 1 yes, -1 no
+    static size_t opted_smem[64] = {};
+    const int slot = n_ctas == 16 ? 0 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(CS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = n_ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    if (dev < 64 && (usable[dev][slot] == 0 || opted_smem[dev] < smem)) {
+        cudaError_t e = cudaFuncSetAttribute(cluster_sort_kernel<IPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(cluster_sort_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_SMEM);
+        int clusters = 0;
+        cfg.numAttrs = 1;
+        cfg.dynamicSmemBytes = CS_MAX_SMEM;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&clusters, cluster_sort_kernel<IPT>, &cfg);
+        cfg.dynamicSmemBytes = smem;
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        usable[dev][slot] = (e == cudaSuccess && clusters >= 1) ? 1 : -1;
+        opted_smem[dev] = CS_MAX_SMEM;
+    }
+    if (dev >= 64 || usable[dev][slot] != 1) return 1;
+    cfg.numAttrs = frb_pdl_enabled() ? 2 : 1;
+    const int n_passes = (nbits + 7) / 8;
+    const uint32_t last_mask = (1u << (nbits - 8 * (n_passes - 1))) - 1u;
+    const uint32_t S = 32u * (uint32_t)W;
+    const uint32_t div_magic = (uint32_t)((0x100000000ull + S - 1) / S);
+    FRB_CUDA_OK(cudaLaunchKernelEx(&cfg, cluster_sort_kernel<IPT>, n, depth_bits, kr, n_passes, last_mask, W, div_magic,
+                                   order, rank, error_word));
+    frb_note_launches(1);
+    FRB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Which of the two sorts frb_depth_order* runs for n <= 131,072 (frb_depth_sort_in_cluster): the cluster keeps 16 SMs
+// busy for ~56 us where the chain keeps all of them waiting on round trips for ~42 us.  One frame at a time the chain is
+// faster (2614 against 2510 frames/s); with several frames in flight on other streams the cluster leaves 132 SMs to
+// their compositor kernels (host-to-host 2893 against 2845 frames/s, profiles/r3_d_cluster_sort_*).  Default: the chain;
+// fresnel_b200.host.HostRenderPipeline captures its graphs with the cluster sort.
+int g_cluster_sort_mode = -1;       // -1: environment FRB_CLUSTER_SORT (unset = off), 0: off, 1: on
+
+int cluster_sort_try(int n, const uint32_t* depth_bits, KeyRange kr, int nbits, uint32_t* order, uint32_t* rank,
+                     uint32_t* error_word, cudaStream_t st) {
+    int mode = __atomic_load_n(&g_cluster_sort_mode, __ATOMIC_RELAXED);
+    if (mode < 0) {
+        const char* sw = getenv("FRB_CLUSTER_SORT");    // read per call: the tests compare both paths in one process
+        mode = (sw && sw[0] == '1') ? 1 : 0;
+    }
+    if (!mode || nbits < 1 || nbits > 32) return 1;
+    for (int n_ctas = CS_MAX_CTAS; n_ctas >= 8; n_ctas /= 2) {
+        const int per_cta = frb_div_up(n, n_ctas);
+        const int W = max(1, frb_div_up(per_cta, 32));
+        if (W > CS_MAX_W) return 1;
+        const int rounds = frb_div_up(W, 32);
+        int rc;
+        if (rounds <= 1) rc = cluster_sort_launch_ipt<1>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        else if (rounds <= 2) rc = cluster_sort_launch_ipt<2>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        else if (rounds <= 4) rc = cluster_sort_launch_ipt<4>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        else if (rounds <= 7) rc = cluster_sort_launch_ipt<7>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        else if (rounds <= 10) rc = cluster_sort_launch_ipt<10>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        else rc = cluster_sort_launch_ipt<13>(n_ctas, W, n, depth_bits, kr, nbits, order, rank, error_word, st);
+        if (rc != 1) return rc;
+    }
+    return 1;
+}
+
 }  // namespace
 
 extern "C" size_t frb_sort_workspace_bytes(int m) {
@@ -694,6 +971,11 @@ extern "C" int frb_radix_sort_pairs_dev(int m_capacity, const uint32_t* m_dev, u
     return sort_pairs(m_capacity, m_dev, keys, vals, keys_tmp, vals_tmp, begin_bit, end_bit, workspace, stream);
 }
 
+extern "C" int frb_depth_sort_in_cluster(int mode) {
+    if (mode < -1 || mode > 1) return FRB_E_INVALID;
+    return __atomic_exchange_n(&g_cluster_sort_mode, mode, __ATOMIC_RELAXED);
+}
+
 extern "C" size_t frb_depth_order_workspace_bytes(int n) {
     if (n < 0) n = 0;
     return 3 * align256(sizeof(uint32_t) * (size_t)n) + align256(sizeof(uint32_t) * sort_ws_words(n, 4, RADIX_MAX));
@@ -716,6 +998,10 @@ extern "C" int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t*
     uint32_t* keys_b = (uint32_t*)(w + a);
     uint32_t* vals_a = (uint32_t*)(w + 2 * a);
     uint32_t* ws = (uint32_t*)(w + 3 * a);
+    {
+        const int rc = cluster_sort_try(n, depth_bits, KeyRange{0u, 0u, 0}, 32, order, rank, ws + WS_ERROR, st);
+        if (rc != 1) return rc;
+    }
     // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
     bool in_b = false;
     int rc = radix_sort_impl<uint32_t, RADIX_BITS>(n, nullptr, depth_bits, nullptr, keys_a, vals_a, keys_b, order, 0, 32, ws, st, &in_b,
@@ -752,7 +1038,8 @@ extern "C" int frb_depth_order_range(int n, const uint32_t* depth_bits, float ne
     uint32_t* ws = (uint32_t*)(w + 3 * a);
     KeyRange kr{lo, hi, 1};
     bool in_b = false;
-    int rc;
+    int rc = cluster_sort_try(n, depth_bits, kr, nbits, order, rank, ws + WS_ERROR, st);
+    if (rc != 1) return rc;
     uint32_t *va = vals_a, *vb = order;
     // Digit width: 8 bits.  Three 9-bit passes for the default [0.01, 100] (27 key bits) were measured against four
     // 8-bit ones: 45-48 us against 41 us at 100k keys - a 512-digit pass costs more (twice the counters to clear and

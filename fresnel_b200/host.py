@@ -165,10 +165,13 @@ class HostRenderPipeline:
     """
 
     def __init__(self, renderer, n_gaussians: int, device: torch.device, depth: int = 2, cuda_graph: bool = True,
-                 outputs=("image", "depth", "grads")):
+                 outputs=("image", "depth", "grads"), cluster_sort=None):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.device, self.depth, self.cuda_graph = device, int(depth), bool(cuda_graph)
+        # the depth order as ONE kernel on a 16-CTA cluster (frb_depth_sort_in_cluster): slower than the multi-kernel
+        # chain for a frame alone, but it leaves 132 SMs to the other frames in flight - on when three or more are
+        self.cluster_sort = (self.depth >= 3) if cluster_sort is None else bool(cluster_sort)
         self.slots = [HostRenderSession(renderer, n_gaussians, device, outputs=outputs) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream(device) for _ in range(self.depth)]
         self.done = [torch.cuda.Event() for _ in range(self.depth)]
@@ -190,15 +193,20 @@ class HostRenderPipeline:
             from . import _lib
             st, sess = self.streams[slot], self.slots[slot]
             st.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(st):                 # warm-up on the slot's stream: allocator, lazy attributes
-                for _ in range(2):
+            previous = _lib.lib().frb_depth_sort_in_cluster(1) if self.cluster_sort else None
+            try:
+                with torch.cuda.stream(st):             # warm-up on the slot's stream: allocator, lazy attributes
+                    for _ in range(2):
+                        sess.step(camera)
+                st.synchronize()
+                g = torch.cuda.CUDAGraph()
+                before = _lib.lib().frb_launch_count()
+                with torch.cuda.graph(g, stream=st):
                     sess.step(camera)
-            st.synchronize()
-            g = torch.cuda.CUDAGraph()
-            before = _lib.lib().frb_launch_count()
-            with torch.cuda.graph(g, stream=st):
-                sess.step(camera)
-            self.kernels_per_step = int(_lib.lib().frb_launch_count() - before)
+                self.kernels_per_step = int(_lib.lib().frb_launch_count() - before)
+            finally:
+                if previous is not None:
+                    _lib.lib().frb_depth_sort_in_cluster(previous)
             if len(self._graphs[slot]) >= 8:
                 self._graphs[slot].clear()
             self._graphs[slot][key] = g

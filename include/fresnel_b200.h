@@ -118,6 +118,14 @@ int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t* order, uin
  * (near < depth < far, DR:541) is exactly frb_depth_order's; culled ones collapse to the two ends in index order. */
 int frb_depth_order_range(int n, const uint32_t* depth_bits, float near_depth, float far_depth, uint32_t* order,
                           uint32_t* rank, void* workspace, void* stream);
+/* For n <= 131,072 the three functions above have a second implementation: ONE kernel on one 16-CTA thread-block
+ * cluster that keeps all (key, index) pairs in distributed shared memory through all passes (no workspace traffic, no
+ * look-back, bit-identical result).  It occupies 16 SMs for longer than the multi-kernel chain occupies all of them:
+ * slower for one frame at a time, faster for the whole device when other streams have work for the remaining SMs.
+ * mode 1 = use it, 0 = do not, -1 = environment variable FRB_CLUSTER_SORT (unset: 0; the initial state).  Returns the
+ * previous mode, FRB_E_INVALID for another value.  Process-wide; it decides which kernels a call enqueues (a captured
+ * CUDA graph keeps what it was captured with). */
+int frb_depth_sort_in_cluster(int mode);
 /* offsets[k] = sum_{j<k} tiles_touched[order[j]] for k = 0..n (order NULL = identity);
  * offsets[n] = number of tile instances M. */
 size_t frb_scan_workspace_bytes(int n);

@@ -163,6 +163,49 @@ def test_depth_order_over_the_camera_range(n, near, far):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 4097, 16384, 100000, 131072, 131073, 250000])
+@pytest.mark.parametrize("near,far", [(0.01, 100.0), (1.0, 1.9), (None, None)])
+def test_cluster_resident_sort_equals_the_one_sweep_chain(n, near, far, monkeypatch):
+    """Depth orders of up to 131,072 Gaussians run as ONE kernel on a 16-CTA cluster (keys in distributed shared
+    memory, csrc/sort.cu cluster_sort_kernel); larger ones, and FRB_CLUSTER_SORT=0, run the one-sweep chain.  Both are
+    stable LSD sorts of the same keys: order and rank must be identical words, and equal numpy's stable argsort.
+    Depths with exact ties, culled values on both sides, a negative zero and an infinity."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n)
+    depth = torch.randn(n, generator=g) * 0.7 + 1.5
+    depth[::7] = depth[0]                                  # ties
+    if n > 40:
+        depth[5], depth[6], depth[7] = -0.0, float("inf"), 1e-9
+    db_host = depth.numpy().view(np.uint32).copy()
+    db = torch.from_numpy(db_host.view(np.int32)).cuda()
+    results = []
+    for switch in ("1", "0"):
+        monkeypatch.setenv("FRB_CLUSTER_SORT", switch)
+        order = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        rank = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(L.frb_depth_order_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+        if near is None:
+            _lib.check(L.frb_depth_order_rank(n, _ptr(db), _ptr(order), _ptr(rank), _ptr(ws), _stream()),
+                       "frb_depth_order_rank")
+        else:
+            _lib.check(L.frb_depth_order_range(n, _ptr(db), float(near), float(far), _ptr(order), _ptr(rank), _ptr(ws),
+                                               _stream()), "frb_depth_order_range")
+        torch.cuda.synchronize()
+        results.append((order.cpu().numpy().view(np.uint32), rank.cpu().numpy().view(np.uint32)))
+    (o1, r1), (o0, r0) = results
+    assert np.array_equal(o1, o0) and np.array_equal(r1, r0)
+    if near is None:
+        keys = db_host
+    else:
+        lo, hi = np.float32(near).view(np.uint32), np.float32(far).view(np.uint32)
+        keys = np.where(db_host.view(np.int32) <= np.int32(lo), np.uint32(0),
+                        np.minimum(db_host, hi).astype(np.uint32) - lo).astype(np.uint32)
+    ref = np.argsort(keys, kind="stable").astype(np.uint32)
+    assert np.array_equal(o1, ref)
+    assert np.array_equal(r1[ref], np.arange(n, dtype=np.uint32))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n_views", [1, 3])
 def test_fused_scan_emit_sort_equals_the_staged_binning(golden, n_views):
     """frb_bin_sort_dev (scan + emit + sort histograms in one kernel, then the tile-bit passes; the whole-pass

@@ -58,6 +58,26 @@ int main(int argc, char** argv) {
         best = std::min(best, ms);
     }
     printf("n=%d the same chain as one graph replay: best %.1f us\n", n, best * 1e3f);
+    {
+        // the cluster-resident sort (what frb_depth_order_range runs for n <= 131,072 unless FRB_CLUSTER_SORT=0)
+        static unsigned long long ct[CS_MAX_CTAS][6][10];
+        cudaMemcpyFromSymbol(ct, frb_cluster_trace, sizeof(ct));
+        unsigned long long c0 = ~0ull;
+        for (int c = 0; c < CS_MAX_CTAS; ++c) if (ct[c][0][0]) c0 = std::min(c0, ct[c][0][0]);
+        if (c0 != ~0ull) {
+            const char* cn[8] = {"pass start", "ranked", "counts sent", "cluster.sync", "bases", "staged", "sent", "cluster.sync"};
+            for (int c = 0; c < CS_MAX_CTAS; c += 5) {
+                printf(" cluster sort, CTA %d (ns after the first CTA started): load begin %lld, loaded %lld, first cluster.sync %lld\n",
+                       c, (long long)(ct[c][0][0] - c0), (long long)(ct[c][0][1] - c0), (long long)(ct[c][0][2] - c0));
+                for (int p = 1; p <= 4; ++p) {
+                    printf("   pass %d:", p - 1);
+                    for (int k = 0; k < 8; ++k) printf(" %s %lld;", cn[k], (long long)(ct[c][p][k] - c0));
+                    printf("\n");
+                }
+                printf("   stored %lld\n", (long long)(ct[c][5][0] - c0));
+            }
+        }
+    }
     static unsigned long long tr[4][1024][8];
     cudaMemcpyFromSymbol(tr, frb_sort_trace, sizeof(tr));
     const int tiles = std::min(1024, (n + 511) / 512);
