@@ -707,10 +707,13 @@ def test_host_render_session_matches_direct_call():
 
 
 @pytest.mark.gpu
-def test_host_render_pipeline_matches_direct_call():
-    """HostRenderPipeline (two graph-replayed HostRenderSession steps in flight on two streams): every step
+@pytest.mark.parametrize("depth", [2, 4])
+def test_host_render_pipeline_matches_direct_call(depth):
+    """HostRenderPipeline (graph-replayed HostRenderSession steps in flight on as many streams): every step
     returns what the module returns for that step's inputs; the slots hold DIFFERENT clouds, so a race
-    between the two in-flight steps (shared scratch, crossed buffers) would show."""
+    between the in-flight steps (shared scratch, crossed buffers) would show.  With three or more in flight the
+    graphs are captured with the depth order on a 16-CTA cluster (frb_depth_sort_in_cluster): same results, and
+    the process-wide switch is back where it was afterwards."""
     from fresnel_b200.host import HostRenderPipeline
     DEV = dev()
     n, R = 6001, 128
@@ -729,7 +732,8 @@ def test_host_render_pipeline_matches_direct_call():
                        return_depth=True)
         torch.autograd.backward((img, dep), (gi.to(DEV), gd.to(DEV)))
         want.append((img.detach().cpu(), dep.detach().cpu(), {k: L[k].grad.cpu() for k in GRAD_NAMES}))
-    pipe = HostRenderPipeline(ren, n, DEV, depth=2)
+    pipe = HostRenderPipeline(ren, n, DEV, depth=depth)
+    assert pipe.cluster_sort == (depth >= 3)
     got = {}
     pending = []
 
@@ -748,6 +752,7 @@ def test_host_render_pipeline_matches_direct_call():
     for item in pending:
         collect(*item)
     assert pipe.kernels_per_step > 0
+    assert _lib.lib().frb_depth_sort_in_cluster(-1) == -1          # restored after every capture
     for i, (img, dep, grads) in enumerate(want):
         assert torch.equal(got[i][0], img) and torch.equal(got[i][1], dep), i
         for k in GRAD_NAMES:
