@@ -340,7 +340,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const float X = gr * bg.x + gg * bg.y + gb * bg.z - ga;
     const float TX = T_final * X;
     float T = T_final;
-    float S = 0.0f;
+    float SX = TX;                      // S + T_final X, S = sum_{j>i} c_j w_j: carried as one sum (one add less per pair)
     float2* my_pair = sm.pair[warp];
 
     for (int visit = 0; visit < n_batches; ++visit) {
@@ -397,8 +397,8 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 if (p.active) {
                     const float Ti = T * p.inv_om;
                     const float c = p.a * Ti;
-                    const float dalpha = Ti * p.w - (S + TX) * p.inv_om;
-                    S = fmaf(c, p.w, S);
+                    const float dalpha = Ti * p.w - SX * p.inv_om;
+                    SX = fmaf(c, p.w, SX);
                     T = Ti;
                     out.x = c;
                     out.y = p.gpass * dalpha;                 // g * gated dL/dalpha (= dL/dopacity part)
