@@ -374,14 +374,18 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             // Two candidates per iteration: everything that does not depend on the running (T, S) is
             // evaluated for both first (independent instruction streams hide the LDS / MUFU latency),
             // then the two short serial tails run back to back.
+            // (addresses as one multiply-add from a per-block / per-lane base, and the candidate index from bfind:
+            // 31 - __clz() compiled to FLO + IADD3 + LOP3 - four instructions less per candidate out of 48)
             struct Pre { float a, inv_om, w, gpass; bool active; };
+            const char* rec_sb = reinterpret_cast<const char*>(rec + RS * (sb * 32));
+            char* pair_lane = reinterpret_cast<char*>(my_pair + lane);
             auto stage_a = [&](int j) {
                 Pre p;
-                const int jb = sb * 32 + j;
-                const float4 r1 = rec[RS * jb + 1], r2 = rec[RS * jb + 2];
+                const float4* rj = reinterpret_cast<const float4*>(rec_sb + j * (RS * 16));
+                const float4 r1 = rj[1], r2 = rj[2];
                 p.active = (j < local_n) &&
                            rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
-                const float4 r0 = rec[RS * jb + 0];
+                const float4 r0 = rj[0];
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                 const float g = frb_ex2(power);
@@ -403,13 +407,13 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                     out.x = c;
                     out.y = p.gpass * dalpha;                 // g * gated dL/dalpha (= dL/dopacity part)
                 }
-                my_pair[j * PAIR_STRIDE + lane] = out;
+                *reinterpret_cast<float2*>(pair_lane + j * (PAIR_STRIDE * 8)) = out;
             };
             while (cand) {
-                const int j0 = 31 - __clz(cand);
+                const int j0 = frb_bfind(cand);
                 cand ^= 1u << j0;
                 if (cand) {
-                    const int j1 = 31 - __clz(cand);
+                    const int j1 = frb_bfind(cand);
                     cand ^= 1u << j1;
                     const Pre p0 = stage_a(j0), p1 = stage_a(j1);
                     stage_b(j0, p0);
