@@ -434,22 +434,33 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const float ux = wbx - r0.x, uy = wby - r0.y;
                 const float2* row = my_pair + lane * PAIR_STRIDE;
                 const float4* pc = sm.pixc[warp];
-                // sums as fp32 pairs (FFMA2: two fmas per issue slot, same bits as fmaf)
-                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg, s_xy = s_rg, s_AB = s_rg;
+                // colour / depth sums as fp32 pairs (FFMA2: two fmas per issue slot, same bits as fmaf).  The geometric
+                // sums over dx = ux + i, dy = uy + k (i, k: the pixel's place in the 8x4 block) are accumulated as the
+                // six moments sum dpow i^a k^b with i and k as IMMEDIATE operands and combined once per Gaussian:
+                // 4 fmas per pixel on average (zero powers drop out at compile time) where forming dx, dy and the
+                // five products took 6 instructions
+                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg;
+                float m00 = 0.f, m10 = 0.f, m01 = 0.f, m20 = 0.f, m11 = 0.f, m02 = 0.f;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) {
                     const float2 cd = row[p];               // (c, g * gated dL/dalpha), formed in phase 1
                     const float4 gpix = pc[p];
-                    const float dx = ux + (float)(p % BWD_FW);
-                    const float dy = uy + (float)(p / BWD_FW);
+                    const int i = p % BWD_FW, k = p / BWD_FW;
                     s_rg = frb_fma2s(cd.x, make_float2(gpix.x, gpix.y), s_rg);
                     s_bd = frb_fma2s(cd.x, make_float2(gpix.z, gpix.w), s_bd);
-                    d_o += cd.y;
-                    const float2 t = frb_mul2s(cd.y, make_float2(dx, dy));      // (dx, dy) * dpow
-                    s_xy = frb_add2(s_xy, t);                                   // sum dx*dpow, sum dy*dpow
-                    s_AB = frb_fma2s(dx, t, s_AB);                              // sum dx^2 dpow, sum dx dy dpow
-                    d_C = fmaf(dy, t.y, d_C);
+                    m00 += cd.y;
+                    if (i) m10 = fmaf(cd.y, (float)i, m10);
+                    if (k) m01 = fmaf(cd.y, (float)k, m01);
+                    if (i) m20 = fmaf(cd.y, (float)(i * i), m20);
+                    if (i && k) m11 = fmaf(cd.y, (float)(i * k), m11);
+                    if (k) m02 = fmaf(cd.y, (float)(k * k), m02);
                 }
+                d_o = m00;
+                // sum dpow dx, dy, dx^2, dx dy, dy^2 from the moments
+                const float2 s_xy = make_float2(fmaf(ux, m00, m10), fmaf(uy, m00, m01));
+                const float2 s_AB = make_float2(fmaf(ux, fmaf(ux, m00, 2.0f * m10), m20),
+                                                fmaf(ux, fmaf(uy, m00, m01), fmaf(uy, m10, m11)));
+                d_C = fmaf(uy, fmaf(uy, m00, 2.0f * m01), m02);
                 d_r = s_rg.x; d_g = s_rg.y; d_b = s_bd.x; d_dep = s_bd.y;
                 // dL/d(power) = gda * o * ln2 (g = 2^power); u, v enter through dx, dy
                 d_A = s_AB.x * oln2; d_B = s_AB.y * oln2; d_C *= oln2;
