@@ -111,6 +111,8 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     load_ids(STAGES);
 
     float T = 1.0f, acc = 0.0f, W1 = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;   // W1 = 1 - acc
+    // (the clamp bound is re-read from the constant bank for every record - LDCU in the loop body; forcing it into a
+    // vector register removed that instruction and made the kernel 0.8 % slower, profiles/r3_m_*)
     int consumed = count;               // list entries walked; lowered when the pixel stops early
     bool done = !in_image;
     const float stop = fmaxf(t_eps, T_FLOOR);

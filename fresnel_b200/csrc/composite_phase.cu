@@ -395,10 +395,10 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
             };
             m = gmask;
             while (m) {
-                const int j0 = 31 - __clz(m);
+                const int j0 = frb_bfind(m);
                 m ^= 1u << j0;
                 if (m) {
-                    const int j1 = 31 - __clz(m);
+                    const int j1 = frb_bfind(m);
                     m ^= 1u << j1;
                     const BwdPre p0 = bwd_pre(j0), p1 = bwd_pre(j1);
                     bwd_step(j0, p0);
@@ -417,25 +417,32 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 const float2* row = my_pair + lane * PH_STRIDE;
                 const float* prow = my_phib + lane * PH_STRIDE;
                 const float4* pc = sm.pixc[warp];
-                float d_C = 0.f, d_o = 0.f, d_phi = 0.f;
-                // sums as fp32 pairs (FFMA2 / FMUL2 / FADD2: two operations per issue slot, same bits as fmaf)
-                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg, s_xy = s_rg, s_AB = s_rg;
+                float d_phi = 0.f;
+                // colour / depth sums as fp32 pairs (FFMA2); the geometric sums as the six moments sum dpow i^a k^b over
+                // the pixel's place (i, k) in the 8x4 block (immediate operands), combined once per Gaussian - see
+                // composite.cu phase 2
+                float2 s_rg = make_float2(0.f, 0.f), s_bd = s_rg;
+                float m00 = 0.f, m10 = 0.f, m01 = 0.f, m20 = 0.f, m11 = 0.f, m02 = 0.f;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) {
                     const float2 cd = row[p];
                     const float4 gpix = pc[p];
-                    const float dx = ux + (float)(p % FOOT_W);
-                    const float dy = uy + (float)(p / FOOT_W);
+                    const int i = p % FOOT_W, k = p / FOOT_W;
                     s_rg = frb_fma2s(cd.x, make_float2(gpix.x, gpix.y), s_rg);
                     s_bd = frb_fma2s(cd.x, make_float2(gpix.z, gpix.w), s_bd);
-                    d_o += cd.y;
                     d_phi += prow[p];
-                    const float2 t = frb_mul2s(cd.y, make_float2(dx, dy));
-                    s_xy = frb_add2(s_xy, t);
-                    s_AB = frb_fma2s(dx, t, s_AB);
-                    d_C = fmaf(dy, t.y, d_C);
+                    m00 += cd.y;
+                    if (i) m10 = fmaf(cd.y, (float)i, m10);
+                    if (k) m01 = fmaf(cd.y, (float)k, m01);
+                    if (i) m20 = fmaf(cd.y, (float)(i * i), m20);
+                    if (i && k) m11 = fmaf(cd.y, (float)(i * k), m11);
+                    if (k) m02 = fmaf(cd.y, (float)(k * k), m02);
                 }
-                const float sx = s_xy.x, sy = s_xy.y, d_A = s_AB.x, d_B = s_AB.y;
+                const float d_o = m00;
+                const float sx = fmaf(ux, m00, m10), sy = fmaf(uy, m00, m01);
+                const float d_A = fmaf(ux, fmaf(ux, m00, 2.0f * m10), m20);
+                const float d_B = fmaf(ux, fmaf(uy, m00, m01), fmaf(uy, m10, m11));
+                const float d_C = fmaf(uy, fmaf(uy, m00, 2.0f * m01), m02);
                 const float d_r = s_rg.x, d_g = s_rg.y, d_b = s_bd.x, d_dep = s_bd.y;
                 float* sp = &sm.sums[visit & 1][0][lane];
                 atomicAdd(sp + 0 * SUB, -(2.0f * r0.z * sx + r0.w * sy) * oln2);

@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of two builds of the library on one box: bash tools/ab_lib.sh TAG ALT.so   (current, ALT, current, ALT)
+# A/B of two builds of the library on one box: bash tools/ab_lib.sh TAG ALT.so [phase]  (current, ALT, current, ALT;
+# with a third argument also the configs[3] phase-blending workload)
 # ALT.so: a build of another revision copied aside before the call (e.g. tools/probes/_lib_prev.so; *.so is
 # git-ignored but travels with the snapshot).
 TAG=${1:-x}; ALT=$2
@@ -14,6 +15,12 @@ import json
 d=json.loads(open("$O/ab_${TAG}_$v.json").read().strip().splitlines()[-1])
 print("$v", round(d["value"],1), "fps e2e", round(d["e2e"]["value"],1), "serial", round(d["e2e"]["serial"]["value"],1), "; stages", {k:v for k,v in d["roofline"]["stage_ms"].items()})
 PY
+  if [ -n "$3" ]; then
+    python bench.py --workload phase --steps 20 --warmup 5 > $O/ab_${TAG}_phase_$v.json 2>>$O/ab_${TAG}.err
+    python -c "
+import json
+d=json.loads(open('$O/ab_${TAG}_phase_$v.json').read().strip().splitlines()[-1]); print('$v phase', round(d['value'],1), d['stage_ms'])"
+  fi
 done
 cp /tmp/_cur.so $LIB
 tail -3 $O/ab_${TAG}.err
