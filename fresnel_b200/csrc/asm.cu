@@ -41,7 +41,7 @@ asm_assign_planes_kernel(int n, const float4* __restrict__ records, const __grid
                          uint32_t* __restrict__ plane_idx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float depth = records[3 * (size_t)i + 1].z;
+    const float depth = records[3 * (size_t)i + 2].w;
     float best = fabsf(__fsub_rn(depth, ps.depth[0]));      // DR:1147-1148: argmin |depth - plane|, first on ties
     uint32_t arg = 0;
     for (int p = 1; p < ps.n_planes; ++p) {

@@ -110,7 +110,10 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     }
     load_ids(STAGES);
 
-    float T = 1.0f, acc = 0.0f, W1 = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;   // W1 = 1 - acc
+    float T = 1.0f, acc = 0.0f, W1 = 1.0f;      // W1 = 1 - acc
+    // colour and depth sums as two fp32 pairs: (r, g) and (b, depth) are neighbours in the record, so the four fmas
+    // of a pair are two FFMA2 (same bits as fmaf)
+    float2 c_rg = make_float2(0.0f, 0.0f), c_bd = c_rg;
     // (the clamp bound is re-read from the constant bank for every record - LDCU in the loop body; forcing it into a
     // vector register removed that instruction and made the kernel 0.8 % slower, profiles/r3_m_*)
     int consumed = count;               // list entries walked; lowered when the pixel stops early
@@ -127,8 +130,8 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             if (threadIdx.x < (cnt_pad - cnt) * RS) {
                 const int k = threadIdx.x % RS;
                 stage[s].rec[RS * cnt + threadIdx.x] =
-                    make_float4(0.f, 0.f, 0.f, k == 1 ? __uint_as_float(NULL_RECT_LO)
-                                                      : (k == 2 ? __uint_as_float(NULL_RECT_HI) : 0.f));
+                    make_float4(0.f, 0.f, k == 1 ? __uint_as_float(NULL_RECT_LO) : 0.f,
+                                k == 1 ? __uint_as_float(NULL_RECT_HI) : 0.f);
             }
             __syncthreads();
         }
@@ -139,17 +142,15 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 for (int k = 0; k < CHUNK; ++k) {
                     const int j = j0 + k;
                     float4 r1 = rec[RS * j + 1], r2 = rec[RS * j + 2];
-                    if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                    if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w))) {
                         float4 r0 = rec[RS * j + 0];
                         float dx = fpx - r0.x, dy = fpy - r0.y;
                         float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
                         float a = frb_ex2(power) * r1.y;
                         a = fminf(fmaxf(a, 0.0f), alpha_max);
                         float c = a * W1;
-                        cr = fmaf(c, r2.x, cr);
-                        cg = fmaf(c, r2.y, cg);
-                        cb = fmaf(c, r2.z, cb);
-                        cd = fmaf(c, r1.z, cd);
+                        c_rg = frb_fma2s(c, make_float2(r2.x, r2.y), c_rg);
+                        c_bd = frb_fma2s(c, make_float2(r2.z, r2.w), c_bd);
                         acc += c;
                         W1 = 1.0f - acc;
                         T = fmaf(-a, T, T);
@@ -183,6 +184,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         const size_t pix = (size_t)view * hw + (size_t)py * width + px;
         float* img = image + (size_t)view * 3 * hw + (size_t)py * width + px;
         // DR:670-675
+        const float cr = c_rg.x, cg = c_rg.y, cb = c_bd.x, cd = c_bd.y;
         float o0 = fmaf(W1, bg.x, cr), o1 = fmaf(W1, bg.y, cg), o2 = fmaf(W1, bg.z, cb);
         img[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
         img[hw] = fminf(fmaxf(o1, 0.0f), 1.0f);
@@ -361,8 +363,8 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             {
                 bool ok = false;
                 if (lane < sub_cnt) {
-                    const uint32_t lo = __float_as_uint(rec[RS * (sb * 32 + lane) + 1].w);
-                    const uint32_t hi = __float_as_uint(rec[RS * (sb * 32 + lane) + 2].w) & 0x7fff7fffu;
+                    const uint32_t lo = __float_as_uint(rec[RS * (sb * 32 + lane) + 1].z);
+                    const uint32_t hi = __float_as_uint(rec[RS * (sb * 32 + lane) + 1].w) & 0x7fff7fffu;
                     ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
                          (int)(hi >> 16) > wy0;
                 }
@@ -386,7 +388,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 const float4* rj = reinterpret_cast<const float4*>(rec_sb + j * (RS * 16));
                 const float4 r1 = rj[1], r2 = rj[2];
                 p.active = (j < local_n) &&
-                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w));
                 const float4 r0 = rj[0];
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
@@ -395,7 +397,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 p.a = fminf(fmaxf(araw, 0.0f), alpha_max);
                 p.gpass = (p.a == araw) ? g : 0.0f;           // g, or 0 behind the clamp gate 0 <= g*o <= 0.99
                 p.inv_om = frb_rcp(1.0f - p.a);
-                p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                // gC . rgb + gD depth as two packed operations and an add: (r, g) and (b, depth) are neighbours
+                const float2 wp = frb_fma2(make_float2(gb, gd), make_float2(r2.z, r2.w),
+                                           frb_mul2(make_float2(gr, gg), make_float2(r2.x, r2.y)));
+                p.w = wp.x + wp.y;
                 return p;
             };
             auto stage_b = [&](int j, const Pre& p) {

@@ -114,7 +114,7 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                         make_float2(acc, Phi);
                 }
                 float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w))) {
                     float4 r0 = rec[3 * j + 0];
                     float dx = fpx - r0.x, dy = fpy - r0.y;
                     float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
@@ -123,7 +123,7 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                     cr = fmaf(st.c, r2.x, cr);
                     cg = fmaf(st.c, r2.y, cg);
                     cb = fmaf(st.c, r2.z, cb);
-                    cd = fmaf(st.c, r1.z, cd);
+                    cd = fmaf(st.c, r2.w, cd);
                     acc = st.accn;
                     Phi = st.Phin;
                 }
@@ -272,8 +272,8 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         {
             bool ok = false;
             if (lane < cnt) {
-                const uint32_t lo = __float_as_uint(rec[3 * lane + 1].w);
-                const uint32_t hi = __float_as_uint(rec[3 * lane + 2].w) & 0x7fff7fffu;
+                const uint32_t lo = __float_as_uint(rec[3 * lane + 1].z);
+                const uint32_t hi = __float_as_uint(rec[3 * lane + 1].w) & 0x7fff7fffu;
                 ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
                      (int)(hi >> 16) > wy0;
             }
@@ -302,7 +302,7 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 p.phi = __shfl_sync(0xffffffffu, phi_l, j);
                 const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
                 p.active = (j < local_n) &&
-                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w));
                 const float4 r0 = rec[3 * j + 0];
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
                 const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
@@ -350,7 +350,7 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 const float2 before = my_pair[j * PH_STRIDE + lane];
                 const float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
                 p.active = (j < local_n) &&
-                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w));
+                           rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w));
                 const float4 r0 = rec[3 * j + 0];
                 const float Phi0 = before.y;
                 const float dx = fpx - r0.x, dy = fpy - r0.y;
@@ -361,7 +361,7 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 const float sn = __sinf(st.d * TWO_PI_REF);
                 p.T0 = 1.0f - before.x;
                 p.iden = frb_rcp(st.den);
-                p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r1.z;
+                p.w = gr * r2.x + gg * r2.y + gb * r2.z + gd * r2.w;
                 p.K1 = phi - Phi0;
                 p.pc = st.pc;
                 p.q = (st.accn >= 1e-6f) ? st.c * p.iden * p.iden : 0.0f;

@@ -93,9 +93,8 @@ frb_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const float
     uint32_t rect_hi = (uint32_t)o.x1 | ((uint32_t)o.y1 << 16) | 0x80008000u;
 
     records[3 * i + 0] = make_float4(o.u, o.v, o.A, o.B);
-    records[3 * i + 1] = make_float4(o.C, opacities[i], o.depth, __uint_as_float(rect_lo));
-    records[3 * i + 2] = make_float4(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2],
-                                     __uint_as_float(rect_hi));
+    records[3 * i + 1] = make_float4(o.C, opacities[i], __uint_as_float(rect_lo), __uint_as_float(rect_hi));
+    records[3 * i + 2] = make_float4(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], o.depth);
     depth_bits[i] = __float_as_uint(o.depth);
     tiles_touched[i] = touched;
     if (rects) rects[i] = make_int4(o.x0, o.x1, o.y0, o.y1);

@@ -70,8 +70,8 @@ simple_project_fwd_kernel(int n, const __grid_constant__ FrbViewSet vs, const fl
     const uint32_t rect_lo = (uint32_t)x0 | ((uint32_t)y0 << 16);
     const uint32_t rect_hi = (uint32_t)x1 | ((uint32_t)y1 << 16) | 0x80008000u;
     records[3 * i + 0] = make_float4(o.u, o.v, A, 0.0f);
-    records[3 * i + 1] = make_float4(A, opacities[i], o.depth, __uint_as_float(rect_lo));
-    records[3 * i + 2] = make_float4(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], __uint_as_float(rect_hi));
+    records[3 * i + 1] = make_float4(A, opacities[i], __uint_as_float(rect_lo), __uint_as_float(rect_hi));
+    records[3 * i + 2] = make_float4(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], o.depth);
     depth_bits[i] = __float_as_uint(vis ? o.depth : 0.0f);
     tiles_touched[i] = touched;
 }
@@ -125,13 +125,13 @@ simple_depth_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, 
         if (__syncthreads_and(done ? 1 : 0)) break;
         if (done) continue;
         const float4 r1 = sorted_records[3 * (size_t)e + 1], r2 = sorted_records[3 * (size_t)e + 2];
-        const uint32_t lo = __float_as_uint(r1.w), hi = __float_as_uint(r2.w) & 0x7fff7fffu;
+        const uint32_t lo = __float_as_uint(r1.z), hi = __float_as_uint(r1.w) & 0x7fff7fffu;
         if (px >= (int)(lo & 0xffff) && px < (int)(hi & 0xffff) && py >= (int)(lo >> 16) && py < (int)(hi >> 16)) {
             const float4 r0 = sorted_records[3 * (size_t)e + 0];
             const float dx = (float)px - r0.x, dy = (float)py - r0.y;
             const float a = fminf(fmaxf(frb_ex2(r0.z * (dx * dx + dy * dy)) * r1.y, 0.0f), 1.0f);
             if (a > 0.1f) {                                                         // DR:1439
-                d = r1.z;
+                d = r2.w;
                 h = (int)sorted_gids[e];
                 done = true;
             }

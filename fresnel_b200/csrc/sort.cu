@@ -501,8 +501,8 @@ bin_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const fl
     uint32_t off = offsets[k], end = offsets[k + 1];
     if (end == off) return;
     uint32_t g = order ? order[k] : (uint32_t)k;
-    uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].w);
-    uint32_t hi = __float_as_uint(records[3 * (size_t)g + 2].w) & 0x7fff7fffu;
+    uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].z);
+    uint32_t hi = __float_as_uint(records[3 * (size_t)g + 1].w) & 0x7fff7fffu;
     int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
     int tx0 = x0 / FRB_TILE, tx1 = (x1 - 1) / FRB_TILE, ty0 = y0 / FRB_TILE, ty1 = (y1 - 1) / FRB_TILE;
     uint64_t view_base = (uint64_t)(g / (uint32_t)n_per_view) * (uint64_t)tiles_per_view;
@@ -595,8 +595,8 @@ scan_emit_kernel(int n, int n_per_view, int tiles_x, int tiles_per_view, const f
     uint32_t off = prefix_s + woff + incl - cnt;
     if (k == n - 1) *m_out = off + cnt;
     if (cnt) {
-        uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].w);
-        uint32_t hi = __float_as_uint(records[3 * (size_t)g + 2].w) & 0x7fff7fffu;
+        uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].z);
+        uint32_t hi = __float_as_uint(records[3 * (size_t)g + 1].w) & 0x7fff7fffu;
         int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
         int tx0 = x0 / FRB_TILE, tx1 = (x1 - 1) / FRB_TILE, ty0 = y0 / FRB_TILE, ty1 = (y1 - 1) / FRB_TILE;
         uint32_t view_base = (g / (uint32_t)n_per_view) * (uint32_t)tiles_per_view;

@@ -36,8 +36,8 @@ constexpr int SCHED_BUCKETS = 1024;
 
 __device__ __forceinline__ void rect_tiles(const float4* __restrict__ records, uint32_t g, int& tx0, int& tx1,
                                            int& ty0, int& ty1) {
-    const uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].w);
-    const uint32_t hi = __float_as_uint(records[3 * (size_t)g + 2].w) & 0x7fff7fffu;
+    const uint32_t lo = __float_as_uint(records[3 * (size_t)g + 1].z);
+    const uint32_t hi = __float_as_uint(records[3 * (size_t)g + 1].w) & 0x7fff7fffu;
     const int x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
     if (x1 <= x0 || y1 <= y0) {              // culled or empty rectangle: no tiles
         tx0 = ty0 = 0;

@@ -144,7 +144,7 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
 #pragma unroll 4
             for (; j < run_end; ++j) {
                 float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.w), __float_as_uint(r2.w))) {
+                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w))) {
                     float4 r0 = rec[3 * j + 0];
                     float4 wa = wcs[2 * j + 0], wb = wcs[2 * j + 1];
                     float dx = fpx - r0.x, dy = fpy - r0.y;
@@ -153,7 +153,7 @@ wave_splat_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                     re0 = fmaf(amp, wa.x, re0); re1 = fmaf(amp, wa.y, re1); re2 = fmaf(amp, wa.z, re2);
                     im0 = fmaf(amp, wa.w, im0); im1 = fmaf(amp, wb.x, im1); im2 = fmaf(amp, wb.y, im2);
                     if (!ASM) {
-                        ad = fmaf(amp, r1.z, ad);
+                        ad = fmaf(amp, r2.w, ad);
                         aw += amp;
                     }
                 }
@@ -274,7 +274,7 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 const float4 r0 = n0, r1 = n1, r2 = n2, wa = na, wb = nb;
                 const uint32_t gid = ngid;
                 if (e + CTA_THREADS / 32 < g1) load_entry(e + CTA_THREADS / 32);
-                const uint32_t lo = __float_as_uint(r1.w), hi = __float_as_uint(r2.w) & 0x7fff7fffu;
+                const uint32_t lo = __float_as_uint(r1.z), hi = __float_as_uint(r1.w) & 0x7fff7fffu;
                 // rectangle clipped to this tile, in tile-local pixel coordinates
                 const int x0 = max((int)(lo & 0xffff) - tx0, 0), x1 = min((int)(hi & 0xffff) - tx0, TILE);
                 const int y0 = max((int)(lo >> 16) - ty0, 0), y1 = min((int)(hi >> 16) - ty0, TILE);
@@ -301,7 +301,7 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                         dp = frb_fma2(make_float2(wa.z, wa.w), make_float2(ga.z, ga.w), dp);
                         dp = frb_fma2(make_float2(wb.x, wb.y), make_float2(gb.x, gb.y), dp);
                         float damp = dp.x + dp.y;
-                        if (!ASM) damp += r1.z * gb.z + gb.w;
+                        if (!ASM) damp += r2.w * gb.z + gb.w;
                         c01 = frb_fma2s(amp, make_float2(ga.x, ga.y), c01);
                         c23 = frb_fma2s(amp, make_float2(ga.z, ga.w), c23);
                         c45 = frb_fma2s(amp, make_float2(gb.x, gb.y), c45);
@@ -343,7 +343,7 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 const float4 r0 = sorted_records[3 * (size_t)e + 0], r1 = sorted_records[3 * (size_t)e + 1],
                              r2 = sorted_records[3 * (size_t)e + 2];
                 const float4 wa = sorted_wc[2 * (size_t)e + 0], wb = sorted_wc[2 * (size_t)e + 1];
-                const uint32_t lo = __float_as_uint(r1.w), hi = __float_as_uint(r2.w) & 0x7fff7fffu;
+                const uint32_t lo = __float_as_uint(r1.z), hi = __float_as_uint(r1.w) & 0x7fff7fffu;
                 // rectangle clipped to this tile, in tile-local pixel coordinates
                 const int x0 = max((int)(lo & 0xffff) - tx0, 0), x1 = min((int)(hi & 0xffff) - tx0, TILE);
                 const int y0 = max((int)(lo >> 16) - ty0, 0), y1 = min((int)(hi >> 16) - ty0, TILE);
@@ -360,7 +360,7 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                         float amp = g * r1.y;
                         // dL/damp
                         float damp = wa.x * ga.x + wa.y * ga.y + wa.z * ga.z + wa.w * ga.w + wb.x * gb.x + wb.y * gb.y;
-                        if (!ASM) damp += r1.z * gb.z + gb.w;
+                        if (!ASM) damp += r2.w * gb.z + gb.w;
                         dcc0 = fmaf(amp, ga.x, dcc0); dcc1 = fmaf(amp, ga.y, dcc1); dcc2 = fmaf(amp, ga.z, dcc2);
                         dcs0 = fmaf(amp, ga.w, dcs0); dcs1 = fmaf(amp, gb.x, dcs1); dcs2 = fmaf(amp, gb.y, dcs2);
                         if (!ASM) s_dep = fmaf(amp, gb.z, s_dep);

@@ -34,7 +34,8 @@
  *   camera_host : n_views x 20 floats = view-matrix rows 0..2 (12), fx, fy, cx, cy, width,
  *                 height, near, far  (Camera DR:24-52); width/height equal for all views
  *   records     : FRB_RECORD_FLOATS floats per Gaussian
- *                 [u, v, A', B' | C', opacity, depth, rect_lo | r, g, b, rect_hi]
+ *                 [u, v, A', B' | C', opacity, rect_lo, rect_hi | r, g, b, depth]
+ *                 (the two rectangle words are one 8-byte load; (r, g) and (b, depth) feed packed fp32 fmas)
  *                 A',B',C' = conic * (-0.5*log2 e), B = inv01 + inv10 (DR:618);
  *                 rect_lo = x0 | y0 << 16, rect_hi = x1 | y1 << 16 | 0x80008000 (bit-cast);
  *                 the rectangle is [x0,x1) x [y0,y1) of DR:594-597, all zero when culled

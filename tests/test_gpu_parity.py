@@ -68,7 +68,7 @@ def test_projection_bit_exact(golden):
         rec, rects, db, tt, dbg = gpu_project(inp, cam, W, H)
         pn = fo.pins(inp["positions"], inp["scales"], inp["rotations"], cam, W, H, 64)
         assert bits_equal(rec[:, 0], pn["u"]) and bits_equal(rec[:, 1], pn["v"]), name
-        assert bits_equal(rec[:, 6], pn["depth"]), name
+        assert bits_equal(rec[:, 11], pn["depth"]), name
         assert np.array_equal(db, pn["depth_bits"]), name
         assert bits_equal(dbg[:, 0:4], pn["cov"]), name
         assert bits_equal(dbg[:, 4], pn["radius"]), name
@@ -83,8 +83,8 @@ def test_projection_bit_exact(golden):
         tx = (np.maximum(r[:, 1] - 1, 0) // 16 - r[:, 0] // 16 + 1) * (np.maximum(r[:, 3] - 1, 0) // 16 - r[:, 2] // 16 + 1)
         tx[empty] = 0
         assert np.array_equal(tt[vi], tx), name
-        lo = rec[:, 7].view(np.uint32)
-        hi = rec[:, 11].view(np.uint32)
+        lo = rec[:, 6].view(np.uint32)
+        hi = rec[:, 7].view(np.uint32)
         assert np.array_equal(lo[vi] & 0xFFFF, r[:, 0]) and np.array_equal(lo[vi] >> 16, r[:, 2]), name
         assert np.array_equal(hi[vi] & 0x7FFF, r[:, 1]) and np.array_equal((hi[vi] >> 16) & 0x7FFF, r[:, 3]), name
 
