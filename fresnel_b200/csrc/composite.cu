@@ -221,6 +221,7 @@ constexpr int BWD_WARPS = CTA_THREADS / 32;
 constexpr int BWD_FW = 8, BWD_FH = 4;           // pixel block of one warp (BWD_FW * BWD_FH = 32)
 constexpr int PAIR_STRIDE = 33;                 // float2 row stride: conflict-free both ways
 constexpr int N_GRADS = 10;
+constexpr int QUAD_MIN = 4;                     // phase 1 takes four candidates per iteration when this many remain
 
 // 105 KB per CTA, 124 registers: two CTAs (16 warps) per SM.  Round 2 tried the judge's suggestion of a 16-Gaussian
 // exchange tile (71.7 KB, __launch_bounds__(256, 3), 80 registers with 24 bytes of spills: three CTAs per SM): achieved
@@ -418,6 +419,21 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 }
                 *reinterpret_cast<float2*>(pair_lane + j * (PAIR_STRIDE * 8)) = out;
             };
+            while (__popc(cand) >= QUAD_MIN) {         // four candidates per iteration while at least four remain
+                const int j0 = frb_bfind(cand);
+                cand ^= 1u << j0;
+                const int j1 = frb_bfind(cand);
+                cand ^= 1u << j1;
+                const int j2 = frb_bfind(cand);
+                cand ^= 1u << j2;
+                const int j3 = frb_bfind(cand);
+                cand ^= 1u << j3;
+                const Pre p0 = stage_a(j0), p1 = stage_a(j1), p2 = stage_a(j2), p3 = stage_a(j3);
+                stage_b(j0, p0);
+                stage_b(j1, p1);
+                stage_b(j2, p2);
+                stage_b(j3, p3);
+            }
             while (cand) {
                 const int j0 = frb_bfind(cand);
                 cand ^= 1u << j0;
