@@ -222,6 +222,7 @@ constexpr int BWD_FW = 8, BWD_FH = 4;           // pixel block of one warp (BWD_
 constexpr int PAIR_STRIDE = 33;                 // float2 row stride: conflict-free both ways
 constexpr int N_GRADS = 10;
 constexpr int QUAD_MIN = 4;                     // phase 1 takes four candidates per iteration when this many remain
+                                                // (two: 0.1775 ms, four: 0.1674 ms, eight: 0.172 ms; profiles/r3_q_*, r3_r_*)
 
 // 105 KB per CTA, 124 registers: two CTAs (16 warps) per SM.  Round 2 tried the judge's suggestion of a 16-Gaussian
 // exchange tile (71.7 KB, __launch_bounds__(256, 3), 80 registers with 24 bytes of spills: three CTAs per SM): achieved

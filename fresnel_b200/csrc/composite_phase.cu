@@ -324,6 +324,19 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 }
             };
             uint32_t m = gmask;
+            while (__popc(m) >= 4) {                    // four candidates per iteration while at least four remain
+                int jj[4];
+                FwdPre pp[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    jj[q] = __ffs(m) - 1;
+                    m &= m - 1;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pp[q] = fwd_pre(jj[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fwd_step(jj[q], pp[q]);
+            }
             while (m) {
                 const int j0 = __ffs(m) - 1;
                 m &= m - 1;
@@ -394,6 +407,19 @@ composite_phase_bwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
                 my_phib[j * PH_STRIDE + lane] = phib;
             };
             m = gmask;
+            while (__popc(m) >= 4) {
+                int jj[4];
+                BwdPre pp[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    jj[q] = frb_bfind(m);
+                    m ^= 1u << jj[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pp[q] = bwd_pre(jj[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bwd_step(jj[q], pp[q]);
+            }
             while (m) {
                 const int j0 = frb_bfind(m);
                 m ^= 1u << j0;
