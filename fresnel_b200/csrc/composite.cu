@@ -45,7 +45,13 @@ struct FwdStage {
 // output and fewer instructions, but a tile then takes twice as long on half the warps and the kernel ends on its
 // longest tiles: 119.5 us against 100.8 us for one frame (profiles/r2_u_*; with six frames in flight, where other
 // frames fill the tail, 2860-2910 against 2855-2860 frames/s).  Kept: one pixel per thread.
-template <bool GATHER>
+// BY_CANDIDATE (round 2, what the whole-pass calls run): instead of testing every record's rectangle in every thread
+// and branching around the body record by record, a warp finds the records whose rectangle touches its 8x4 block
+// with one ballot per 32 records (lane = record) and walks only those, FOUR per iteration: the state-independent part
+// (loads, rectangle test, power, exp2, clamp) of the four first, then their four short accumulation tails - four
+// independent chains in flight instead of one behind a branch.  A lane outside a candidate's rectangle carries
+// alpha = 0 through the tail (c = 0: no bit of its sums changes).  Early termination is tested once per iteration.
+template <bool GATHER, bool BY_CANDIDATE>
 __global__ void __launch_bounds__(CTA_THREADS)
 composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
                      const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
@@ -68,6 +74,12 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const float fpx = (float)px, fpy = (float)py;
     const uint32_t pxy = (uint32_t)px | ((uint32_t)py << 16);
     const uint32_t pxy_guard = pxy | 0x80008000u, pxy_plus1 = pxy + 0x00010001u;
+    // BY_CANDIDATE: the warp's 8x4 pixel block, and the pixel's words for the rectangle test - moved to a pixel that is
+    // in no rectangle (32766, 32766) once the pixel is done or when it lies outside the image
+    constexpr uint32_t NO_PIXEL_GUARD = 0xfffefffeu, NO_PIXEL_PLUS1 = 0x7fff7fffu;
+    const int wx0 = tx * TILE + ((threadIdx.x >> 5) % (TILE / FOOT_W)) * FOOT_W, wx1 = wx0 + FOOT_W;
+    const int wy0 = ty * TILE + ((threadIdx.x >> 5) / (TILE / FOOT_W)) * FOOT_H, wy1 = wy0 + FOOT_H;
+    uint32_t pxy_guard_v = in_image ? pxy_guard : NO_PIXEL_GUARD, pxy_plus1_v = in_image ? pxy_plus1 : NO_PIXEL_PLUS1;
 
     const int2 range = ranges[tile];
     const int count = range.y - range.x;
@@ -127,7 +139,7 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         const int cnt = min(BATCH, count - b * BATCH);
         const int cnt_pad = (cnt + CHUNK - 1) & ~(CHUNK - 1);
         frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
-        if (cnt_pad != cnt) {
+        if (!BY_CANDIDATE && cnt_pad != cnt) {
             // last batch: pad to a whole chunk with records whose rectangle contains no pixel
             if (threadIdx.x < (cnt_pad - cnt) * RS) {
                 const int k = threadIdx.x % RS;
@@ -137,7 +149,82 @@ composite_fwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             }
             __syncthreads();
         }
-        if (!done) {
+        if (BY_CANDIDATE) {
+            const float4* rec = stage[s].rec;
+            // (a warp whose pixels are all done skips the batch; done lanes sit on a pixel no rectangle contains)
+            if (__any_sync(0xffffffffu, !done)) {
+                for (int sb = 0; sb * 32 < cnt; ++sb) {
+                    const int sub_cnt = min(32, cnt - sb * 32);
+                    uint32_t cand;
+                    {
+                        bool ok = false;
+                        if (lane_f < sub_cnt) {
+                            const float4 q = rec[RS * (sb * 32 + lane_f) + 1];
+                            const uint32_t lo = __float_as_uint(q.z), hi = __float_as_uint(q.w) & 0x7fff7fffu;
+                            ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
+                                 (int)(hi >> 16) > wy0;
+                        }
+                        cand = __brev(__ballot_sync(0xffffffffu, ok));      // bit 31 - j: walked front to back by bfind
+                    }
+                    const char* rec_sb = reinterpret_cast<const char*>(rec + RS * (sb * 32));
+                    struct Pre { float a, d; float2 rg, bd; };
+                    auto stage_a = [&](int j) {
+                        Pre p;
+                        const float4* rj = reinterpret_cast<const float4*>(rec_sb + j * (RS * 16));
+                        const float4 r1 = rj[1], r0 = rj[0], r2 = rj[2];
+                        const bool in = rect_contains(pxy_guard_v, pxy_plus1_v, __float_as_uint(r1.z), __float_as_uint(r1.w));
+                        const float dx = fpx - r0.x, dy = fpy - r0.y;
+                        const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                        const float a = fminf(fmaxf(frb_ex2(power) * r1.y, 0.0f), alpha_max);
+                        p.a = in ? a : 0.0f;
+                        p.rg = make_float2(r2.x, r2.y);
+                        p.bd = make_float2(r2.z, r2.w);
+                        return p;
+                    };
+                    auto stage_b = [&](const Pre& p) {
+                        const float c = p.a * W1;
+                        c_rg = frb_fma2s(c, p.rg, c_rg);
+                        c_bd = frb_fma2s(c, p.bd, c_bd);
+                        acc += c;
+                        W1 = 1.0f - acc;
+                        T = fmaf(-p.a, T, T);
+                    };
+                    int last = -1;
+                    while (cand) {
+                        if (__popc(cand) >= 4) {
+                            int jj[4];
+                            Pre pp[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int bpos = frb_bfind(cand);
+                                cand ^= 1u << bpos;
+                                jj[q] = 31 - bpos;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) pp[q] = stage_a(jj[q]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) stage_b(pp[q]);
+                            last = jj[3];
+                        } else {
+                            const int bpos = frb_bfind(cand);
+                            cand ^= 1u << bpos;
+                            last = 31 - bpos;
+                            const Pre p0 = stage_a(last);
+                            stage_b(p0);
+                        }
+                        // early termination, tested once per iteration; the backward pass replays exactly the
+                        // entries [0, consumed)
+                        if (!done && T < stop) {
+                            done = true;
+                            consumed = b * BATCH + sb * 32 + last + 1;
+                            pxy_guard_v = NO_PIXEL_GUARD;       // in no rectangle from here on
+                            pxy_plus1_v = NO_PIXEL_PLUS1;
+                        }
+                        if (!__any_sync(0xffffffffu, !done)) cand = 0;
+                    }
+                }
+            }
+        } else if (!done) {
             const float4* rec = stage[s].rec;
             for (int j0 = 0; j0 < cnt_pad; j0 += CHUNK) {
 #pragma unroll
@@ -635,7 +722,7 @@ extern "C" int frb_composite_fwd_cap(int n_views, int width, int height, const i
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     CUtensorMap no_map = {};
-    frb_launch(composite_fwd_kernel<false>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
+    frb_launch(composite_fwd_kernel<false, false>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
         width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)sorted_records, no_map,
         (const uint32_t*)nullptr, bg, t_eps, alpha_max, image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
@@ -660,9 +747,15 @@ extern "C" int frb_composite_fwd_gather(int n_views, int width, int height, cons
     int tiles_x = frb_div_up(width, TILE), tiles_y = frb_div_up(height, TILE);
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
-    frb_launch(composite_fwd_kernel<true>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
-        width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map, sorted_gids, bg,
-        t_eps, alpha_max, image, depth, alpha, state_T, state_n);
+    static const bool by_record = getenv("FRB_FWD_BY_RECORD") && getenv("FRB_FWD_BY_RECORD")[0] == '1';
+    if (by_record)
+        frb_launch(composite_fwd_kernel<true, false>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
+            width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map, sorted_gids, bg,
+            t_eps, alpha_max, image, depth, alpha, state_T, state_n);
+    else
+        frb_launch(composite_fwd_kernel<true, true>, dim3(n_views * tpv), dim3(CTA_THREADS), 0, (cudaStream_t)stream,
+            width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map, sorted_gids, bg,
+            t_eps, alpha_max, image, depth, alpha, state_T, state_n);
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
