@@ -57,6 +57,27 @@ __device__ __forceinline__ float warp_reduce_multi(const float (&in)[N], int lan
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// The same over the 16 lanes of a half-warp (both halves at once): 15 shuffles; lane l of the half (hl = lane & 15)
+// ends with the half's total of value hl.
+template <int N>
+__device__ __forceinline__ float halfwarp_reduce_multi(const float (&in)[N], int hl) {
+    static_assert(N <= 16, "at most 16 values");
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (k < N) ? in[k] : 0.0f;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool upper = (hl & half) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            float keep = upper ? v[k + half] : v[k];
+            float send = upper ? v[k] : v[k + half];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
 __device__ __forceinline__ int warp_reduce_multi_index(int lane) {
     return ((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1);
 }

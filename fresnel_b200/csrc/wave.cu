@@ -258,8 +258,13 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
             // that is moved down the rectangle; cols = 4, 8 or 16 (the smallest that holds the rectangle's width), so
             // at least half of the lanes are on pixels of the rectangle and neighbouring lanes read neighbouring
             // shared-memory words.  The thirteen partial sums are reduced over the warp with the halving butterfly.
+            // (round 2: HALF a warp per entry - at config 5 a rectangle clipped to the tile is ~8 x 8 pixels, i.e. two
+            // trips of the pixel loop against ~130 instructions of fixed cost per entry (prefetch, rectangle, the
+            // 16-shuffle butterfly, atomics); two entries per warp instruction halve that fixed cost.)
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            // the entry's 80 bytes come straight from global memory (L2): the next entry of this warp is loaded
+            const int hl = lane & 15, upper_half = lane >> 4;
+            constexpr int N_SUB = CTA_THREADS / 16;                // half-warps per CTA
+            // the entry's 80 bytes come straight from global memory (L2): the next entry of this half-warp is loaded
             // before the current one is processed, so the load latency hides behind the pixel loop
             float4 n0, n1, n2, na, nb;
             uint32_t ngid = 0;
@@ -269,26 +274,28 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 na = sorted_wc[2 * (size_t)e + 0]; nb = sorted_wc[2 * (size_t)e + 1];
                 ngid = sorted_gids[e];
             };
-            if (g0 + warp < g1) load_entry(g0 + warp);
-            for (int e = g0 + warp; e < g1; e += CTA_THREADS / 32) {
+            if (g0 + 2 * warp + upper_half < g1) load_entry(g0 + 2 * warp + upper_half);
+            for (int eb = g0 + 2 * warp; eb < g1; eb += N_SUB) {            // eb: the lower half's entry (uniform)
+                const int e = eb + upper_half;
+                const bool have = e < g1;
                 const float4 r0 = n0, r1 = n1, r2 = n2, wa = na, wb = nb;
                 const uint32_t gid = ngid;
-                if (e + CTA_THREADS / 32 < g1) load_entry(e + CTA_THREADS / 32);
+                if (e + N_SUB < g1) load_entry(e + N_SUB);
                 const uint32_t lo = __float_as_uint(r1.z), hi = __float_as_uint(r1.w) & 0x7fff7fffu;
-                // rectangle clipped to this tile, in tile-local pixel coordinates
-                const int x0 = max((int)(lo & 0xffff) - tx0, 0), x1 = min((int)(hi & 0xffff) - tx0, TILE);
-                const int y0 = max((int)(lo >> 16) - ty0, 0), y1 = min((int)(hi >> 16) - ty0, TILE);
+                // rectangle clipped to this tile, in tile-local pixel coordinates (empty for a half without an entry)
+                const int x0 = max((int)(lo & 0xffff) - tx0, 0), x1 = have ? min((int)(hi & 0xffff) - tx0, TILE) : 0;
+                const int y0 = max((int)(lo >> 16) - ty0, 0), y1 = have ? min((int)(hi >> 16) - ty0, TILE) : 0;
                 const int wr = x1 - x0;
                 const int shift = (wr <= 4) ? 2 : ((wr <= 8) ? 3 : 4);           // patch width 4 / 8 / 16
-                const int lx = x0 + (lane & ((1 << shift) - 1));
-                const int rows = 32 >> shift;
+                const int lx = x0 + (hl & ((1 << shift) - 1));
+                const int rows = 16 >> shift;
                 const bool col_ok = lx < x1;
                 const float dx = bx - r0.x + (float)lx;
                 float part[13];
     #pragma unroll
                 for (int q = 0; q < 13; ++q) part[q] = 0.0f;
                 float2 c01 = make_float2(0.f, 0.f), c23 = c01, c45 = c01;
-                for (int ly = y0 + (lane >> shift); ly < y1; ly += rows) {
+                for (int ly = y0 + (hl >> shift); ly < y1; ly += rows) {
                     if (col_ok) {
                         const float dy = by - r0.y + (float)ly;
                         const float4 ga = gp_a[ly * TILE + lx], gb = gp_b[ly * TILE + lx];
@@ -319,12 +326,12 @@ wave_splat_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, co
                 part[0] = dx * part[5];                               // sx
                 part[2] = dx * part[0];                               // sum dx^2 gd
                 part[3] = dx * part[1];                               // sum dx dy gd
-                const float tot = warp_reduce_multi<13>(part, lane);
-                const int slot = warp_reduce_multi_index(lane);
-                const float sx = __shfl_sync(0xffffffffu, tot, 0), sy = __shfl_sync(0xffffffffu, tot, 2);   // slots 0, 1
-                // lane 2k holds the total of value k: thirteen lanes of ONE atomic instruction on two contiguous rows
-                // (as four 16-byte vector reductions gathered by shuffles this was 25 % slower: 2.32 -> 2.90 ms)
-                if ((lane & 1) == 0 && slot < 13) {
+                const float tot = halfwarp_reduce_multi<13>(part, hl);
+                const int slot = hl;
+                const float sx = __shfl_sync(0xffffffffu, tot, lane & 16), sy = __shfl_sync(0xffffffffu, tot, (lane & 16) | 1);
+                // lane k of the half holds the total of value k: thirteen lanes per entry of ONE atomic instruction on
+                // two contiguous rows (as four 16-byte vector reductions gathered by shuffles this was 25 % slower)
+                if (have && slot < 13) {
                     const float oln2 = r1.y * FRB_LN2;                // dL/d(power) = g * damp * o * ln2
                     float* g2 = grad2d + (size_t)gid * FRB_GRAD_FLOATS;
                     float* gw = gwc + (size_t)gid * WC_FLOATS;
