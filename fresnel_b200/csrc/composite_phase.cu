@@ -90,9 +90,16 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
     if (threadIdx.x == 0)
         for (int b = 0; b < STAGES && b < n_batches; ++b) issue(b);
 
-    float acc = 0.0f, Phi = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f;
+    float acc = 0.0f, Phi = 0.0f;
+    float2 c_rg = make_float2(0.0f, 0.0f), c_bd = c_rg;        // (r, g) and (b, depth) sums as fp32 pairs (FFMA2)
     int consumed = count;
     bool done = !in_image;
+    // the warp's 8x4 pixel block; the pixel's words for the rectangle test move to a pixel that is in no rectangle
+    // (32766, 32766) once the pixel is done or when it lies outside the image
+    constexpr uint32_t NO_PIXEL_GUARD = 0xfffefffeu, NO_PIXEL_PLUS1 = 0x7fff7fffu;
+    const int wx0 = tx * TILE + ((threadIdx.x >> 5) % (TILE / FOOT_W)) * FOOT_W, wx1 = wx0 + FOOT_W;
+    const int wy0 = ty * TILE + ((threadIdx.x >> 5) / (TILE / FOOT_W)) * FOOT_H, wy1 = wy0 + FOOT_H;
+    uint32_t pxy_guard_v = in_image ? pxy_guard : NO_PIXEL_GUARD, pxy_plus1_v = in_image ? pxy_plus1 : NO_PIXEL_PLUS1;
     const float stop = fmaxf(t_eps, T_FLOOR);
 
     for (int b = 0; b < n_batches; ++b) {
@@ -101,31 +108,81 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         if (threadIdx.x < cnt) phase_s[s][threadIdx.x] = sorted_phases[range.x + b * BATCH + threadIdx.x];
         frb_mbar_wait(&full_bar[s], (b / STAGES) & 1);
         __syncthreads();
-        if (!done) {
+        // Per 32-entry block (= checkpoint interval): termination test and checkpoint, then the warp walks the records
+        // whose rectangle touches its 8x4 block, four per iteration - the state-independent part (loads, rectangle
+        // test, exp2, phase fetch) of the four first, then the four serial steps; a lane outside a rectangle carries
+        // a0 = 0 through its step (alpha = c = pc = 0: neither acc nor Phi changes a bit).  Same arithmetic per pixel
+        // as the record-by-record loop this replaces (0.226 ms at configs[3]).
+        {
             const float4* rec = stage[s].rec;
-            for (int j = 0; j < cnt; ++j) {
-                if ((j & (SUB - 1)) == 0) {
+            const int lane = threadIdx.x & 31;
+            for (int sb = 0; sb * SUB < cnt; ++sb) {
+                if (!done) {
                     if (1.0f - acc < stop) {              // tested at checkpoint boundaries
                         done = true;
-                        consumed = b * BATCH + j;
-                        break;
+                        consumed = b * BATCH + sb * SUB;
+                        pxy_guard_v = NO_PIXEL_GUARD;     // in no rectangle from here on
+                        pxy_plus1_v = NO_PIXEL_PLUS1;
+                    } else if (ckpt) {
+                        ckpt[ckpt_slot(range.x, tile, (b * BATCH + sb * SUB) >> 5) * CTA_THREADS + threadIdx.x] =
+                            make_float2(acc, Phi);
                     }
-                    if (ckpt) ckpt[ckpt_slot(range.x, tile, (b * BATCH + j) >> 5) * CTA_THREADS + threadIdx.x] =
-                        make_float2(acc, Phi);
                 }
-                float4 r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-                if (rect_contains(pxy_guard, pxy_plus1, __float_as_uint(r1.z), __float_as_uint(r1.w))) {
-                    float4 r0 = rec[3 * j + 0];
-                    float dx = fpx - r0.x, dy = fpy - r0.y;
-                    float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                if (!__any_sync(0xffffffffu, !done)) break;
+                const int sub_cnt = min(SUB, cnt - sb * SUB);
+                uint32_t cand;
+                {
+                    bool ok = false;
+                    if (lane < sub_cnt) {
+                        const float4 q = rec[3 * (sb * SUB + lane) + 1];
+                        const uint32_t lo = __float_as_uint(q.z), hi = __float_as_uint(q.w) & 0x7fff7fffu;
+                        ok = (int)(lo & 0xffff) < wx1 && (int)(hi & 0xffff) > wx0 && (int)(lo >> 16) < wy1 &&
+                             (int)(hi >> 16) > wy0;
+                    }
+                    cand = __brev(__ballot_sync(0xffffffffu, ok));          // bit 31 - j: front to back by bfind
+                }
+                const char* rec_sb = reinterpret_cast<const char*>(rec + 3 * (sb * SUB));
+                const float* phase_sb = &phase_s[s][sb * SUB];
+                struct Pre { float g, o, phi; float2 rg, bd; };
+                auto pre = [&](int j) {
+                    Pre p;
+                    const float4* rj = reinterpret_cast<const float4*>(rec_sb + j * 48);
+                    const float4 r1 = rj[1], r0 = rj[0], r2 = rj[2];
+                    const bool in = rect_contains(pxy_guard_v, pxy_plus1_v, __float_as_uint(r1.z), __float_as_uint(r1.w));
+                    const float dx = fpx - r0.x, dy = fpy - r0.y;
+                    const float power = dx * (r0.z * dx + r0.w * dy) + r1.x * (dy * dy);
+                    p.g = in ? frb_ex2(power) : 0.0f;
+                    p.o = r1.y;
+                    p.phi = phase_sb[j];
+                    p.rg = make_float2(r2.x, r2.y);
+                    p.bd = make_float2(r2.z, r2.w);
+                    return p;
+                };
+                auto step = [&](const Pre& p) {
                     PhaseStep st;
-                    phase_step(frb_ex2(power), r1.y, phase_s[s][j], A, acc, Phi, st);
-                    cr = fmaf(st.c, r2.x, cr);
-                    cg = fmaf(st.c, r2.y, cg);
-                    cb = fmaf(st.c, r2.z, cb);
-                    cd = fmaf(st.c, r2.w, cd);
+                    phase_step(p.g, p.o, p.phi, A, acc, Phi, st);
+                    c_rg = frb_fma2s(st.c, p.rg, c_rg);
+                    c_bd = frb_fma2s(st.c, p.bd, c_bd);
                     acc = st.accn;
                     Phi = st.Phin;
+                };
+                while (cand) {
+                    if (__popc(cand) >= 4) {
+                        Pre pp[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int bpos = frb_bfind(cand);
+                            cand ^= 1u << bpos;
+                            pp[q] = pre(31 - bpos);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) step(pp[q]);
+                    } else {
+                        const int bpos = frb_bfind(cand);
+                        cand ^= 1u << bpos;
+                        const Pre p0 = pre(31 - bpos);
+                        step(p0);
+                    }
                 }
             }
         }
@@ -143,6 +200,7 @@ composite_phase_fwd_kernel(int width, int height, int tiles_x, int tiles_per_vie
         const size_t pix = (size_t)view * hw + (size_t)py * width + px;
         float* img = image + (size_t)view * 3 * hw + (size_t)py * width + px;
         const float T = 1.0f - acc;
+        const float cr = c_rg.x, cg = c_rg.y, cb = c_bd.x, cd = c_bd.y;
         float o0 = fmaf(T, bg.x, cr), o1 = fmaf(T, bg.y, cg), o2 = fmaf(T, bg.z, cb);
         img[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
         img[hw] = fminf(fmaxf(o1, 0.0f), 1.0f);
