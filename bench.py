@@ -1149,7 +1149,9 @@ def stage_algorithmic_bytes(N, HW, M):
         "frb_bin_sort_dev": 20 * N + 12 * M + 2 * (2 * 12 * M),
         "frb_tile_count_scan": 8 * N + 8 * (HW // 256) * 98,
         "frb_tile_emit": 12 * N + 4 * M,
-        "frb_tile_rank_gather": 8 * M + 4 * M + 96 * M,
+        # whole-pass calls with the gather compositors: depth rank in, Gaussian id out, no record copy
+        # (the staged path with a sorted record copy moves 96 M more)
+        "frb_tile_rank_gather": 4 * M + 4 * M + 4 * N,
         "frb_radix_sort_pairs": 2 * (2 * 12 * M),
         "frb_tile_ranges": 8 * M,
         "frb_gather_records": 4 * M + 96 * M,
