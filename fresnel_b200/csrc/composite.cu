@@ -319,19 +319,23 @@ constexpr int QUAD_MIN = 4;                     // phase 1 takes four candidates
 // Also tried: the second block-wide barrier of a visit split into bar.arrive by the summing threads / bar.sync before
 // the next visit's first part[] store, so that the cross-warp sum overlaps the next phase 1 - 197.8 us against
 // 194.6 us (profiles/r2_t_*): the barrier stall in the capture is warps whose pixels ended early, not the sum.
-template <bool GATHER>
+// HALVES = 1: one CTA of eight warps per tile, four ring stages.  HALVES = 2: TWO CTAs of four warps per tile (the
+// upper and the lower 16 x 8 pixels), two ring stages, four CTAs per SM: the same sixteen warps per SM in four barrier
+// groups instead of two - a batch ends when the slowest of four warps is done, not the slowest of eight.
+template <bool GATHER, int HALVES>
 struct BwdSmem {
-    FwdStage<GATHER> stage[STAGES];                 // first: the gather destinations need 128-byte alignment
-    float2 pair[BWD_WARPS][32 * PAIR_STRIDE];
-    float part[BWD_WARPS][N_GRADS][BATCH];
-    float4 pixc[BWD_WARPS][32];
-    uint32_t gid[STAGES][BATCH];
-    uint64_t full_bar[STAGES];
+    static constexpr int NW = BWD_WARPS / HALVES, NST = HALVES == 2 ? 2 : STAGES;
+    FwdStage<GATHER> stage[NST];                    // first: the gather destinations need 128-byte alignment
+    float2 pair[NW][32 * PAIR_STRIDE];
+    float part[NW][N_GRADS][BATCH];
+    float4 pixc[NW][32];
+    uint32_t gid[NST][BATCH];
+    uint64_t full_bar[NST];
     int max_n;
 };
 
-template <bool GATHER>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+template <bool GATHER, int HALVES>
+__global__ void __launch_bounds__(CTA_THREADS / HALVES, 2 * HALVES)
 composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, const int* __restrict__ tile_order,
                      const int2* __restrict__ ranges, const float4* __restrict__ sorted_records,
                      const __grid_constant__ CUtensorMap record_map, const uint32_t* __restrict__ sorted_gids,
@@ -342,16 +346,20 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     frb_pdl_prologue();
     constexpr int RS = FwdStage<GATHER>::RS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    BwdSmem<GATHER>& sm = *reinterpret_cast<BwdSmem<GATHER>*>(smem_raw);
+    using Smem = BwdSmem<GATHER, HALVES>;
+    constexpr int NW = Smem::NW, NST = Smem::NST, NT = 32 * NW;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-    const int tile = tile_order ? tile_order[blockIdx.x] : blockIdx.x;   // heaviest tiles first
+    const int tile_slot = blockIdx.x / HALVES, half_of_tile = blockIdx.x % HALVES;
+    const int tile = tile_order ? tile_order[tile_slot] : tile_slot;     // heaviest tiles first
     const int view = tile / tiles_per_view;
     const int t_in_view = tile - view * tiles_per_view;
     const int ty = t_in_view / tiles_x, tx = t_in_view - ty * tiles_x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a warp owns a BWD_FW x BWD_FH pixel block of the tile: the squarer the block, the fewer list entries
     // whose rectangle touches it (phase 1 walks only those)
-    const int wx0 = tx * TILE + (warp % (TILE / BWD_FW)) * BWD_FW, wy0 = ty * TILE + (warp / (TILE / BWD_FW)) * BWD_FH;
+    const int wx0 = tx * TILE + (warp % (TILE / BWD_FW)) * BWD_FW,
+              wy0 = ty * TILE + half_of_tile * (TILE / HALVES) + (warp / (TILE / BWD_FW)) * BWD_FH;
     const int wx1 = wx0 + BWD_FW, wy1 = wy0 + BWD_FH;
     const int px = wx0 + (lane % BWD_FW);
     const int py = wy0 + (lane / BWD_FW);
@@ -382,7 +390,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     sm.pixc[warp][lane] = make_float4(gr, gg, gb, gd);
     if (threadIdx.x == 0) {
         sm.max_n = 0;
-        for (int s = 0; s < STAGES; ++s) frb_mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < NST; ++s) frb_mbar_init(&sm.full_bar[s], 1);
         frb_mbar_fence_init();
     }
     __syncthreads();
@@ -395,13 +403,13 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     const int n_batches = (count + BATCH - 1) / BATCH;
     if (n_batches == 0) return;
 
-    // batches are visited last to first; ring slot (visit % STAGES) holds visit.  Producer: thread 0 (bulk copy of the
+    // batches are visited last to first; ring slot (visit % NST) holds visit.  Producer: thread 0 (bulk copy of the
     // sorted records) or lanes 0..15 of warp 0 (gather4 by Gaussian id, ids prefetched one visit ahead).
     // (the producer of visit v is warp v % 8, so that its few dozen instructions per batch do not always delay the
     // same warp at the batch barrier)
     uint4 pre_g = make_uint4(0u, 0u, 0u, 0u);
     auto load_ids = [&](int visit) {
-        if (GATHER && warp == (visit & (BWD_WARPS - 1)) && lane < BATCH / 4 && visit < n_batches) {
+        if (GATHER && warp == (visit & (NW - 1)) && lane < BATCH / 4 && visit < n_batches) {
             const int b = n_batches - 1 - visit;
             const int i0 = b * BATCH + 4 * lane, last = count - 1;
             const uint32_t* g = sorted_gids + range.x;
@@ -410,7 +418,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
     };
     auto issue = [&](int visit) {
         const int b = n_batches - 1 - visit;
-        const int s = visit % STAGES;
+        const int s = visit % NST;
         const int cnt = min(BATCH, count - b * BATCH);
         if (!GATHER) {
             if (threadIdx.x == 0) {
@@ -418,7 +426,7 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 frb_tma_load_1d(sm.stage[s].rec, sorted_records + 3 * (size_t)(range.x + b * BATCH), cnt * RECORD_BYTES,
                                 &sm.full_bar[s]);
             }
-        } else if (warp == (visit & (BWD_WARPS - 1))) {
+        } else if (warp == (visit & (NW - 1))) {
             const int groups = (cnt + 3) >> 2;
             if (lane == 0) frb_mbar_expect_tx(&sm.full_bar[s], groups * 4 * RS * 16);
             __syncwarp();
@@ -426,11 +434,11 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
                 frb_tma_gather4(sm.stage[s].rec + 4 * RS * lane, &record_map, pre_g, &sm.full_bar[s]);
         }
     };
-    for (int v = 0; v < STAGES && v < n_batches; ++v) {
+    for (int v = 0; v < NST && v < n_batches; ++v) {
         load_ids(v);
         issue(v);
     }
-    load_ids(STAGES);
+    load_ids(NST);
 
     const float X = gr * bg.x + gg * bg.y + gb * bg.z - ga;
     const float TX = T_final * X;
@@ -440,10 +448,10 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
 
     for (int visit = 0; visit < n_batches; ++visit) {
         const int b = n_batches - 1 - visit;
-        const int s = visit % STAGES;
+        const int s = visit % NST;
         const int cnt = min(BATCH, count - b * BATCH);
         if (threadIdx.x < cnt) sm.gid[s][threadIdx.x] = sorted_gids[range.x + b * BATCH + threadIdx.x];
-        frb_mbar_wait(&sm.full_bar[s], (visit / STAGES) & 1);
+        frb_mbar_wait(&sm.full_bar[s], (visit / NST) & 1);
         const float4* rec = sm.stage[s].rec;
 
         for (int sb = (cnt - 1) >> 5; sb >= 0; --sb) {
@@ -593,13 +601,13 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
         // one thread per (Gaussian, float4 of its grad2d row [du dv dA dB | dC do ddepth _ | dr dg db _]):
         // the eight warps' partial sums are added and leave as ONE 16-byte vector reduction (red.global.add.v4.f32)
         // instead of up to four scalar atomics
-        if (threadIdx.x < 3 * BATCH) {
-            const int q = threadIdx.x / BATCH, jb = threadIdx.x - q * BATCH;
+        for (int t = threadIdx.x; t < 3 * BATCH; t += NT) {
+            const int q = t / BATCH, jb = t - q * BATCH;
             if (jb < cnt) {
                 const int v0 = (q == 0) ? 0 : (q == 1 ? 4 : 7);
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int w = 0; w < BWD_WARPS; ++w) {
+                for (int w = 0; w < NW; ++w) {
                     sum.x += sm.part[w][v0][jb];
                     sum.y += sm.part[w][v0 + 1][jb];
                     sum.z += sm.part[w][v0 + 2][jb];
@@ -610,9 +618,9 @@ composite_bwd_kernel(int width, int height, int tiles_x, int tiles_per_view, con
             }
         }
         __syncthreads();    // stage s, gid[s] and part are free
-        if (visit + STAGES < n_batches) {
-            issue(visit + STAGES);
-            load_ids(visit + STAGES + 1);
+        if (visit + NST < n_batches) {
+            issue(visit + NST);
+            load_ids(visit + NST + 1);
         }
     }
 }
@@ -806,9 +814,9 @@ extern "C" int frb_composite_bwd_cap(int n_views, int width, int height, const i
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     static unsigned long long smem_opted_in = 0;          // per-device bitmask (the attribute is per device)
-    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<false>, (int)sizeof(BwdSmem<false>), &smem_opted_in));
+    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<false, 1>, (int)sizeof(BwdSmem<false, 1>), &smem_opted_in));
     CUtensorMap no_map = {};
-    frb_launch(composite_bwd_kernel<false>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<false>),
+    frb_launch(composite_bwd_kernel<false, 1>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<false, 1>),
         (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges,
         (const float4*)sorted_records, no_map, sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha,
         grad2d);
@@ -833,10 +841,21 @@ extern "C" int frb_composite_bwd_gather(int n_views, int width, int height, cons
     int tpv = tiles_x * tiles_y;
     float3 bg = make_float3(background_host[0], background_host[1], background_host[2]);
     static unsigned long long smem_opted_in = 0;
-    FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<true>, (int)sizeof(BwdSmem<true>), &smem_opted_in));
-    frb_launch(composite_bwd_kernel<true>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<true>),
-        (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr, map,
-        sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    static unsigned long long smem_opted_in_halves = 0;
+    // default: two CTAs per tile (0.168 -> 0.164 ms, resident 2942 -> 2987, host to host 3131 -> 3202 frames/s on one box,
+    // profiles/r4_d_*); FRB_BWD_HALVES=1 launches the one-CTA form
+    static const bool halves = !(getenv("FRB_BWD_HALVES") && getenv("FRB_BWD_HALVES")[0] == '1');
+    if (halves) {
+        FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<true, 2>, (int)sizeof(BwdSmem<true, 2>), &smem_opted_in_halves));
+        frb_launch(composite_bwd_kernel<true, 2>, dim3(2 * n_views * tpv), dim3(CTA_THREADS / 2), sizeof(BwdSmem<true, 2>),
+            (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr,
+            map, sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    } else {
+        FRB_CUDA_OK(frb_opt_in_smem(composite_bwd_kernel<true, 1>, (int)sizeof(BwdSmem<true, 1>), &smem_opted_in));
+        frb_launch(composite_bwd_kernel<true, 1>, dim3(n_views * tpv), dim3(CTA_THREADS), sizeof(BwdSmem<true, 1>),
+            (cudaStream_t)stream, width, height, tiles_x, tpv, tile_order, (const int2*)ranges, (const float4*)nullptr,
+            map, sorted_gids, bg, alpha_max, state_T, state_n, g_image, g_depth, g_alpha, grad2d);
+    }
     frb_note_launches(1);
     FRB_LAUNCH_CHECK();
     return 0;
