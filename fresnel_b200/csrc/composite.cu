@@ -38,6 +38,8 @@ struct FwdStage {
     float4 rec[BATCH * RS];
 };
 
+// Tried in round 2: two CTAs of four warps per tile, as the backward kernel now runs: 0.0948 against 0.0927 ms
+// (profiles/r4_e_*) - the forward's batch barrier costs less than staging every tile's records twice.
 // Tried in round 2: __launch_bounds__(256, 6) (40 registers instead of 47, six CTAs per SM instead of five): 0.104 against
 // 0.096 ms (profiles/r3_p_*) - the register cap costs more instructions than the sixth CTA hides.
 // Tried in round 2: two pixels per thread (128 threads, a warp owns an 8x8 block, the pixel-independent part of a
