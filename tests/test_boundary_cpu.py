@@ -48,6 +48,18 @@ def test_argument_validation_needs_no_gpu(cuda_lib):
     assert cuda_lib.frb_sort_workspace_bytes(1 << 20) >= 256 * 4 * (1 << 20) // 2048
 
 
+def test_depth_sort_mode_switch_is_a_host_side_setting(cuda_lib):
+    """frb_depth_sort_in_cluster: -1 (environment) is the initial state, the call returns the previous mode, other
+    values are refused and leave the mode alone."""
+    L = cuda_lib
+    assert L.frb_depth_sort_in_cluster(1) == -1
+    assert L.frb_depth_sort_in_cluster(0) == 1
+    assert L.frb_depth_sort_in_cluster(7) == -1          # FRB_E_INVALID
+    assert L.frb_depth_sort_in_cluster(-2) == -1
+    assert L.frb_depth_sort_in_cluster(-1) == 0          # unchanged by the refused calls; back to the initial state
+    assert L.frb_depth_sort_in_cluster(-1) == -1
+
+
 def test_no_cpu_fallback():
     r = fresnel_b200.TileBasedRenderer(32, 32)
     z = torch.zeros
