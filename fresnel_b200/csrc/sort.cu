@@ -69,6 +69,7 @@ struct PassPlan {
 struct KeyRange {
     uint32_t lo, hi;
     int on;
+    int ballot;     // this pass finds equal digits in a warp with ballots instead of match.any (radix_onesweep_kernel)
 };
 template <typename KeyT>
 __device__ __forceinline__ KeyT key_xform(KeyT k, const KeyRange& kr) { return k; }
@@ -191,7 +192,23 @@ radix_onesweep_kernel(int m, const uint32_t* __restrict__ m_dev, const KeyT* __r
     for (int r = 0; r < IPT; ++r) {
         long long i = base + r * 32 + lane;
         uint32_t d = (i < m) ? digit_of(key[r], shift, mask) : RDX;     // invalid lanes match each other only
-        peers[r] = __match_any_sync(0xffffffffu, d);
+        // lanes with my digit from one ballot per digit bit: MATCH.ANY iterates over the distinct values of the warp
+        // (up to 32 for an 8-bit digit), the ballots are a fixed log2(RDX) + 1
+        // - faster for the spread-out low digits of depth keys (depth order of 100k keys 42.8 -> 41.2 us), slower
+        // where a warp holds few distinct digits (plane indices of the ASM renderer: 65 -> 88 us for 1M keys), so the
+        // caller chooses per pass (kr.ballot)
+        if (kr.ballot) {
+            uint32_t pm = 0xffffffffu;
+#pragma unroll
+            for (int bb = 0; (1 << bb) <= RDX; ++bb) {
+                const bool bit = (d >> bb) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                pm &= bit ? bal : ~bal;
+            }
+            peers[r] = pm;
+        } else {
+            peers[r] = __match_any_sync(0xffffffffu, d);
+        }
     }
 #pragma unroll
     for (int r = 0; r < IPT; ++r) {
@@ -347,7 +364,7 @@ template <typename KeyT, int RB>
 int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const uint32_t* first_vals, KeyT* keys_a, uint32_t* vals_a,
                     KeyT* keys_b, uint32_t* vals_b, int begin_bit, int end_bit, uint32_t* ws, cudaStream_t st,
                     bool* result_in_b, bool hist_ready = false, uint32_t* rank_out = nullptr,
-                    KeyRange kr = KeyRange{0u, 0u, 0}) {
+                    KeyRange kr = KeyRange{0u, 0u, 0, 0}) {
     constexpr int RDX = 1 << RB;
     PassPlan plan;
     plan.n_passes = 0;
@@ -375,10 +392,12 @@ int radix_sort_impl(int m, const uint32_t* m_dev, const KeyT* first_keys, const 
         uint32_t* status = ws + WS_STATUS + (size_t)p * n_blocks * RDX;
         const int grid = min(n_blocks, SORT_GRID_MAX);
         const bool xf = kr.on && p == 0;
+        KeyRange kr_pass = kr;
+        kr_pass.ballot = (kr.on && plan.mask[p] == (uint32_t)(RDX - 1) && p + 1 < plan.n_passes) ? 1 : 0;
 #define FRB_ONESWEEP(GEN, IPT_, XF)                                                                                 \
     frb_launch(radix_onesweep_kernel<KeyT, GEN, IPT_, RDX, XF>, dim3(grid), dim3(SORT_THREADS), 0, st,              \
         m, m_dev, kin, vin, kout, vout, plan.shift[p], plan.mask[p], ws + WS_HIST + p * RDX, status,                \
-        ws + WS_TICKET + p, ws + WS_ERROR, (p == plan.n_passes - 1) ? rank_out : (uint32_t*)nullptr, kr)
+        ws + WS_TICKET + p, ws + WS_ERROR, (p == plan.n_passes - 1) ? rank_out : (uint32_t*)nullptr, kr_pass)
         if (vin == nullptr) {
             if (xf) { if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL, true); else FRB_ONESWEEP(true, SORT_IPT, true); }
             else { if (small) FRB_ONESWEEP(true, SORT_IPT_SMALL, false); else FRB_ONESWEEP(true, SORT_IPT, false); }
@@ -999,7 +1018,7 @@ extern "C" int frb_depth_order_rank(int n, const uint32_t* depth_bits, uint32_t*
     uint32_t* vals_a = (uint32_t*)(w + 2 * a);
     uint32_t* ws = (uint32_t*)(w + 3 * a);
     {
-        const int rc = cluster_sort_try(n, depth_bits, KeyRange{0u, 0u, 0}, 32, order, rank, ws + WS_ERROR, st);
+        const int rc = cluster_sort_try(n, depth_bits, KeyRange{0u, 0u, 0, 0}, 32, order, rank, ws + WS_ERROR, st);
         if (rc != 1) return rc;
     }
     // 4 passes: depth_bits -> A -> B -> A -> B ; the value buffer B is `order` itself
@@ -1036,7 +1055,7 @@ extern "C" int frb_depth_order_range(int n, const uint32_t* depth_bits, float ne
     uint32_t* keys_b = (uint32_t*)(w + a);
     uint32_t* vals_a = (uint32_t*)(w + 2 * a);
     uint32_t* ws = (uint32_t*)(w + 3 * a);
-    KeyRange kr{lo, hi, 1};
+    KeyRange kr{lo, hi, 1, 0};
     bool in_b = false;
     int rc = cluster_sort_try(n, depth_bits, kr, nbits, order, rank, ws + WS_ERROR, st);
     if (rc != 1) return rc;
