@@ -209,3 +209,22 @@ def test_forward_and_backward_on_two_devices_of_one_process():
         ref = outs[1 if phase else 0]
         assert torch.equal(img, ref[2]), (idx, phase)
         assert rel(g, ref[3]) < 1e-5, (idx, phase)
+
+
+@pytest.mark.parametrize("switches", [{"FRB_FWD_BY_RECORD": "1", "FRB_BWD_HALVES": "1"}, {"FRB_GATHER": "0"},
+                                      {"FRB_CLUSTER_SORT": "1", "FRB_PDL": "0"}])
+def test_alternate_kernel_paths_pass_the_golden_tests(switches):
+    """The library keeps the slower form of four choices behind environment switches (the
+    record-by-record forward, the one-CTA-per-tile backward, the sorted record copy instead of the TMA gather, the
+    cluster-resident depth sort, plain launches).  They are read once per process, so the golden parity tests of the
+    tile renderer run again in a child process with the switches set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **switches)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q",
+                        "-k", "matches_reference_golden or tile_keys_bit_exact or batched"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
