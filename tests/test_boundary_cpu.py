@@ -156,3 +156,25 @@ def test_instance_capacity_rounding():
         assert c >= prev or m < 2000
         prev = c
     assert instance_capacity(5_820_000) == instance_capacity(5_820_321) == instance_capacity(5_900_000)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the oracle port timed on the host cores; no GPU involved): one JSON line with the
+    keys the driver reads, the reference-arm extras, and a value that is a rate.  One bounded sample step, no full
+    frame (--ref-full-budget 0), so the test stays under a minute."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-full-budget", "0"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["full_frame_measured"] is False and "workload" in line["config"]
